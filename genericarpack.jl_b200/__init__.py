@@ -1,0 +1,457 @@
+"""genericarpack.jl_b200 -- B200-native implicitly restarted Lanczos for GenericArpack.jl.
+
+Python host-side mirror of the reference's user interface for the accelerated path
+(/root/reference/src/interface.jl, src/idonow_ops.jl): ``eigs`` / ``symeigs`` / ``hermeigs`` /
+``svds`` with the same keyword names, defaults and error behaviour, driving the hand-written
+CUDA library ``libgarpack_b200.so`` through its C ABI (include/garpack_b200.h) with ctypes.
+Julia is not installed in the build image; INTEGRATION.md shows the ``ccall`` shim a Julia
+maintainer adds instead of this file.
+
+There is NO CPU fallback: importing works without a GPU (so the symbol table can be checked),
+but every compute entry point raises if the library or a CUDA device is missing.
+
+Element types (``dtype=``): ``"f64"`` (Float64), ``"c64"`` (ComplexF64), ``"dd"`` (Double64,
+numpy float64 arrays with a trailing axis of 2 = (hi, lo), the memory layout of Julia's
+DoubleFloats.Double64).
+
+The directory name contains a dot, so load it with ``__graft_entry__.load_package()`` (or
+importlib) under the module name ``genericarpack_jl_b200``.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+__all__ = [
+    "ArpackException", "ArpackSimpleOp", "ArpackNormalOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
+    "Context", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libgarpack_b200.so")
+_LIB = None
+
+GA_F64, GA_C64, GA_DD = 0, 1, 2
+_DTYPES = {"f64": GA_F64, "float64": GA_F64, "c64": GA_C64, "complex128": GA_C64, "dd": GA_DD, "double64": GA_DD,
+           GA_F64: GA_F64, GA_C64: GA_C64, GA_DD: GA_DD}
+_WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
+
+# every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = [
+    "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init",
+    "ga_set_csr", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
+    "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
+    "ga_get_stats", "ga_reset_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+]
+
+
+class ArpackException(Exception):  # src/interface.jl:125-127
+    pass
+
+
+class ga_stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in ("nopx", "nbx", "nrorth", "nitref", "nrstrt")] + [
+        (n, ctypes.c_double)
+        for n in ("taupd", "taup2", "taitr", "teigt", "tgets", "tapps", "tconv", "tmvopx", "tmvbx", "tgetv0",
+                  "titref", "trvec")
+    ]
+
+
+class ArpackStats(dict):
+    """Counters/timers of the reference's ArpackStats (src/macros.jl:173-198)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def build(force=False):
+    """Compile libgarpack_b200.so in-tree (nvcc, sm_100a)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ga_b200_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force)
+
+
+def lib():
+    """The loaded CUDA library.  Raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                "libgarpack_b200.so is missing: run `python genericarpack.jl_b200/build.py` "
+                "(there is no CPU fallback for the Lanczos hot path)")
+        L = ctypes.CDLL(_SO)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        L.ga_create.argtypes = [ctypes.POINTER(vp), i32, i64, i64, i64, i32, i32, i32, i32]
+        L.ga_destroy.argtypes = [vp]
+        L.ga_destroy.restype = None
+        L.ga_last_error.argtypes = [vp]
+        L.ga_last_error.restype = ctypes.c_char_p
+        L.ga_device_sm_count.argtypes = [vp]
+        L.ga_comm_unique_id.argtypes = [vp]
+        L.ga_comm_init.argtypes = [vp, vp]
+        L.ga_set_csr.argtypes = [vp, vp, vp, vp]
+        L.ga_set_normal_csr.argtypes = [vp, i64, i64, vp, vp, vp]
+        L.ga_opx.argtypes = [vp, vp, vp]
+        L.ga_upload_resid.argtypes = [vp, vp]
+        L.ga_download_resid.argtypes = [vp, vp]
+        L.ga_upload_v.argtypes = [vp, i32, i32, vp, i64]
+        L.ga_download_v.argtypes = [vp, i32, i32, vp, i64]
+        L.ga_getv0.argtypes = [vp, vp, i32, i32, vp]
+        L.ga_lanczos.argtypes = [vp, i32, i32, vp, i32, vp, vp]
+        L.ga_apply_shifts.argtypes = [vp, i32, i32, vp, i32, vp, vp]
+        L.ga_ritz_vectors.argtypes = [vp, i32, vp, i32, vp, i64]
+        L.ga_norm2_resid.argtypes = [vp, vp]
+        L.ga_get_stats.argtypes = [vp, ctypes.POINTER(ga_stats)]
+        L.ga_reset_stats.argtypes = [vp]
+        L.ga_symeigs.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
+        L.ga_symeigs_begin.argtypes = [vp, i32, i32, vp, i32, vp]
+        L.ga_symeigs_iterate.argtypes = [vp, i32]
+        L.ga_symeigs_end.argtypes = [vp, i32, vp, vp, vp, i64, vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _np_dtype(dt):
+    return np.complex128 if dt == GA_C64 else np.float64
+
+
+def _eshape(dt):
+    return (2,) if dt == GA_DD else ()
+
+
+class DDArr(np.ndarray):
+    """float64 ndarray whose LAST axis (length 2) is the (hi, lo) pair of a Double64."""
+
+
+def as_dd(x):
+    """Mark an array that already has the trailing (hi, lo) axis as Double64 data."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    assert x.shape[-1] == 2
+    return x.view(DDArr)
+
+
+def to_elem(x, dt):
+    """numpy array -> element layout of dtype dt.  Double64: arrays marked with as_dd() are
+    taken as (hi, lo) pairs, plain arrays are widened to (x, 0)."""
+    if dt == GA_DD:
+        if isinstance(x, DDArr):
+            return np.ascontiguousarray(x).view(DDArr)
+        x = np.asarray(x, dtype=np.float64)
+        out = np.zeros(x.shape + (2,), dtype=np.float64)
+        out[..., 0] = x
+        return out.view(DDArr)
+    return np.ascontiguousarray(np.asarray(x), dtype=_np_dtype(dt))
+
+
+def dd_to_float(x):
+    """Double64 array -> nearest float64."""
+    x = np.asarray(x)
+    return x[..., 0] + x[..., 1]
+
+
+# ------------------------------------------------------------------ operators (src/idonow_ops.jl)
+class B200ArpackOp:
+    """ArpackOp whose OP*x runs on the B200: a full (both triangles) CSR matrix.
+
+    Mirrors the required methods of ``abstract type ArpackOp`` (src/idonow_ops.jl:50-56, 360-368):
+    ``size(op)`` (problem dimension), ``arpack_mode(op)``, ``bmat(op)``, ``opx!``.
+    """
+
+    arpack_mode = 1
+    bmat = "I"
+    normal = False
+
+    def __init__(self, A, dtype=None):
+        import scipy.sparse as sp
+
+        if isinstance(A, tuple):  # (rowptr, col, val, shape)
+            rowptr, col, val, shape = A
+            self.shape = tuple(shape)
+            self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+            self.col = np.ascontiguousarray(col, dtype=np.int32)
+            data = np.asarray(val)
+        else:
+            A = sp.csr_matrix(A)
+            A.sort_indices()
+            self.shape = A.shape
+            self.rowptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+            self.col = np.ascontiguousarray(A.indices, dtype=np.int32)
+            data = A.data
+        if dtype is None:
+            dtype = GA_C64 if np.iscomplexobj(data) else GA_F64
+        self.dtype = _DTYPES[dtype]
+        self.val = to_elem(data, self.dtype)
+
+    def size(self):
+        return self.shape[0]
+
+    def is_arpack_mode_valid_for_op(self, mode):
+        return mode == 1
+
+
+class ArpackSimpleOp(B200ArpackOp):  # src/idonow_ops.jl:115-123
+    pass
+
+
+class ArpackNormalOp(B200ArpackOp):  # src/idonow_ops.jl:216-277
+    normal = True
+
+    def size(self):
+        m, n = self.shape
+        return m if m <= n else n
+
+    @property
+    def At_side(self):
+        m, n = self.shape
+        return "right" if m <= n else "left"
+
+
+# ------------------------------------------------------------------ low-level context
+class Context:
+    """One device problem instance = the arrays symeigs allocates (src/interface.jl:245-251) on
+    the GPU, plus the operator.  Thin, 1:1 over the C ABI; used by the tests and by eigs."""
+
+    def __init__(self, op, ncv, device=0, rank=0, world_size=1, n_global=None, row_offset=0):
+        L = lib()
+        self.op = op
+        self.dtype = op.dtype
+        self.ncv = int(ncv)
+        self.n = int(op.size()) if world_size == 1 else int(len(op.rowptr) - 1)
+        self.n_global = int(n_global) if n_global is not None else self.n
+        h = ctypes.c_void_p()
+        rc = L.ga_create(ctypes.byref(h), self.dtype, self.n_global, self.n, int(row_offset), self.ncv, device, rank,
+                         world_size)
+        if rc != 0 or not h:
+            raise RuntimeError("ga_create failed with code %d (is a CUDA device present? there is no CPU fallback)" % rc)
+        self.h = h
+        if op.normal:
+            m, n = op.shape
+            self._ck(L.ga_set_normal_csr(self.h, m, n, _p(op.rowptr), _p(op.col), _p(op.val)))
+        else:
+            self._ck(L.ga_set_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val)))
+        self.iseed = np.array([1, 3, 5, 7], dtype=np.int64)  # src/macros.jl:291
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ga_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            msg = lib().ga_last_error(self.h)
+            raise ArpackException("garpack_b200 error %d: %s" % (rc, msg.decode() if msg else ""))
+        return rc
+
+    def _real(self, v=0.0):
+        a = np.zeros(2)
+        a[: np.size(v)] = np.ravel(v)
+        return a
+
+    def _real_out(self, a):
+        return a.copy() if self.dtype == GA_DD else float(a[0])
+
+    @property
+    def sm_count(self):
+        return int(lib().ga_device_sm_count(self.h))
+
+    # --- data movement
+    def upload_resid(self, x):
+        x = to_elem(x, self.dtype)
+        assert x.shape[0] == self.n
+        self._ck(lib().ga_upload_resid(self.h, _p(x)))
+
+    def download_resid(self):
+        x = np.zeros((self.n,) + _eshape(self.dtype), dtype=_np_dtype(self.dtype))
+        self._ck(lib().ga_download_resid(self.h, _p(x)))
+        return x
+
+    def upload_v(self, V, col0=0):
+        """V: n x k (column j of the basis = V[:, j])."""
+        V = np.asarray(V)
+        k = V.shape[1]
+        Vt = np.ascontiguousarray(np.swapaxes(to_elem(V, self.dtype), 0, 1))  # [col][row](,2)
+        self._ck(lib().ga_upload_v(self.h, col0, k, _p(Vt), self.n))
+
+    def download_v(self, col0=0, ncols=None):
+        ncols = self.ncv - col0 if ncols is None else ncols
+        Vt = np.zeros((ncols, self.n) + _eshape(self.dtype), dtype=_np_dtype(self.dtype))
+        self._ck(lib().ga_download_v(self.h, col0, ncols, _p(Vt), self.n))
+        return np.swapaxes(Vt, 0, 1)
+
+    def opx(self, x):
+        x = to_elem(x, self.dtype)
+        y = np.zeros_like(x)
+        self._ck(lib().ga_opx(self.h, _p(x), _p(y)))
+        return y
+
+    # --- hot path
+    def getv0(self, initv=False, j=1):
+        """dgetv0! : returns (ierr, rnorm)."""
+        rn = np.zeros(2)
+        rc = lib().ga_getv0(self.h, _p(self.iseed), int(initv), int(j), _p(rn))
+        self._ck(rc, allow=(-1,))
+        return rc, self._real_out(rn)
+
+    def lanczos(self, k, np_, H, rnorm):
+        """dsaitr! : H is an (ncv, 2[, 2]) array (col 0 sub-diagonal, col 1 diagonal), updated in
+        place for rows k..k+np-1.  returns (info, rnorm)."""
+        Hf = np.ascontiguousarray(np.swapaxes(H, 0, 1))  # [col][row]
+        rn = self._real(rnorm)
+        rc = lib().ga_lanczos(self.h, int(k), int(np_), _p(Hf), H.shape[0], _p(rn), _p(self.iseed))
+        if rc < 0:
+            self._ck(rc)
+        H[...] = np.swapaxes(Hf, 0, 1)
+        return rc, self._real_out(rn)
+
+    def apply_shifts(self, kev, np_, Q, beta):
+        """device tail of dsapps!: Q is (kplusp, kplusp[, 2]) real. returns rnorm."""
+        Qf = np.ascontiguousarray(np.swapaxes(Q, 0, 1))
+        b = self._real(beta)
+        out = np.zeros(2)
+        self._ck(lib().ga_apply_shifts(self.h, int(kev), int(np_), _p(Qf), Q.shape[0], _p(b), _p(out)))
+        return self._real_out(out)
+
+    def ritz_vectors(self, nconv, Qh, want_z=True):
+        Qf = np.ascontiguousarray(np.swapaxes(Qh, 0, 1))
+        Zt = np.zeros((max(nconv, 1), self.n) + _eshape(self.dtype), dtype=_np_dtype(self.dtype)) if want_z else None
+        self._ck(lib().ga_ritz_vectors(self.h, int(nconv), _p(Qf), Qh.shape[0], _p(Zt), self.n))
+        return np.swapaxes(Zt[:nconv], 0, 1) if want_z else None
+
+    def norm2_resid(self):
+        out = np.zeros(2)
+        self._ck(lib().ga_norm2_resid(self.h, _p(out)))
+        return self._real_out(out)
+
+    def stats(self):
+        s = ga_stats()
+        lib().ga_get_stats(self.h, ctypes.byref(s))
+        return ArpackStats({n: getattr(s, n) for n, _ in ga_stats._fields_})
+
+    def reset_stats(self):
+        lib().ga_reset_stats(self.h)
+
+    # --- whole solve
+    def symeigs_begin(self, nev, which="LM", tol=0.0, maxiter=300, v0=None):
+        t = self._real(tol)
+        v = None if v0 is None else to_elem(v0, self.dtype)
+        return lib().ga_symeigs_begin(self.h, _WHICH[which], int(nev), _p(t), int(maxiter), _p(v))
+
+    def symeigs_iterate(self, max_restarts=-1):
+        return lib().ga_symeigs_iterate(self.h, int(max_restarts))
+
+    def symeigs_end(self, nev, ritzvec=True):
+        es = _eshape(self.dtype)
+        values = np.zeros((nev,) + es)
+        bounds = np.zeros((nev,) + es)
+        Zt = np.zeros((nev, self.n) + es, dtype=_np_dtype(self.dtype)) if ritzvec else None
+        iparam = np.zeros(11, dtype=np.int64)
+        rc = lib().ga_symeigs_end(self.h, int(ritzvec), _p(values), _p(bounds), _p(Zt), self.n, _p(iparam))
+        nconv = int(iparam[4])
+        vecs = np.swapaxes(Zt[:nconv], 0, 1) if ritzvec else None
+        return rc, values[:nconv], bounds[:nconv], vecs, iparam
+
+
+class ArpackEigen:
+    """Result of symeigs (src/interface.jl:173-213): iterates as (values, vectors)."""
+
+    def __init__(self, which, iparam, values, vectors, bounds, op, ctx, stats, info):
+        self.which, self.iparam, self.values, self.vectors = which, iparam, values, vectors
+        self.bounds, self.op, self.ctx, self.stats, self.info = bounds, op, ctx, stats, info
+
+    def __iter__(self):
+        yield self.values
+        yield self.vectors
+
+    @property
+    def V(self):
+        return self.ctx.download_v()
+
+    @property
+    def resid(self):
+        return self.ctx.download_resid()
+
+
+def _as_op(A, dtype=None, normal=False):
+    if isinstance(A, B200ArpackOp):
+        return A
+    return (ArpackNormalOp if normal else ArpackSimpleOp)(A, dtype=dtype)
+
+
+def symeigs(A, nev, *, which="LM", maxiter=None, ncv=None, v0=None, stats=None, tol=0.0, ritzvec=True,
+            failonmaxiter=True, dtype=None, device=0, keep_context=False):
+    """symeigs(TV, TF, op, nev; which, maxiter, ncv, v0, stats, tol, ritzvec, failonmaxiter)
+    (src/interface.jl:215-290) on the B200.  ``A``: scipy sparse matrix (full storage) or a
+    B200ArpackOp.  Returns an ArpackEigen; values ascending like the reference."""
+    op = _as_op(A, dtype)
+    n = op.size()
+    if maxiter is None:
+        maxiter = max(300, int(math.ceil(math.sqrt(n))))            # :217
+    if ncv is None:
+        ncv = min(n, max(2 * nev, 20))                              # :219
+    if not ncv <= n:
+        raise ValueError("ncv=%d must be at most n=%d" % (ncv, n))  # :231
+    if not nev < ncv:
+        raise ValueError("nev=%d must be strictly less than ncv=%d" % (nev, ncv))  # :232
+    ctx = Context(op, ncv, device=device)
+    try:
+        rc = ctx.symeigs_begin(nev, which, tol, maxiter, v0)
+        if rc != 0:
+            raise ArpackException("symmetric aupd gave error code info=%d (%s)" % (rc, (lib().ga_last_error(ctx.h) or b"").decode()))
+        rc = ctx.symeigs_iterate(-1)
+        if rc != 99:
+            raise ArpackException("symmetric aupd gave error code info=%d (%s)" % (rc, (lib().ga_last_error(ctx.h) or b"").decode()))
+        info, values, bounds, vecs, iparam = ctx.symeigs_end(nev, ritzvec)
+        if info == 1 and failonmaxiter:                             # :269-270
+            raise ArpackException("symmetric aupd hit maxiter=%d with %d < %d eigenvalues converged" % (maxiter, int(iparam[4]), nev))
+        if info not in (0, 1):                                      # :271-273, :285-287
+            raise ArpackException("symmetric aupd/eupd gave error code info=%d" % info)
+        st = ctx.stats()
+        if isinstance(stats, dict):
+            stats.update(st)
+        return ArpackEigen(which, iparam, values, vecs, bounds, op, ctx if keep_context else None, st, info)
+    finally:
+        if not keep_context:
+            ctx.close()
+
+
+def eigs(A, k, **kw):
+    """eigs(Symmetric(A) / Hermitian(A), k; kwargs...) (src/interface.jl:133-139)."""
+    return symeigs(A, k, **kw)
+
+
+def hermeigs(A, k, **kw):  # src/interface.jl:158-168
+    kw.setdefault("dtype", "c64")
+    return symeigs(A, k, **kw)
+
+
+def svds(A, k, *, which="LM", dtype=None, **kw):
+    """svds(A, k) (src/interface.jl:304-337) via ArpackNormalOp: singular values (largest first
+    for which=:LM) and right/left singular vectors.  The Lanczos iteration on A'A / AA' runs on
+    the device; turning eigenvectors into the other side's singular vectors
+    (eigenvecs_to_singvecs!, src/idonow_ops.jl:295-333) uses the device OP for A*v and a host QR --
+    SURVEY.md section 8(f) rank 1 ("next")."""
+    op = _as_op(A, dtype, normal=True)
+    arwhich = {"LM": "LM", "LA": "LM", "SM": "SA", "SA": "SA", "BE": "BE"}[which]  # :240-253
+    einfo = symeigs(op, k, which=arwhich, **kw)
+    vals = np.sqrt(np.maximum(einfo.values, 0.0))                    # :255-260
+    order = np.argsort(-vals, kind="stable") if which in ("LM", "LA") else np.argsort(vals, kind="stable")
+    S = vals[order]
+    Z = None if einfo.vectors is None else einfo.vectors[:, order]
+    return S, Z, einfo

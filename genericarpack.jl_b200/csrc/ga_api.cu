@@ -1,0 +1,463 @@
+// C ABI of the hot path (include/garpack_b200.h): context, operator upload, dgetv0!, dsaitr!,
+// the device tails of dsapps! and simple_dseupd!.  Host logic here is only what the reference
+// routine itself does around its vector operations (loop over steps, restart handling).
+#include <chrono>
+#include <cstring>
+
+#include "ga_ctx.cuh"
+
+namespace ga {
+int comm_unique_id(void* id128);
+int comm_init(ga_ctx* c, const void* id128);
+void comm_destroy(ga_ctx* c);
+void solve_free(ga_ctx* c);  // ga_host.cu
+
+int set_err(ga_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static size_t real_size(const ga_ctx* c) { return c->dtype == GA_DD ? 16 : 8; }
+
+int sync_ctl(ga_ctx* c) {
+  GA_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, c->stream));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static void host_real_to_pair(const ga_ctx* c, const double* in, double out[2]) {
+  out[0] = in[0];
+  out[1] = c->dtype == GA_DD ? in[1] : 0.0;
+}
+static void pair_to_host_real(const ga_ctx* c, const double in[2], double* out) {
+  out[0] = in[0];
+  if (c->dtype == GA_DD) out[1] = in[1];
+}
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" {
+
+int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_t row_offset, int ncv, int device,
+              int rank, int world_size) {
+  if (!out) return GA_ERR_ARG;
+  *out = nullptr;
+  if (dtype < 0 || dtype > 2 || n_global <= 0 || n_local <= 0 || ncv <= 0 || ncv > kMaxNcv || world_size < 1 ||
+      rank < 0 || rank >= world_size || row_offset < 0 || row_offset + n_local > n_global)
+    return GA_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GA_ERR_CUDA;  // no silent CPU fallback
+  ga_ctx* c = new ga_ctx();
+  c->dtype = dtype;
+  c->esize = dtype == GA_F64 ? 8 : 16;
+  c->n_global = n_global; c->n = n_local; c->row0 = row_offset;
+  c->ncv = ncv; c->ncv_pad = kMaxNcv;
+  c->device = device; c->rank = rank; c->world = world_size;
+  i64 blk = n_local;
+  if (world_size > 1) {
+    blk = (n_global + world_size - 1) / world_size;  // uniform block partition
+    i64 expect = n_global - (i64)rank * blk;
+    if (expect > blk) expect = blk;
+    if (row_offset != (i64)rank * blk || n_local != expect) { delete c; return GA_ERR_ARG; }
+  }
+  c->n_pad = (blk + kRowPad - 1) / kRowPad * kRowPad;
+#define CK(call)                                            \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) {                                \
+      fprintf(stderr, "ga_create: %s: %s\n", #call, cudaGetErrorString(e_)); \
+      ga_destroy(c);                                        \
+      return GA_ERR_CUDA;                                   \
+    }                                                       \
+  } while (0)
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  CK(cudaMalloc(&c->V, (size_t)c->n_pad * ncv * c->esize));
+  CK(cudaMalloc(&c->resid, (size_t)c->n_pad * c->esize));
+  CK(cudaMemsetAsync(c->V, 0, (size_t)c->n_pad * ncv * c->esize, c->stream));
+  CK(cudaMemsetAsync(c->resid, 0, (size_t)c->n_pad * c->esize, c->stream));
+  if (world_size > 1) {
+    c->xfull_len = c->n_pad * world_size;
+    CK(cudaMalloc(&c->xfull, (size_t)c->xfull_len * c->esize));
+    CK(cudaMemsetAsync(c->xfull, 0, (size_t)c->xfull_len * c->esize, c->stream));
+  }
+  CK(cudaMalloc(&c->ctl, sizeof(DevCtl)));
+  CK(cudaMemsetAsync(c->ctl, 0, sizeof(DevCtl), c->stream));
+  CK(cudaMallocHost(&c->ctl_host, sizeof(DevCtl)));
+  memset(c->ctl_host, 0, sizeof(DevCtl));
+  CK(cudaMalloc(&c->partial, sizeof(double2) * (size_t)kMaxCtas * kMaxSlots));
+  CK(cudaMalloc(&c->gather, sizeof(double2) * (size_t)world_size * kMaxSlots));
+  CK(cudaMalloc(&c->qdev, (size_t)kMaxNcv * kMaxNcv * 16));
+  CK(cudaStreamSynchronize(c->stream));
+#undef CK
+  *out = c;
+  return 0;
+}
+
+void ga_destroy(ga_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  solve_free(c);
+  comm_destroy(c);
+  c->A.free_all();
+  c->At.free_all();
+  cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
+  cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev);
+  if (c->ctl_host) cudaFreeHost(c->ctl_host);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* ga_last_error(const ga_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int ga_device_sm_count(const ga_ctx* c) { return c ? c->sm_count : 0; }
+
+int ga_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+int ga_comm_init(ga_ctx* c, const void* id128) { return c ? comm_init(c, id128) : GA_ERR_ARG; }
+
+// ------------------------------------------------------------------ operator
+int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void* val) {
+  if (!c || !rowptr || !col || !val) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  c->op_kind = 0;
+  int rc;
+  if (c->world == 1) {
+    rc = csr_upload(c, c->A, c->n, c->n_global, rowptr, col, val, 0);
+  } else {
+    // remap global column g (owned by rank q = g / blk) to its slot in the gathered vector
+    const i64 blk = (c->n_global + c->world - 1) / c->world;
+    const i64 nnz = rowptr[c->n] - rowptr[0];
+    std::vector<int32_t> cc((size_t)rowptr[c->n]);
+    for (i64 k = rowptr[0]; k < rowptr[0] + nnz; ++k) {
+      const i64 g = col[k], q = g / blk;
+      cc[(size_t)k] = (int32_t)(q * c->n_pad + (g - q * blk));
+    }
+    rc = csr_upload(c, c->A, c->n, c->xfull_len, rowptr, cc.data(), val, 0);
+  }
+  if (rc) return rc;
+  c->op_kind = 1;
+  return 0;
+}
+
+int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col, const void* val) {
+  if (!c || !rowptr || !col || !val || m <= 0 || n <= 0) return GA_ERR_ARG;
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "normal operator: multi-GPU sharding not implemented yet");
+  const bool left = !(m <= n);  // src/idonow_ops.jl:222-235
+  if (c->n != (left ? n : m)) return set_err(c, GA_ERR_ARG, "normal operator: context size must be min(m, n) side");
+  GA_CUDA(c, cudaSetDevice(c->device));
+  c->op_kind = 0;
+  int rc = csr_upload(c, c->A, m, n, rowptr, col, val, 0);
+  if (rc) return rc;
+  // explicit adjoint (conjugate transpose) CSR, built on the host once
+  const i64 nnz = rowptr[m];
+  std::vector<int64_t> tp((size_t)n + 1, 0);
+  for (i64 k = 0; k < nnz; ++k) tp[(size_t)col[k] + 1]++;
+  for (i64 j = 0; j < n; ++j) tp[(size_t)j + 1] += tp[(size_t)j];
+  std::vector<int32_t> tc((size_t)nnz);
+  std::vector<char> tv((size_t)nnz * c->esize);
+  std::vector<int64_t> pos(tp.begin(), tp.end() - 1);
+  for (i64 i = 0; i < m; ++i)
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const i64 d = pos[(size_t)col[k]]++;
+      tc[(size_t)d] = (int32_t)i;
+      memcpy(&tv[(size_t)d * c->esize], (const char*)val + (size_t)k * c->esize, c->esize);
+      if (c->dtype == GA_C64) {
+        double* z = (double*)&tv[(size_t)d * c->esize];
+        z[1] = -z[1];
+      }
+    }
+  rc = csr_upload(c, c->At, n, m, tp.data(), tc.data(), tv.data(), 0);
+  if (rc) return rc;
+  c->normal_m = m; c->normal_n = n; c->normal_left = left;
+  const i64 extra = left ? m : n;
+  const i64 extra_pad = (extra + kRowPad - 1) / kRowPad * kRowPad;
+  cudaFree(c->xfull);
+  c->xfull = nullptr;
+  GA_CUDA(c, cudaMalloc(&c->xfull, (size_t)extra_pad * c->esize));
+  GA_CUDA(c, cudaMemset(c->xfull, 0, (size_t)extra_pad * c->esize));
+  c->xfull_len = extra_pad;
+  c->op_kind = 2;
+  return 0;
+}
+
+int ga_opx(ga_ctx* c, const void* x_host, void* y_host) {
+  if (!c || !x_host || !y_host) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  void *dx = nullptr, *dy = nullptr;
+  GA_CUDA(c, cudaMalloc(&dx, (size_t)c->n_pad * c->esize));
+  GA_CUDA(c, cudaMalloc(&dy, (size_t)c->n_pad * c->esize));
+  GA_CUDA(c, cudaMemsetAsync(dx, 0, (size_t)c->n_pad * c->esize, c->stream));
+  GA_CUDA(c, cudaMemsetAsync(dy, 0, (size_t)c->n_pad * c->esize, c->stream));
+  GA_CUDA(c, cudaMemcpyAsync(dx, x_host, (size_t)c->n * c->esize, cudaMemcpyHostToDevice, c->stream));
+  int rc = launch_opx(c, dx, dy, false);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(y_host, dy, (size_t)c->n * c->esize, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_err(c, GA_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
+// ------------------------------------------------------------------ data movement
+int ga_upload_resid(ga_ctx* c, const void* h) {
+  if (!c || !h) return GA_ERR_ARG;
+  GA_CUDA(c, cudaMemcpyAsync(c->resid, h, (size_t)c->n * c->esize, cudaMemcpyHostToDevice, c->stream));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int ga_download_resid(ga_ctx* c, void* h) {
+  if (!c || !h) return GA_ERR_ARG;
+  GA_CUDA(c, cudaMemcpyAsync(h, c->resid, (size_t)c->n * c->esize, cudaMemcpyDeviceToHost, c->stream));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int ga_upload_v(ga_ctx* c, int col0, int ncols, const void* h, int64_t ldv) {
+  if (!c || !h || col0 < 0 || ncols < 0 || col0 + ncols > c->ncv || ldv < c->n) return GA_ERR_ARG;
+  if (ncols == 0) return 0;
+  GA_CUDA(c, cudaMemcpy2DAsync((char*)c->V + (size_t)col0 * c->n_pad * c->esize, (size_t)c->n_pad * c->esize, h,
+                               (size_t)ldv * c->esize, (size_t)c->n * c->esize, ncols, cudaMemcpyHostToDevice,
+                               c->stream));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int ga_download_v(ga_ctx* c, int col0, int ncols, void* h, int64_t ldv) {
+  if (!c || !h || col0 < 0 || ncols < 0 || col0 + ncols > c->ncv || ldv < c->n) return GA_ERR_ARG;
+  if (ncols == 0) return 0;
+  GA_CUDA(c, cudaMemcpy2DAsync(h, (size_t)ldv * c->esize, (char*)c->V + (size_t)col0 * c->n_pad * c->esize,
+                               (size_t)c->n_pad * c->esize, (size_t)c->n * c->esize, ncols, cudaMemcpyDeviceToHost,
+                               c->stream));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ dgetv0!
+static int reset_status(ga_ctx* c) {
+  static const int zeros[4] = {0, 0, 0, 0};  // status, phase, j_break, rstart_j
+  GA_CUDA(c, cudaMemcpyAsync(c->ctl, zeros, sizeof(zeros), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+static bool real_gt_717(const ga_ctx* c, const double a[2], const double b[2]) {  // a > 0.717 * b
+  if (c->dtype == GA_DD) {
+    ddbl x(a[0], a[1]), y(b[0], b[1]);
+    return x > dd_mul_d(y, 0.717);
+  }
+  return a[0] > 0.717 * b[0];
+}
+
+int ga_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm) {
+  if (!c || !iseed || !rnorm || j < 1 || j > c->ncv) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  const double t0 = now_s();
+  int rc = reset_status(c);
+  if (rc) return rc;
+  int ierr = 0;
+  if (!initv) {                                                // src/dgetv0.jl:542-553
+    i64 seed[4] = {iseed[0], iseed[1], iseed[2], iseed[3]};
+    rc = launch_lcg_fill(c, seed);
+    if (rc) return rc;
+    const i64 per = c->dtype == GA_C64 ? 2 : 1;
+    lcg_advance_seed(seed, per * c->n_global);
+    for (int i = 0; i < 4; ++i) iseed[i] = seed[i];
+  }
+  if (j == 1) {                                                // :630-637
+    rc = launch_norm_resid(c, DK_NORM);
+    if (rc) return rc;
+    rc = sync_ctl(c);
+    if (rc) return rc;
+    pair_to_host_real(c, c->ctl_host->rnorm, rnorm);
+  } else {
+    // s = V[:,1:j-1]' r ; r -= V s ; repeat while ||r|| <= 0.717 ||r_prev||, at most 5 refinements
+    rc = launch_gs(c, 0, j - 1, -1, DK_GETV0_DOT);             // :630,662 (norm + first dots)
+    if (rc) return rc;
+    int iter = 0;
+    double rnorm0[2], rn[2];
+    rc = sync_ctl(c);
+    if (rc) return rc;
+    rnorm0[0] = c->ctl_host->rnorm0[0]; rnorm0[1] = c->ctl_host->rnorm0[1];
+    while (true) {
+      rc = launch_gs(c, 1, j - 1, -1, DK_GETV0_UPD);           // :665,700 (+ next dots)
+      if (rc) return rc;
+      rc = sync_ctl(c);
+      if (rc) return rc;
+      rn[0] = c->ctl_host->rnorm[0]; rn[1] = c->ctl_host->rnorm[1];
+      if (real_gt_717(c, rn, rnorm0)) break;                   // :711
+      iter += 1;
+      if (iter <= 5) { rnorm0[0] = rn[0]; rnorm0[1] = rn[1]; } // :716-720
+      else {                                                   // :725-729
+        rc = launch_zero_resid(c);
+        if (rc) return rc;
+        rn[0] = rn[1] = 0.0;
+        GA_CUDA(c, cudaMemcpyAsync(c->ctl->rnorm, rn, sizeof(rn), cudaMemcpyHostToDevice, c->stream));
+        GA_CUDA(c, cudaStreamSynchronize(c->stream));
+        ierr = -1;
+        break;
+      }
+    }
+    pair_to_host_real(c, rn, rnorm);
+  }
+  c->stats.tgetv0 += now_s() - t0;
+  return ierr;
+}
+
+// ------------------------------------------------------------------ dsaitr!
+static int enqueue_steps(ga_ctx* c, int jfirst, int jlast) {
+  // One Lanczos step = 6 launches, no host synchronisation (1-based step j, column j-1)
+  for (int j = jfirst; j <= jlast; ++j) {
+    int rc;
+    if ((rc = launch_normalize(c, j - 1))) return rc;                       // STEP 2 (:1097-1105)
+    if ((rc = launch_opx(c, (const char*)c->V + (size_t)(j - 1) * c->n_pad * c->esize, c->resid, true))) return rc;  // STEP 3
+    if ((rc = launch_gs(c, 0, j, -1, DK_DOT))) return rc;                   // wnorm, h = V'w (:1208,1227)
+    if ((rc = launch_gs(c, 1, j, -1, DK_CGS))) return rc;                   // r = w - V h, s = V'r, ||r|| (:1240-1324)
+    if ((rc = launch_gs(c, 1, j, PH_ORTH1, DK_ORTH1))) return rc;           // DGKS round 1 (:1352-1434)
+    if ((rc = launch_gs(c, 2, j, PH_ORTH2, DK_ORTH2))) return rc;           // DGKS round 2 (:1424-1446)
+  }
+  return 0;
+}
+
+int ga_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, int64_t iseed[4]) {
+  if (!c || !H || !rnorm || !iseed || k < 0 || np < 0 || k + np > c->ncv || ldh < k + np) return GA_ERR_ARG;
+  if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
+  if (np == 0) return 0;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  const double t0 = now_s();
+  const size_t rs = real_size(c);
+  // control block: status/phase cleared, counters cleared, rnorm from the caller
+  DevCtl* hc = c->ctl_host;
+  int rc = reset_status(c);
+  if (rc) return rc;
+  {
+    int zeros[3] = {0, 0, 0};  // nrorth, nitref, zero_resid
+    GA_CUDA(c, cudaMemcpyAsync(&c->ctl->nrorth, zeros, sizeof(zeros), cudaMemcpyHostToDevice, c->stream));
+    double rn[2];
+    host_real_to_pair(c, rnorm, rn);
+    GA_CUDA(c, cudaMemcpyAsync(c->ctl->rnorm, rn, sizeof(rn), cudaMemcpyHostToDevice, c->stream));
+  }
+  int info = 0;
+  int jfirst = k + 1;
+  const int jlast = k + np;
+  while (jfirst <= jlast) {
+    if ((rc = enqueue_steps(c, jfirst, jlast))) return rc;
+    if ((rc = sync_ctl(c))) return rc;
+    c->stats.nrorth += hc->nrorth;
+    c->stats.nitref += hc->nitref;
+    if (hc->status == ST_OK) {
+      c->stats.nopx += jlast - jfirst + 1;
+      break;
+    }
+    if (hc->status == ST_NUMERIC) return set_err(c, GA_ERR_NUMERIC, "non-finite residual norm in the Lanczos step");
+    // ---- invariant subspace at step jb: restart with dgetv0 (src/dsaitr.jl:1061-1087,1497-1525)
+    const int jb = hc->j_break;
+    c->stats.nopx += jb - jfirst;
+    c->stats.nrstrt += 1;
+    int itry = 1, ierr;
+    double rn[2] = {0.0, 0.0};
+    while (true) {
+      ierr = ga_getv0(c, iseed, 0, jb, rn);
+      if (ierr < GA_ERR_CUDA + 1 && ierr != -1) return ierr;  // library error
+      if (ierr < 0) {
+        itry += 1;
+        if (itry <= 3) continue;
+        info = jb - 1;                                         // :1520
+        break;
+      }
+      break;
+    }
+    if (info > 0) { jfirst = jb; break; }
+    // resume at step jb with rstart = true (H[jb,1] = 0), counters restarted
+    int st[4] = {ST_OK, PH_DONE, 0, jb};
+    GA_CUDA(c, cudaMemcpyAsync(c->ctl, st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    int zeros[3] = {0, 0, 0};
+    GA_CUDA(c, cudaMemcpyAsync(&c->ctl->nrorth, zeros, sizeof(zeros), cudaMemcpyHostToDevice, c->stream));
+    jfirst = jb;
+  }
+  // results: H rows k..k+np-1 (both columns), rnorm
+  if ((rc = sync_ctl(c))) return rc;
+  if (hc->zero_resid) {                                         // :1442-1443 on the last step
+    if ((rc = launch_zero_resid(c))) return rc;
+    GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  const int jdone = info > 0 ? info : jlast;
+  const char* Hd = (const char*)hc->H;
+  for (int col = 0; col < 2; ++col)
+    for (int r = k; r < jdone; ++r)
+      memcpy((char*)H + ((size_t)col * ldh + r) * rs, Hd + ((size_t)col * c->ncv + r) * rs, rs);
+  pair_to_host_real(c, hc->rnorm, rnorm);
+  c->stats.taitr += now_s() - t0;
+  return info;
+}
+
+// ------------------------------------------------------------------ dsapps! tail
+int ga_apply_shifts(ga_ctx* c, int kev, int np, const void* Q, int ldq, const double* beta, double* rnorm_out) {
+  if (!c || !Q || !beta || !rnorm_out || kev < 1 || np < 0 || kev + np > c->ncv || ldq < kev + np) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  const double t0 = now_s();
+  const int kplusp = kev + np;
+  const size_t rs = real_size(c);
+  int rc = reset_status(c);
+  if (rc) return rc;
+  // Q columns 1..kev+1 -> device (ld = ncv_pad)
+  const int ncolq = kev + 1 <= kplusp ? kev + 1 : kplusp;
+  GA_CUDA(c, cudaMemcpy2DAsync(c->qdev, (size_t)c->ncv_pad * rs, Q, (size_t)ldq * rs, (size_t)kplusp * rs, ncolq,
+                               cudaMemcpyHostToDevice, c->stream));
+  const bool bpos = c->dtype == GA_DD ? (beta[0] > 0.0 || (beta[0] == 0.0 && beta[1] > 0.0)) : beta[0] > 0.0;
+  const int nout = (bpos && kev + 1 <= kplusp) ? kev + 1 : kev;       // src/dsapps.jl:813,839
+  rc = launch_vq(c, kplusp, nout, true, nullptr, beta, kev);
+  if (rc) return rc;
+  if ((rc = sync_ctl(c))) return rc;
+  pair_to_host_real(c, c->ctl_host->rnorm, rnorm_out);
+  c->stats.tapps += now_s() - t0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ dseupd! tail
+int ga_ritz_vectors(ga_ctx* c, int nconv, const void* Qh, int ldq, void* z_host, int64_t ldz) {
+  if (!c || !Qh || nconv < 0 || nconv > c->ncv || ldq < c->ncv) return GA_ERR_ARG;
+  if (z_host && ldz < c->n) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  const double t0 = now_s();
+  const size_t rs = real_size(c);
+  int rc = reset_status(c);
+  if (rc) return rc;
+  GA_CUDA(c, cudaMemcpy2DAsync(c->qdev, (size_t)c->ncv_pad * rs, Qh, (size_t)ldq * rs, (size_t)c->ncv * rs, c->ncv,
+                               cudaMemcpyHostToDevice, c->stream));
+  rc = launch_vq(c, c->ncv, c->ncv, false, nullptr, nullptr, 0);      // V <- V Qh (src/dseupd.jl:1431)
+  if (rc) return rc;
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (z_host && nconv > 0) rc = ga_download_v(c, 0, nconv, z_host, ldz);  // Z <- V[:,1:nconv] (:1434)
+  c->stats.trvec += now_s() - t0;
+  return rc;
+}
+
+int ga_norm2_resid(ga_ctx* c, double* out) {
+  if (!c || !out) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  int rc = reset_status(c);
+  if (rc) return rc;
+  if ((rc = launch_norm_resid(c, DK_NORM))) return rc;
+  if ((rc = sync_ctl(c))) return rc;
+  pair_to_host_real(c, c->ctl_host->rnorm, out);
+  return 0;
+}
+
+int ga_get_stats(const ga_ctx* c, ga_stats* out) {
+  if (!c || !out) return GA_ERR_ARG;
+  *out = c->stats;
+  return 0;
+}
+int ga_reset_stats(ga_ctx* c) {
+  if (!c) return GA_ERR_ARG;
+  c->stats = ga_stats{};
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Collective layer: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// The Lanczos data distribution is P_ARPACK's (src/dsaup2.jl:911-926): rows of A, V, resid are
+// block-partitioned, H/Q/ritz are replicated.  The exchanges the path needs are tiny:
+//   - per Gram-Schmidt sweep: the (j+3) 16-byte reduction slots of every rank are ALL-GATHERED and
+//     summed in rank order by every rank (bit-identical results on all ranks, and a correct
+//     double-double sum, which a NCCL sum of hi/lo words would not be);
+//   - per OP*x: the operand vector is all-gathered (general sparsity).
+// libnccl is opened at run time (the one torch already loaded, if any) so the library has no
+// link-time dependency and a single-GPU user never touches NCCL.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "ga_ctx.cuh"
+
+namespace ga {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  return api;
+}
+
+#define GA_NCCL(ctx, call)                                                                          \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess)                                                                          \
+      return set_err((ctx), GA_ERR_COMM, std::string(#call) + ": " + nccl().GetErrorString(r_));    \
+  } while (0)
+
+int comm_unique_id(void* id128) {
+  NcclApi& a = nccl();
+  if (!a.ok) return GA_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  return a.GetUniqueId((ncclUniqueId*)id128) == ncclSuccess ? 0 : GA_ERR_COMM;
+}
+
+int comm_init(ga_ctx* c, const void* id128) {
+  NcclApi& a = nccl();
+  if (!a.ok) return set_err(c, GA_ERR_COMM, "libnccl.so.2 could not be loaded");
+  if (c->world <= 1) return 0;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  GA_NCCL(c, a.CommInitRank(&comm, c->world, id, c->rank));
+  c->nccl_comm = (void*)comm;
+  return 0;
+}
+
+void comm_destroy(ga_ctx* c) {
+  if (c->nccl_comm) {
+    nccl().CommDestroy((ncclComm_t)c->nccl_comm);
+    c->nccl_comm = nullptr;
+  }
+}
+
+// gather[rank][0..kMaxSlots) <- every rank's ctl->red
+int comm_allgather_slots(ga_ctx* c, int nslots) {
+  (void)nslots;
+  if (c->world <= 1) return 0;
+  if (!c->nccl_comm) return set_err(c, GA_ERR_COMM, "ga_comm_init was not called");
+  GA_NCCL(c, nccl().AllGather(c->ctl->red, c->gather, (size_t)kMaxSlots * 2, ncclFloat64, (ncclComm_t)c->nccl_comm,
+                              c->stream));
+  return 0;
+}
+
+// xfull[rank * n_pad_uniform ...] <- every rank's x (all ranks use the same padded block length)
+int comm_allgather_x(ga_ctx* c, const void* x_local) {
+  if (c->world <= 1) return 0;
+  if (!c->nccl_comm) return set_err(c, GA_ERR_COMM, "ga_comm_init was not called");
+  const size_t cnt = (size_t)c->n_pad * (c->esize / 8);
+  GA_NCCL(c, nccl().AllGather(x_local, c->xfull, cnt, ncclFloat64, (ncclComm_t)c->nccl_comm, c->stream));
+  return 0;
+}
+
+}  // namespace ga

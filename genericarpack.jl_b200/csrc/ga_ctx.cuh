@@ -1,0 +1,132 @@
+// Device-side control block and the per-problem context of the B200 Lanczos library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/garpack_b200.h"
+#include "ga_types.cuh"
+
+namespace ga {
+
+constexpr int kMaxNcv = GA_MAX_NCV;
+constexpr int kRowPad = 256;  // n_local is padded to a multiple of this many rows (rows beyond n stay 0)
+constexpr int kMaxSlots = kMaxNcv + 4;  // dots + 3 norm accumulators (+1 spare)
+constexpr int kMaxCtas = 1024;
+
+// Step phases written by the on-device decision logic (dsaitr's flags, src/dsaitr.jl:1324-1447)
+enum : int { PH_DONE = 0, PH_ORTH1 = 1, PH_ORTH2 = 2 };
+enum : int { ST_OK = 0, ST_BREAKDOWN = 1, ST_NUMERIC = 2 };
+
+// What the last CTA of a reduction kernel does with the reduced slots.
+enum : int {
+  DK_NONE = 0,    // leave the reduced slots in ctl->red (multi-GPU: a later kernel decides)
+  DK_DOT = 1,     // h <- dots, wnorm <- norm                         (src/dsaitr.jl:1208,1227)
+  DK_CGS = 2,     // first CGS update done: H[j,:], rnorm, 0.717 test (:1243-1263,1304,1324)
+  DK_ORTH1 = 3,   // first DGKS correction done                        (:1364-1367,1410,1424-1434)
+  DK_ORTH2 = 4,   // second DGKS correction done                       (:1424-1446)
+  DK_GETV0_DOT = 5,  // getv0 restart: h <- dots, rnorm0 <- norm       (src/dgetv0.jl:630,662)
+  DK_GETV0_UPD = 6,  // getv0 restart: rnorm <- norm, h <- dots        (:665,700)
+  DK_NORM = 7     // rnorm <- norm                                    (src/dsaup2.jl:1414)
+};
+
+// Small control block in device memory.  Reals are stored as (hi, lo); lo = 0 for F64/C64.
+struct DevCtl {
+  int status;        // ST_*
+  int phase;         // PH_*
+  int j_break;       // 1-based step at which rnorm <= 0 was met
+  int rstart_j;      // 1-based step that follows a dgetv0 restart (H[j,1] = 0), else 0
+  int nrorth, nitref;
+  int zero_resid;    // dsaitr set resid = 0, rnorm = 0 (src/dsaitr.jl:1442-1443)
+  unsigned int ticket;  // last-block counter
+  double rnorm[2], wnorm[2], rnorm0[2], rnorm1[2];
+  double2 red[kMaxSlots];    // reduced slots of the last reduction kernel
+  double2 hbuf[kMaxNcv];     // coefficient vector h / s (element type T, padded to 16 B)
+  double2 H[2 * kMaxNcv];    // H(:,1) sub-diagonal [0..ncv), H(:,2) diagonal [ncv..2ncv), real type
+};
+
+struct CsrDev {
+  i64 nrows = 0, ncols = 0, nnz = 0;
+  int* rowptr = nullptr;    // nrows+1 (32-bit: nnz < 2^31 per rank)
+  int* col = nullptr;       // nnz, local column index into the x vector handed to the kernel
+  void* val = nullptr;      // nnz elements of T
+  int* rowblk = nullptr;    // nblk+1 row-block boundaries for the row-segment kernel
+  int nblk = 0;
+  void free_all() {
+    cudaFree(rowptr); cudaFree(col); cudaFree(val); cudaFree(rowblk);
+    rowptr = col = rowblk = nullptr; val = nullptr; nblk = 0; nnz = 0;
+  }
+};
+
+}  // namespace ga
+
+// The opaque context of include/garpack_b200.h
+struct ga_ctx {
+  int dtype = 0;
+  size_t esize = 8;          // sizeof(T)
+  ga::i64 n_global = 0, n = 0, row0 = 0, n_pad = 0;
+  int ncv = 0, ncv_pad = 0;
+  int device = 0, rank = 0, world = 1, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // big arrays (element type T), all n_pad long with zero padding rows
+  void* V = nullptr;       // n_pad x ncv, column-major, ld = n_pad
+  void* resid = nullptr;   // n_pad   (also holds w = OP v_j before orthogonalisation, like the reference)
+  void* xfull = nullptr;   // multi-GPU: gathered x of length n_global (padded); normal op: scratch of length m
+  ga::i64 xfull_len = 0;
+
+  ga::DevCtl* ctl = nullptr;       // device
+  ga::DevCtl* ctl_host = nullptr;  // pinned mirror
+  double2* partial = nullptr;      // kMaxCtas x kMaxSlots
+  double2* gather = nullptr;       // world x kMaxSlots (multi-GPU all-gather target)
+  void* qdev = nullptr;            // ncv_pad x ncv_pad reals for apply_shifts / ritz_vectors
+  void* zdev = nullptr; ga::i64 zcols = 0;
+
+  // operator
+  int op_kind = 0;  // 0 none, 1 simple CSR, 2 normal (A^H A / A A^H)
+  ga::CsrDev A, At;  // At: explicit adjoint CSR for the normal operator
+  ga::i64 normal_m = 0, normal_n = 0; bool normal_left = true;
+
+  // collectives (NCCL, loaded at run time)
+  void* nccl_comm = nullptr;
+
+  // host-side solve state for ga_symeigs_begin/iterate/end
+  void* solve = nullptr;
+
+  ga_stats stats{};
+  std::string err;
+};
+
+namespace ga {
+
+int set_err(ga_ctx* c, int code, const std::string& msg);
+#define GA_CUDA(ctx, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return ga::set_err((ctx), GA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- kernel launchers (each in its own .cu) -------------------------------------------------
+// k_lcg.cu
+int launch_lcg_fill(ga_ctx* c, const i64 iseed[4]);
+void lcg_advance_seed(i64 iseed[4], i64 nvalues);
+// k_vec.cu
+int launch_normalize(ga_ctx* c, int jcol);                 // V[:,jcol] = resid / rnorm (device rnorm)
+int launch_norm_resid(ga_ctx* c, int decide_kind);         // ||resid|| -> ctl
+int launch_zero_resid(ga_ctx* c);
+// k_spmv.cu
+int launch_opx(ga_ctx* c, const void* x, void* y, bool gated);  // y = OP x (device vectors)
+int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
+               const void* val, i64 col_shift);
+// k_gs.cu
+int launch_gs(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind);
+int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind);
+// k_update.cu
+int launch_vq(ga_ctx* c, int kplusp, int nout, bool do_resid, const void* sigma, const void* beta, int kev);
+
+int sync_ctl(ga_ctx* c);  // copy DevCtl to the pinned mirror and synchronise the stream
+
+}  // namespace ga

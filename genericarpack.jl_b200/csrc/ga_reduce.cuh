@@ -1,0 +1,156 @@
+// Device helpers shared by the reduction kernels:
+//   - NormAcc: overflow/underflow-safe, extended-precision sum of squares.  The reference's
+//     norm2 (src/arpack-blas-nrm2.jl:272-299, 355-372) accumulates in x87 80-bit registers so it
+//     neither overflows nor loses the low bits; here every square is formed exactly (TwoProd)
+//     and accumulated in double-double, and Blue's three-range scaling (the LAPACK >= 3.10
+//     dnrm2 constants) keeps huge/tiny inputs in range.
+//   - slot reductions: every partial result is a 16-byte "slot" (hi,lo) or (re,im); CTAs write
+//     their slots to a [cta][slot] array and the last CTA to finish sums them in a fixed order,
+//     so results are bit-reproducible run to run.
+#pragma once
+#include "ga_ctx.cuh"
+
+namespace ga {
+
+// Blue's scaling constants for IEEE double (LAPACK la_constants: dtsml, dtbig, dssml, dsbig)
+#define GA_TSML 1.4916681462400413e-154   /* 2^-511 */
+#define GA_TBIG 1.9979190722022350e+146   /* 2^486  */
+#define GA_SSML 4.4989137945431964e+161   /* 2^537  */
+#define GA_SBIG 1.1113793747425387e-162   /* 2^-538 */
+
+struct NormAcc {
+  ddbl med, big, sml;
+  __device__ __forceinline__ void init() { med = ddbl(0.0, 0.0); big = ddbl(0.0, 0.0); sml = ddbl(0.0, 0.0); }
+  __device__ __forceinline__ void add(double x) {
+    double ax = fabs(x);
+    if (ax > GA_TBIG) {
+      double s = ax * GA_SBIG, p, e;
+      two_prod(s, s, p, e);
+      big = dd_add(big, ddbl(p, e));
+    } else if (ax < GA_TSML) {
+      if (ax != 0.0) {
+        double s = ax * GA_SSML, p, e;
+        two_prod(s, s, p, e);
+        sml = dd_add(sml, ddbl(p, e));
+      }
+    } else {
+      double p, e;
+      two_prod(x, x, p, e);
+      // sloppy add is enough here: all terms are non-negative
+      double sh, sl;
+      two_sum(med.hi, p, sh, sl);
+      sl += med.lo + e;
+      fast_two_sum(sh, sl, med.hi, med.lo);
+    }
+  }
+  __device__ __forceinline__ void add(cdbl x) { add(x.re); add(x.im); }
+  __device__ __forceinline__ void add(ddbl x) {
+    double ax = fabs(x.hi);
+    if (ax > GA_TBIG) {
+      ddbl s(x.hi * GA_SBIG, x.lo * GA_SBIG);
+      big = dd_add(big, dd_mul(s, s));
+    } else if (ax < GA_TSML) {
+      if (ax != 0.0) {
+        ddbl s(x.hi * GA_SSML, x.lo * GA_SSML);
+        sml = dd_add(sml, dd_mul(s, s));
+      }
+    } else {
+      med = dd_add(med, dd_mul(x, x));
+    }
+  }
+};
+
+// sqrt of the combined accumulators, in double-double (LAPACK dnrm2 combination rule)
+__device__ __forceinline__ ddbl norm_finalize(ddbl med, ddbl big, ddbl sml) {
+  if (big.hi > 0.0) {
+    if (med.hi > 0.0 || med.hi != med.hi) {
+      ddbl m(med.hi * GA_SBIG, med.lo * GA_SBIG);
+      m = ddbl(m.hi * GA_SBIG, m.lo * GA_SBIG);
+      big = dd_add(big, m);
+    }
+    ddbl r = dd_sqrt(big);
+    const double inv = 1.0 / GA_SBIG;
+    return ddbl(r.hi * inv, r.lo * inv);
+  } else if (sml.hi > 0.0) {
+    if (med.hi > 0.0 || med.hi != med.hi) {
+      ddbl a = dd_sqrt(med);
+      ddbl b = dd_sqrt(sml);
+      const double inv = 1.0 / GA_SSML;
+      b = ddbl(b.hi * inv, b.lo * inv);
+      ddbl ymin = a < b ? a : b, ymax = a < b ? b : a;
+      ddbl q = dd_div(ymin, ymax);
+      ddbl s = dd_mul(dd_mul(ymax, ymax), dd_add_d(dd_mul(q, q), 1.0));
+      return dd_sqrt(s);
+    }
+    ddbl r = dd_sqrt(sml);
+    const double inv = 1.0 / GA_SSML;
+    return ddbl(r.hi * inv, r.lo * inv);
+  }
+  return dd_sqrt(med);
+}
+
+// ---- warp shuffles of 16-byte slots ------------------------------------------------------------
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ ddbl warp_sum_dd(ddbl v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    ddbl o(shfl_xor_d(v.hi, m), shfl_xor_d(v.lo, m));
+    v = dd_add(v, o);
+  }
+  return v;
+}
+__device__ __forceinline__ double2 warp_sum_slot(double v) {  // compensated: returns (hi,lo)
+  ddbl r = warp_sum_dd(ddbl(v, 0.0));
+  return make_double2(r.hi, r.lo);
+}
+__device__ __forceinline__ double2 warp_sum_slot(ddbl v) {
+  ddbl r = warp_sum_dd(v);
+  return make_double2(r.hi, r.lo);
+}
+__device__ __forceinline__ double2 warp_sum_slot(cdbl v) {  // (re, im), plain tree
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    v.re += shfl_xor_d(v.re, m);
+    v.im += shfl_xor_d(v.im, m);
+  }
+  return make_double2(v.re, v.im);
+}
+
+// slot kinds: pair = (hi,lo) compensated sum; cplx = independent (re,im)
+template <bool CPLX>
+__device__ __forceinline__ double2 slot_add(double2 a, double2 b) {
+  if (CPLX) return make_double2(a.x + b.x, a.y + b.y);
+  ddbl r = dd_add(ddbl(a.x, a.y), ddbl(b.x, b.y));
+  return make_double2(r.hi, r.lo);
+}
+
+// Called by all threads of a CTA after it wrote partial[blockIdx.x][0..nslots).  Returns true in
+// the last CTA to arrive (after summing all CTAs' slots into ctl->red in a fixed order).
+// dot slots [0, ndot) use CPLX_DOT semantics, the remaining slots are (hi,lo) pairs.
+template <bool CPLX_DOT>
+__device__ __forceinline__ bool last_block_reduce(DevCtl* ctl, const double2* partial, int ndot, int nslots,
+                                                  int* sh_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(&ctl->ticket, 1u);
+    *sh_flag = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!*sh_flag) return false;
+  __threadfence();
+  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
+    double2 acc = make_double2(0.0, 0.0);
+    const bool cplx = CPLX_DOT && s < ndot;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+      double2 v = __ldcg(&partial[(size_t)b * kMaxSlots + s]);
+      acc = cplx ? slot_add<true>(acc, v) : slot_add<false>(acc, v);
+    }
+    ctl->red[s] = acc;
+  }
+  if (threadIdx.x == 0) ctl->ticket = 0u;
+  __syncthreads();
+  return true;
+}
+
+}  // namespace ga

@@ -1,0 +1,255 @@
+// Fused tall-skinny Gram-Schmidt sweeps of the Lanczos step (dsaitr! steps 4-5).
+//
+// Reference (src/dsaitr.jl):  h = V_j' w (:1227, dgemv 'T');  r = w - V_j h (:1240, dgemv 'N');
+// DGKS: s = V_j' r (:1352); r -= V_j s (:1363); each followed by a norm2 pass (:1208,1304,1410).
+// That is 2 sweeps of V[:,1:j] per Gram-Schmidt round plus ~6 n-vector passes.
+//
+// Here one persistent kernel streams V[:,1:j] through shared memory ONCE per sweep with TMA bulk
+// copies (one 1 KiB column segment per copy, multi-stage mbarrier pipeline, dedicated producer
+// warp) and does, per row tile resident in shared memory:
+//     MODE 0:  s += V' w,  ||w||^2                                   (first dgemv 'T' + norm)
+//     MODE 1:  r = w - V h  (written once),  s += V' r,  ||r||^2    (dgemv 'N' + the NEXT dgemv 'T' + norm)
+//     MODE 2:  r = w - V h,  ||r||^2                                (last correction)
+// MODE 1 is what removes a whole sweep: the DGKS coefficients s = V' r are row-local once r is
+// known for the tile, so they are accumulated while the tile is still in shared memory.  The
+// arithmetic (classical Gram-Schmidt with DGKS correction) is unchanged.
+//
+// Thread layout: R rows per tile (R * sizeof(T) = 1 KiB), TG thread groups; thread (row, g) owns
+// row `row` of the tile and columns c = g, g+TG, ...  -> NC = 64/TG register accumulators.
+// Groups exchange their partial row sums through shared memory behind a named barrier that
+// only spans the TG warps sharing 32 rows.  Reductions are fixed-order (bit-reproducible).
+#include "ga_decide.cuh"
+#include "ga_tma.cuh"
+
+namespace ga {
+
+template <class T> struct GsCfg {
+  static constexpr int R = 1024 / (int)sizeof(T);     // rows per tile: 128 (F64) / 64 (C64, DD)
+  static constexpr int TG = (sizeof(T) == 8) ? 4 : 8; // thread groups
+  static constexpr int NC = kMaxNcv / TG;             // columns per thread (register accumulators)
+  static constexpr int SLICES = R / 32;
+  static constexpr int CWARPS = SLICES * TG;          // consumer warps
+  static constexpr int THREADS = CWARPS * 32 + 32;    // + producer warp
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int FIXED_SMEM = kMaxNcv * 16 /*hs*/ + 2 * TG * 1024 /*pr*/ + CWARPS * (NC + 3) * 16 /*red*/ +
+                                    2 * MAX_STAGES * 8 /*mbar*/ + 64;
+};
+
+template <class T, int MODE>
+__global__ void __launch_bounds__(GsCfg<T>::THREADS, 1)
+k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
+     int nstages, int gate_phase, int decide_kind, int ncv, int single_rank) {
+  typedef GsCfg<T> C;
+  constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS;
+  constexpr bool CPLX = Elem<T>::is_complex;
+
+  if (ctl->status != ST_OK) return;
+  if (gate_phase >= 0 && ctl->phase != gate_phase) return;
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t stage_bytes = (uint32_t)(j + 1) * 1024u;
+  unsigned char* p = smem + (size_t)nstages * stage_bytes;
+  T* hs = reinterpret_cast<T*>(p);                  p += kMaxNcv * 16;
+  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * 1024;
+  double2* redw = reinterpret_cast<double2*>(p);    p += CWARPS * (NC + 3) * 16;
+  uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += C::MAX_STAGES * 8;
+  uint64_t* empty = reinterpret_cast<uint64_t*>(p); p += C::MAX_STAGES * 8;
+  int* sh_flag = reinterpret_cast<int*>(p);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CWARPS); }
+    fence_mbar_init();
+  }
+  if (MODE != 0) {
+    const T* hb = hbuf_ptr<T>(ctl);
+    for (int c = tid; c < j; c += blockDim.x) hs[c] = hb[c];
+  }
+  __syncthreads();
+
+  T acc[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) acc[i] = Elem<T>::zero();
+  NormAcc nacc;
+  nacc.init();
+
+  if (warp == CWARPS) {
+    // ---------------- producer warp: TMA bulk copies of the (j columns + w) x R tile
+    int it = 0;
+    for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], stage_bytes);
+      __syncwarp();
+      unsigned char* st = smem + (size_t)s * stage_bytes;
+      const i64 row0 = t * R;
+      for (int c = lane; c <= j; c += 32) {
+        const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (w + row0);
+        bulk_g2s(st + (size_t)c * 1024, src, 1024u, &full[s]);
+      }
+    }
+  } else {
+    // ---------------- consumers
+    const int slice = warp % SLICES, g = warp / SLICES, row = slice * 32 + lane;
+    int it = 0;
+    for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      mbar_wait(&full[s], ph);
+      const T* tile = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
+      T rr = tile[(size_t)j * R + row];  // w
+      if (MODE != 0) {
+        T p0 = Elem<T>::zero(), p1 = Elem<T>::zero();
+#pragma unroll
+        for (int i = 0; i < NC; i += 2) {
+          const int c0 = g + TG * i, c1 = c0 + TG;
+          if (c0 < j) Elem<T>::sub_mul(p0, tile[(size_t)c0 * R + row], hs[c0]);
+          if (c1 < j) Elem<T>::sub_mul(p1, tile[(size_t)c1 * R + row], hs[c1]);
+        }
+        Elem<T>::add(p0, p1);
+        T* prb = pr + (size_t)(it & 1) * TG * R;
+        prb[g * R + row] = p0;
+        named_bar_sync(1 + slice, TG * 32);
+#pragma unroll
+        for (int g2 = 0; g2 < TG; ++g2) Elem<T>::add(rr, prb[g2 * R + row]);
+        if (g == 0) r[t * R + row] = rr;
+      }
+      if (MODE != 2) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int c = g + TG * i;
+          if (c < j) Elem<T>::acc_conj_mul(acc[i], tile[(size_t)c * R + row], rr);
+        }
+      }
+      if (g == 0) nacc.add(rr);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // warp-level reduction of this warp's accumulators
+    if (MODE != 2) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        double2 sl = warp_sum_slot(acc[i]);
+        if (lane == 0) redw[warp * (NC + 3) + i] = sl;
+      }
+    }
+    if (g == 0) {
+      ddbl m = warp_sum_dd(nacc.med), b = warp_sum_dd(nacc.big), sm = warp_sum_dd(nacc.sml);
+      if (lane == 0) {
+        redw[warp * (NC + 3) + NC + 0] = make_double2(m.hi, m.lo);
+        redw[warp * (NC + 3) + NC + 1] = make_double2(b.hi, b.lo);
+        redw[warp * (NC + 3) + NC + 2] = make_double2(sm.hi, sm.lo);
+      }
+    }
+  }
+  __syncthreads();
+  // CTA partials -> global
+  const int nslots = j + 3;
+  for (int s = tid; s < nslots; s += blockDim.x) {
+    double2 a = make_double2(0.0, 0.0);
+    if (s < j) {
+      if (MODE != 2) {
+        const int g = s % TG, i = s / TG;
+        for (int sl = 0; sl < SLICES; ++sl) {
+          double2 v = redw[(g * SLICES + sl) * (NC + 3) + i];
+          a = CPLX ? slot_add<true>(a, v) : slot_add<false>(a, v);
+        }
+      }
+    } else {
+      const int k = s - j;
+      for (int sl = 0; sl < SLICES; ++sl) a = slot_add<false>(a, redw[sl * (NC + 3) + NC + k]);
+    }
+    partial[(size_t)blockIdx.x * kMaxSlots + s] = a;
+  }
+  if (last_block_reduce<CPLX>(ctl, partial, j, nslots, sh_flag)) {
+    if (single_rank) gs_decide<T>(ctl, ctl->red, j, ncv, decide_kind);
+  }
+}
+
+// One-CTA kernel that sums the gathered per-rank slots and runs the decision logic (multi GPU).
+template <class T>
+__global__ void k_decide(DevCtl* ctl, const double2* gathered, int world, int j, int ncv, int gate_phase,
+                         int decide_kind) {
+  if (ctl->status != ST_OK) return;
+  if (gate_phase >= 0 && ctl->phase != gate_phase) return;
+  constexpr bool CPLX = Elem<T>::is_complex;
+  __shared__ double2 red[kMaxSlots];
+  const int nslots = j + 3;
+  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
+    double2 a = make_double2(0.0, 0.0);
+    for (int rk = 0; rk < world; ++rk) {
+      double2 v = gathered[(size_t)rk * kMaxSlots + s];
+      a = (CPLX && s < j) ? slot_add<true>(a, v) : slot_add<false>(a, v);
+    }
+    red[s] = a;
+  }
+  __syncthreads();
+  gs_decide<T>(ctl, red, j, ncv, decide_kind);
+}
+
+template <class T, int MODE>
+static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
+  typedef GsCfg<T> C;
+  const i64 ntiles = c->n_pad / C::R;
+  const size_t stage_bytes = (size_t)(j + 1) * 1024;
+  const size_t budget = 227 * 1024 - C::FIXED_SMEM;
+  int nstages = (int)(budget / stage_bytes);
+  if (nstages > C::MAX_STAGES) nstages = C::MAX_STAGES;
+  if (nstages < 2) return set_err(c, GA_ERR_ARG, "gs: too many columns for the shared-memory pipeline");
+  const size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
+  if (grid > kMaxCtas) grid = kMaxCtas;
+  const T* V = (const T*)c->V;
+  T* r = (T*)c->resid;
+  k_gs<T, MODE><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
+                                                      gate_phase, c->world == 1 ? decide_kind : DK_NONE, c->ncv,
+                                                      c->world == 1 ? 1 : 0);
+  GA_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+template <class T>
+static int launch_gs_mode(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind) {
+  switch (mode) {
+    case 0: return launch_gs_t<T, 0>(c, j, gate_phase, decide_kind);
+    case 1: return launch_gs_t<T, 1>(c, j, gate_phase, decide_kind);
+    default: return launch_gs_t<T, 2>(c, j, gate_phase, decide_kind);
+  }
+}
+
+// mode: 0 dot, 1 update+dot, 2 update.  j = number of basis columns.  The vector being
+// orthogonalised is c->resid (in place).  gate_phase >= 0: run only if ctl->phase == gate_phase.
+int launch_gs(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind) {
+  if (j < 0 || j > kMaxNcv) return set_err(c, GA_ERR_ARG, "gs: j out of range");
+  int rc;
+  switch (c->dtype) {
+    case GA_F64: rc = launch_gs_mode<double>(c, mode, j, gate_phase, decide_kind); break;
+    case GA_C64: rc = launch_gs_mode<cdbl>(c, mode, j, gate_phase, decide_kind); break;
+    default: rc = launch_gs_mode<ddbl>(c, mode, j, gate_phase, decide_kind); break;
+  }
+  if (rc) return rc;
+  if (c->world > 1) return launch_decide(c, j, gate_phase, decide_kind);
+  return 0;
+}
+
+int comm_allgather_slots(ga_ctx* c, int nslots);  // ga_comm.cu
+
+int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind) {
+  int rc = comm_allgather_slots(c, j + 3);
+  if (rc) return rc;
+  switch (c->dtype) {
+    case GA_F64: k_decide<double><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
+    case GA_C64: k_decide<cdbl><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
+    default: k_decide<ddbl><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
+  }
+  GA_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ga

@@ -1,0 +1,138 @@
+// n-vector kernels of the Lanczos step: v_j = r / rnorm (dsaitr step 2), ||resid|| and zero fill.
+#include "ga_decide.cuh"
+
+namespace ga {
+
+// ---- dsaitr! STEP 2 (src/dsaitr.jl:1061-1105): v_j = resid * (1/rnorm), or the dlascl-safe
+// rescaling of _scale_from_to (src/arpack-blas.jl:25-72) when rnorm < floatmin.  Also the
+// step's entry test: rnorm <= 0 means an invariant subspace was found; the device flags it and
+// every later kernel of this call returns immediately so the host can run the dgetv0 restart.
+template <class TR>
+__device__ __forceinline__ void lascl_factor(TR cfrom, TR cto, TR& mul, TR& cfromc, TR& ctoc, bool& done) {
+  const TR smlnum = Real<TR>::floatmin();
+  const TR bignum = Real<TR>::from(1.0) / smlnum;
+  cfromc = cfrom; ctoc = cto;
+  const TR cfrom1 = cfromc * smlnum;
+  if (cfrom1 == cfromc) { mul = ctoc / cfromc; done = true; }
+  else {
+    const TR cto1 = ctoc / bignum;
+    if (cto1 == ctoc) { mul = ctoc; done = true; cfromc = Real<TR>::from(1.0); }
+    else if (r_abs(cfrom1) > r_abs(ctoc) && ctoc != Real<TR>::from(0.0)) { mul = smlnum; done = false; cfromc = cfrom1; }
+    else if (r_abs(cto1) > r_abs(cfromc)) { mul = bignum; done = false; ctoc = cto1; }
+    else { mul = ctoc / cfromc; done = true; }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_normalize(T* __restrict__ vj, const T* __restrict__ resid, i64 n,
+                                                   DevCtl* ctl, int jstep) {
+  typedef typename Elem<T>::real_t TR;
+  if (ctl->status != ST_OK) return;
+  const TR rnorm = load_real<TR>(ctl->rnorm);
+  if (!(rnorm > Real<TR>::from(0.0))) {  // src/dsaitr.jl:1061
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      ctl->j_break = jstep;
+      ctl->status = r_isnan(rnorm) ? ST_NUMERIC : ST_BREAKDOWN;
+    }
+    return;
+  }
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  if (rnorm >= Real<TR>::floatmin()) {
+    const TR temp1 = Real<TR>::from(1.0) / rnorm;  // :1099
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      vj[i] = Elem<T>::mul_real(resid[i], temp1);
+  } else {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      T x = resid[i];
+      TR mul, cf, ct; bool done;
+      lascl_factor<TR>(rnorm, Real<TR>::from(1.0), mul, cf, ct, done);
+      x = Elem<T>::mul_real(x, mul);
+      int guard = 0;
+      while (!done && guard++ < 8) {
+        TR f = cf, t = ct;
+        lascl_factor<TR>(f, t, mul, cf, ct, done);
+        x = Elem<T>::mul_real(x, mul);
+      }
+      vj[i] = x;
+    }
+  }
+}
+
+int launch_normalize(ga_ctx* c, int jcol) {
+  const int threads = 256;
+  i64 blocks = (c->n + threads - 1) / threads;
+  const i64 maxb = (i64)c->sm_count * 8;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  switch (c->dtype) {
+    case GA_F64:
+      k_normalize<double><<<(int)blocks, threads, 0, c->stream>>>((double*)c->V + (size_t)jcol * c->n_pad,
+                                                                 (const double*)c->resid, c->n, c->ctl, jcol + 1);
+      break;
+    case GA_C64:
+      k_normalize<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)c->V + (size_t)jcol * c->n_pad,
+                                                               (const cdbl*)c->resid, c->n, c->ctl, jcol + 1);
+      break;
+    default:
+      k_normalize<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->V + (size_t)jcol * c->n_pad,
+                                                               (const ddbl*)c->resid, c->n, c->ctl, jcol + 1);
+      break;
+  }
+  GA_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+// ---- ||resid||_2 (norm2(TR, resid): src/arpack-blas-nrm2.jl:355-372; call sites
+// src/dsaup2.jl:1414, src/dgetv0.jl:630) ------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_norm(const T* __restrict__ x, i64 n, DevCtl* ctl, double2* partial,
+                                              int decide_kind, int ncv, int single_rank) {
+  if (ctl->status != ST_OK && ctl->status != ST_BREAKDOWN) return;
+  __shared__ double2 sw[8 * 3];
+  __shared__ int sh_flag;
+  NormAcc a;
+  a.init();
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a.add(x[i]);
+  ddbl m = warp_sum_dd(a.med), b = warp_sum_dd(a.big), s = warp_sum_dd(a.sml);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sw[warp * 3 + 0] = make_double2(m.hi, m.lo);
+    sw[warp * 3 + 1] = make_double2(b.hi, b.lo);
+    sw[warp * 3 + 2] = make_double2(s.hi, s.lo);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc = slot_add<false>(acc, sw[w * 3 + threadIdx.x]);
+    partial[(size_t)blockIdx.x * kMaxSlots + threadIdx.x] = acc;
+  }
+  if (last_block_reduce<false>(ctl, partial, 0, 3, &sh_flag)) {
+    if (single_rank) gs_decide<T>(ctl, ctl->red, 0, ncv, decide_kind);
+  }
+}
+
+int launch_norm_resid(ga_ctx* c, int decide_kind) {
+  const int threads = 256;
+  i64 blocks = (c->n + threads * 4 - 1) / (threads * 4);
+  const i64 maxb = (i64)c->sm_count * 4;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  const int single = c->world == 1 ? 1 : 0;
+  const int dk = single ? decide_kind : DK_NONE;
+  switch (c->dtype) {
+    case GA_F64: k_norm<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
+    case GA_C64: k_norm<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
+    default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
+  }
+  GA_CUDA(c, cudaGetLastError());
+  if (!single) return launch_decide(c, 0, -1, decide_kind);
+  return 0;
+}
+
+int launch_zero_resid(ga_ctx* c) {
+  GA_CUDA(c, cudaMemsetAsync(c->resid, 0, (size_t)c->n_pad * c->esize, c->stream));
+  return 0;
+}
+
+}  // namespace ga

@@ -1,0 +1,146 @@
+/*
+ * garpack_b200.h -- C ABI of the B200 (sm_100a) implicitly-restarted-Lanczos library.
+ *
+ * This is the drop-in boundary for GenericArpack.jl's hot path.  Every entry point replaces
+ * one reference routine (citations: /root/reference/<file>:<lines>, GenericArpack.jl v0.2.1)
+ * and is what the reference's Julia side binds with `ccall` from a method specialised on a
+ * `B200ArpackState <: AbstractArpackState` / `B200ArpackOp <: ArpackOp` (INTEGRATION.md shows
+ * the exact stubs).  Plain pointers and sizes only; no C++/torch types; no exceptions cross the
+ * boundary.  All state lives in the opaque context (the reference keeps all formerly-static
+ * Fortran state in ArpackState, src/macros.jl:358-366), so independent contexts are re-entrant.
+ *
+ * Conventions
+ *   - return value: 0 = ok; >0 informational (ARPACK `info`); <0 error.  -1..-13 and -9999
+ *     mirror dsaupd's codes (src/dsaupd.jl:885-917); GA_ERR_* are library errors.
+ *   - element types: GA_F64 (double), GA_C64 (re,im pairs), GA_DD (hi,lo pairs = Julia Double64).
+ *   - "real" scalars (rnorm, H, Q, tol, shifts, Ritz values) are `double` for GA_F64/GA_C64 and
+ *     (hi,lo) pairs of double for GA_DD; pointers to them are `void*`/`double*` documented per call.
+ *   - host pointers are caller-owned; the library never keeps them after the call returns.
+ *   - matrices are column-major (Julia layout) with explicit leading dimensions.
+ */
+#ifndef GARPACK_B200_H
+#define GARPACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ga_ctx ga_ctx;
+
+enum { GA_F64 = 0, GA_C64 = 1, GA_DD = 2 };
+enum { GA_LM = 0, GA_SM = 1, GA_LA = 2, GA_SA = 3, GA_BE = 4 }; /* which::Symbol */
+
+enum {
+  GA_ERR_CUDA = -100,      /* a CUDA runtime call failed; see ga_last_error */
+  GA_ERR_ARG = -101,       /* invalid argument (sizes, NULL, unsupported ncv) */
+  GA_ERR_NOOP = -102,      /* no operator uploaded */
+  GA_ERR_COMM = -103,      /* collective layer failure */
+  GA_ERR_NUMERIC = -104,   /* non-finite value met on the device */
+  GA_ERR_TRIDIAG = -8      /* dsaupd's code for a failed tridiagonal eigen-solve */
+};
+
+#define GA_MAX_NCV 64
+
+/* Counters and timers of ArpackStats (src/macros.jl:173-198).  Times are seconds measured
+ * with CUDA events / host clocks inside the library. */
+typedef struct ga_stats {
+  int64_t nopx, nbx, nrorth, nitref, nrstrt;
+  double taupd, taup2, taitr, teigt, tgets, tapps, tconv, tmvopx, tmvbx, tgetv0, titref, trvec;
+} ga_stats;
+
+/* ---- context ------------------------------------------------------------------------------
+ * One context = one eigenproblem's device state on one GPU: V (n_local x ncv), resid, scratch,
+ * the operator.  Replaces the allocations of symeigs (src/interface.jl:245-251).
+ *   n_local   rows owned by this rank;   row_offset  first global row;   n_global  total rows.
+ *   Single GPU: n_local = n_global, row_offset = 0, rank 0 of 1.
+ */
+int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_t row_offset, int ncv,
+              int device, int rank, int world_size);
+void ga_destroy(ga_ctx* ctx);
+const char* ga_last_error(const ga_ctx* ctx);
+int ga_device_sm_count(const ga_ctx* ctx);
+
+/* Multi-GPU plumbing.  The caller owns rendezvous (torch.distributed / MPI / Julia Distributed):
+ * rank 0 calls ga_comm_unique_id, broadcasts the 128 bytes, every rank calls ga_comm_init.
+ * Collectives are then issued by the library on its own stream (NCCL over NVLink 5 / NVSwitch). */
+int ga_comm_unique_id(void* id128);
+int ga_comm_init(ga_ctx* ctx, const void* id128);
+
+/* ---- operator (OP*x of dsaitr step 3: src/dsaitr.jl:1120-1133 -> opx!, src/idonow_ops.jl:74-76)
+ * ga_set_csr: ArpackSimpleOp(A) (src/idonow_ops.jl:115-123).  Full (both triangles) CSR of the
+ * n_local rows owned by this rank, global column indices, 0-based.  val has the ctx dtype.
+ * ga_set_normal_csr: ArpackNormalOp(A) for svds (src/idonow_ops.jl:216-277): A is m x n CSR,
+ * OP = A^H A (m > n, problem size n) or A A^H (m <= n, problem size m). */
+int ga_set_csr(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col, const void* val);
+int ga_set_normal_csr(ga_ctx* ctx, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
+                      const void* val);
+/* y = OP*x on host vectors of the problem size (test / svds post-processing helper). */
+int ga_opx(ga_ctx* ctx, const void* x_host, void* y_host);
+
+/* ---- data movement (copyto!(resid, v0) src/interface.jl:260; results of ArpackEigen) --------- */
+int ga_upload_resid(ga_ctx* ctx, const void* resid_host);
+int ga_download_resid(ga_ctx* ctx, void* resid_host);
+int ga_upload_v(ga_ctx* ctx, int col0, int ncols, const void* v_host, int64_t ldv);
+int ga_download_v(ga_ctx* ctx, int col0, int ncols, void* v_host, int64_t ldv);
+
+/* ---- dgetv0! (src/dgetv0.jl:504-753) ---------------------------------------------------------
+ * iseed[4]: dlarnv seed limbs, in/out (src/macros.jl:291).  initv != 0: resid already holds v0.
+ * j: 1-based column being generated; j > 1 orthogonalises against V[:,1:j-1] with <= 5
+ * refinements.  rnorm out (1 or 2 doubles).  Returns ierr: 0 or -1 (src/dgetv0.jl:725-729). */
+int ga_getv0(ga_ctx* ctx, int64_t iseed[4], int initv, int j, double* rnorm);
+
+/* ---- dsaitr! (src/dsaitr.jl:962-1535), mode 1, bmat = :I --------------------------------------
+ * Extends a k-step Lanczos factorisation by np steps entirely on the device: per step
+ * v_j = r/rnorm, w = OP v_j, classical Gram-Schmidt + DGKS refinement with the 0.717 tests
+ * decided on the device, overflow-safe norms; no host round trip inside the call.
+ * H: host (ldh x 2) reals, column 0 = sub-diagonal, column 1 = diagonal; rows k..k+np-1 written.
+ * rnorm in/out.  iseed in/out (used only if an invariant subspace forces a restart).
+ * Returns info: 0, or j-1 = size of the invariant subspace found (src/dsaitr.jl:1515-1523). */
+int ga_lanczos(ga_ctx* ctx, int k, int np, void* H, int ldh, double* rnorm, int64_t iseed[4]);
+
+/* ---- device tail of dsapps! (src/dsapps.jl:813-854) + dsaup2's residual norm (src/dsaup2.jl:1397-1414)
+ * Q: host (ldq x kplusp) reals from the host bulge chase.  beta = H[kev+1,1] after the chase.
+ * V[:,1:kev] <- V[:,1:kplusp] Q[:,1:kev]; if beta > 0: V[:,kev+1] <- V Q[:,kev+1];
+ * resid <- Q[kplusp,kev] resid + beta V[:,kev+1]; rnorm_out = ||resid||. */
+int ga_apply_shifts(ga_ctx* ctx, int kev, int np, const void* Q, int ldq, const double* beta,
+                    double* rnorm_out);
+
+/* ---- device tail of simple_dseupd! (src/dseupd.jl:1413-1435) ------------------------------------
+ * Qh: host (ldq x ncv) reals = H(1)...H(nconv) accumulated on the host (the product the
+ * reference applies reflector by reflector with dorm2r!).  V <- V Qh (all ncv columns, like the
+ * reference leaves V), Z <- V[:,1:nconv] copied to z_host (ldz >= n_local) when z_host != NULL. */
+int ga_ritz_vectors(ga_ctx* ctx, int nconv, const void* Qh, int ldq, void* z_host, int64_t ldz);
+
+/* ---- small device services used by tests and by the Julia shim ---------------------------------
+ * ga_norm2: norm2(TR, resid) (src/arpack-blas-nrm2.jl:355-372) of the device resid. */
+int ga_norm2_resid(ga_ctx* ctx, double* out);
+int ga_get_stats(const ga_ctx* ctx, ga_stats* out);
+int ga_reset_stats(ga_ctx* ctx);
+
+/* ---- whole solve: symeigs (src/interface.jl:215-290) = dsaupd! + simple_dseupd! -----------------
+ * Host control (dsaup2 loop, dsgets, dsconv, dseigt/dstqrb, dsapps bulge chase, dseupd's small
+ * eigenproblem) runs on the host inside this call and drives the entry points above; it exists
+ * because Julia is not available in the build image -- with Julia the reference's own dsaupd!/
+ * dsaup2! call ga_getv0/ga_lanczos/ga_apply_shifts/ga_ritz_vectors directly.
+ *   tol: 1 (or 2 for DD) doubles, <= 0 -> eps/2.   v0_host NULL -> dlarnv start vector.
+ *   values[nev] (ascending), bounds[nev]: reals.  vectors_host: n_local x nev (ldz) or NULL.
+ *   iparam_out[11]: ARPACK iparam (iparam[2] = restarts, iparam[4] = nconv, iparam[8..10] counters).
+ * Returns dsaupd/dseupd info: 0 ok, 1 maxiter reached, <0 error. */
+int ga_symeigs(ga_ctx* ctx, int which, int nev, const double* tol, int maxiter, const void* v0_host,
+               int ritzvec, void* values, void* bounds, void* vectors_host, int64_t ldz,
+               int64_t iparam_out[11]);
+
+/* Restartable form used by bench.py: run at most `max_restarts` more outer iterations of the
+ * dsaup2 loop of a solve started with ga_symeigs_begin; returns 0 while unconverged, 99 when
+ * finished (then call ga_symeigs_end to post-process). */
+int ga_symeigs_begin(ga_ctx* ctx, int which, int nev, const double* tol, int maxiter, const void* v0_host);
+int ga_symeigs_iterate(ga_ctx* ctx, int max_restarts);
+int ga_symeigs_end(ga_ctx* ctx, int ritzvec, void* values, void* bounds, void* vectors_host, int64_t ldz,
+                   int64_t iparam_out[11]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GARPACK_B200_H */

@@ -1,0 +1,94 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/garpack_b200.h declares; the Python mirror has the reference's entry points; and without a
+GPU the product path fails loudly instead of falling back to a CPU implementation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "garpack_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ga_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(pkg):
+    pkg.build()
+    L = pkg.lib()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), "libgarpack_b200.so does not export %s" % n
+    assert sorted(pkg.ABI_SYMBOLS) == names
+
+
+def test_python_mirror_surface(pkg):
+    """names of the reference's interface for this path (src/interface.jl, src/idonow_ops.jl)"""
+    for name in ("eigs", "symeigs", "hermeigs", "svds", "ArpackSimpleOp", "ArpackNormalOp", "ArpackException",
+                 "ArpackEigen", "ArpackStats"):
+        assert hasattr(pkg, name)
+    op = pkg.ArpackSimpleOp(sp.identity(7).tocsr())
+    assert op.size() == 7 and op.arpack_mode == 1 and op.bmat == "I" and op.is_arpack_mode_valid_for_op(1)
+    nop = pkg.ArpackNormalOp(sp.random(9, 4, density=0.5, format="csr", random_state=np.random.RandomState(0)))
+    assert nop.size() == 4 and nop.At_side == "left"
+    with pytest.raises(ValueError):
+        pkg.symeigs(op, 3, ncv=8)   # ncv > n (src/interface.jl:231)
+    with pytest.raises(ValueError):
+        pkg.symeigs(op, 5, ncv=5)   # nev >= ncv (src/interface.jl:232)
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device ga_create must fail (GA_ERR_CUDA); eigs must raise, not compute."""
+    L = pkg.lib()
+    h = ctypes.c_void_p()
+    rc = L.ga_create(ctypes.byref(h), 0, 10, 10, 0, 4, 0, 0, 1)
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = os.path.exists("/dev/nvidia0")
+    if has_gpu:
+        assert rc == 0
+        L.ga_destroy(h)
+    else:
+        assert rc == -100 and not h
+        with pytest.raises(RuntimeError):
+            pkg.eigs(sp.identity(30).tocsr(), 3)
+
+
+def test_product_never_imports_oracle():
+    """the product package may not reference oracle/ (only tests/, smoke() and bench.py may)"""
+    pk = os.path.join(ROOT, "genericarpack.jl_b200")
+    for dirpath, _, files in os.walk(pk):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt and \
+                    "oracle.hpp" not in txt and "oracle/" not in txt.replace("oracle/ ", ""), f
+
+
+def test_synthetic_generators(syn):
+    rp, col, val, shape = syn.laplacian2d(7)
+    A = syn.to_scipy((rp, col, val, shape)).toarray()
+    assert shape == (49, 49) and len(col) == 5 * 49 - 4 * 7
+    assert np.allclose(A, A.T) and np.all(np.diag(A) == 4)
+    w = np.linalg.eigvalsh(A)
+    assert np.allclose(np.sort(w)[-5:], syn.laplacian2d_eigs(7, 5))
+    part = syn.laplacian2d(7, row_range=(14, 30))
+    assert np.allclose(syn.to_scipy(part).toarray(), A[14:30])
+    S = syn.to_scipy(syn.sprand_sym(200, 5.0, seed=1)).toarray()
+    assert np.allclose(S, S.T) and 7 < (S != 0).sum() / 200 < 13
+    Hm = syn.to_scipy(syn.hermitian_stencil(6)).toarray()
+    assert np.allclose(Hm, Hm.conj().T)
+    T = syn.to_scipy(syn.tall_sparse(300, 40, 5))
+    assert T.shape == (300, 40)
+    assert np.array_equal(syn.splitmix64(1234, 3), syn.splitmix64(1234, 5)[:3])

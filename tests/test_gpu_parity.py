@@ -1,0 +1,462 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the reference's golden vectors / KATs, and -- at BASELINE.json's full size --
+through size-independent properties (orthonormality, the Lanczos three-term relation, analytic
+spectrum).  Tolerances follow BASELINE.json's north_star: start vector bit-exact; Float64
+eigenvalues <= 1e-10 relative; Double64 <= 1e-26; restart counts within +-1 of the oracle."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN_V0, kat15
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f64": 0, "c64": 1, "dd": 2}
+
+
+def _dd_float(x):
+    return x[..., 0] + x[..., 1]
+
+
+# ---------------------------------------------------------------- dgetv0: start vector, bit-exact
+@pytest.mark.parametrize("dtype", ["f64", "c64", "dd"])
+@pytest.mark.parametrize("n", [10, 129, 4097, 100003])
+def test_start_vector_bit_exact(pkg, O, dtype, n):
+    op = pkg.ArpackSimpleOp(sp.identity(n, format="csr"), dtype=dtype)
+    ctx = pkg.Context(op, 2)
+    ierr, rnorm = ctx.getv0(initv=False, j=1)
+    x = np.asarray(ctx.download_resid())
+    ref, seed = O.dlarnv(n, dtype=DT[dtype])
+    assert ierr == 0
+    assert x.tobytes() == np.asarray(ref).tobytes()          # bit-exact (integer LCG)
+    assert tuple(ctx.iseed) == seed
+    if n == 10 and dtype == "f64":
+        assert np.array_equal(x, np.array(GOLDEN_V0))        # test/dgetv0_simple.jl:6-35
+    nr = O.norm2(ref, DT[dtype])
+    if dtype == "dd":
+        assert abs(_dd_float(np.asarray(rnorm) - 0) - _dd_float(nr)) <= 4e-30 * _dd_float(nr) or \
+            abs((rnorm[0] - nr[0]) + (rnorm[1] - nr[1])) <= 1e-29 * nr[0]
+    else:
+        assert abs(rnorm - nr) <= np.spacing(nr)             # within 1 ulp of the x87 norm
+    ctx.close()
+
+
+def test_norm2_overflow_safe(pkg, O):
+    """norm2 semantics (src/arpack-blas-nrm2.jl): no overflow/underflow, ~correctly rounded."""
+    import mpmath as mp
+
+    mp.mp.prec = 200
+    rng = np.random.default_rng(0)
+    n = 5000
+    op = pkg.ArpackSimpleOp(sp.identity(n, format="csr"))
+    ctx = pkg.Context(op, 2)
+    for scale in (1.0, 1e200, 1e-200, 1e-300):
+        x = rng.standard_normal(n) * scale
+        ctx.upload_resid(x)
+        got = ctx.norm2_resid()
+        exact = mp.sqrt(sum(mp.mpf(float(v)) ** 2 for v in x))
+        assert abs(mp.mpf(got) - exact) <= abs(exact) * 2.0 ** -52, scale
+    x = np.zeros(n)
+    x[[3, 77, 4000]] = [1e300, 1e-300, 3e10]   # mixed ranges (Blue's three accumulators)
+    ctx.upload_resid(x)
+    assert ctx.norm2_resid() == pytest.approx(1e300, rel=1e-15)
+    ctx.upload_resid(np.zeros(n))
+    assert ctx.norm2_resid() == 0.0                           # test/runtests.jl:164-166
+    ctx.close()
+
+
+# ---------------------------------------------------------------- OP*x
+@pytest.mark.parametrize("dtype", ["f64", "c64", "dd"])
+def test_opx(pkg, syn, O, dtype):
+    if dtype == "c64":
+        csr = syn.hermitian_stencil(37)
+    else:
+        csr = syn.sprand_sym(3000, 5.0, seed=11)
+    A = syn.to_scipy(csr)
+    n = A.shape[0]
+    # add one very long row/column to exercise the long-row path
+    if dtype == "f64":
+        A = A.tolil()
+        A[5, :] = 1.0
+        A[:, 5] = 1.0
+        A = A.tocsr()
+    op = pkg.ArpackSimpleOp(A, dtype=dtype)
+    ctx = pkg.Context(op, 2)
+    x, _ = O.dlarnv(n, dtype=DT[dtype])
+    y = np.asarray(ctx.opx(pkg.as_dd(x) if dtype == "dd" else x))
+    if dtype == "dd":
+        yref = A @ x[:, 0]
+        assert np.allclose(_dd_float(y), yref, rtol=1e-14, atol=1e-14)
+        yo = O.Oracle(A, 2, dtype=O.DD).opx(x)
+        assert np.max(np.abs((y[:, 0] - yo[:, 0]) + (y[:, 1] - yo[:, 1]))) <= 1e-28 * np.max(np.abs(yref))
+    else:
+        yref = A @ x
+        assert np.allclose(y, yref, rtol=1e-13, atol=1e-13)
+    ctx.close()
+
+
+def test_normal_opx(pkg, syn, O):
+    A = syn.to_scipy(syn.tall_sparse(5000, 300, 6))
+    op = pkg.ArpackNormalOp(A)
+    ctx = pkg.Context(op, 4)
+    x, _ = O.dlarnv(300)
+    y = ctx.opx(x)
+    assert np.allclose(y, A.T @ (A @ x), rtol=1e-12)
+    ctx.close()
+    op2 = pkg.ArpackNormalOp(A.T.tocsr())
+    ctx2 = pkg.Context(op2, 4)
+    assert np.allclose(ctx2.opx(x), A.T @ (A @ x), rtol=1e-12)
+    ctx2.close()
+
+
+# ---------------------------------------------------------------- dsaitr
+def _run_both(pkg, O, A, ncv, dtype, k_np_list):
+    op = pkg.ArpackSimpleOp(A, dtype=dtype)
+    ctx = pkg.Context(op, ncv)
+    ora = O.Oracle(A, ncv, dtype=DT[dtype])
+    assert ctx.getv0()[0] == 0 and ora.dgetv0() == 0
+    rn = ctx.norm2_resid()
+    es = (2,) if dtype == "dd" else ()
+    H = np.zeros((ncv, 2) + es)
+    out = []
+    for (k, np_) in k_np_list:
+        info, rn = ctx.lanczos(k, np_, H, rn)
+        oinfo = ora.dsaitr(k, np_)
+        out.append((info, oinfo))
+    return ctx, ora, H, rn, out
+
+
+@pytest.mark.parametrize("dtype", ["f64", "c64", "dd"])
+def test_lanczos_parity_small(pkg, syn, O, dtype):
+    """ga_lanczos vs the oracle's dsaitr! on the same start vector: H, V, resid, rnorm, DGKS counts.
+    Tolerance: the two differ only in summation order, so 40 steps agree to ~1e-9 (f64)."""
+    if dtype == "c64":
+        A = syn.to_scipy(syn.hermitian_stencil(40))
+    else:
+        A = syn.to_scipy(syn.laplacian2d(48))
+    ncv = 24
+    ctx, ora, H, rn, infos = _run_both(pkg, O, A, ncv, dtype, [(0, 6), (6, 18)])
+    assert infos == [(0, 0), (0, 0)]
+    V = np.asarray(ctx.download_v())
+    r = np.asarray(ctx.download_resid())
+    Vo = np.swapaxes(np.asarray(ora.Vt), 0, 1)
+    if dtype == "dd":
+        Vf, Vof, rf, rof = _dd_float(V), _dd_float(Vo), _dd_float(r), _dd_float(np.asarray(ora.resid))
+        Hf, Hof = _dd_float(H), _dd_float(np.asarray(ora.H))
+        rnf, rnof = rn[0] + rn[1], ora.rnorm[0] + ora.rnorm[1]
+        tol = 1e-20
+        # double-double agreement well beyond double precision
+        assert np.max(np.abs((H[..., 0] - ora.H[..., 0]) + (H[..., 1] - ora.H[..., 1]))) <= 1e-24 * np.max(np.abs(Hof))
+    else:
+        Vf, Vof, rf, rof, Hf, Hof, rnf, rnof = V, Vo, r, np.asarray(ora.resid), H, np.asarray(ora.H), rn, ora.rnorm
+        tol = 1e-9
+    assert np.allclose(Hf, Hof, rtol=tol, atol=tol * np.max(np.abs(Hof)))
+    assert np.allclose(Vf, Vof, atol=max(tol, 1e-20) * 10)
+    assert np.allclose(rf, rof, atol=10 * tol * np.max(np.abs(rof)))
+    assert abs(rnf - rnof) <= tol * abs(rnof)
+    # invariants of test/dsaitr_simple.jl:119-137
+    G = Vf.conj().T @ Vf
+    assert np.allclose(G, np.eye(ncv), atol=1e-13)
+    assert np.linalg.norm(Vf.conj().T @ rf) <= 1e-13 * np.linalg.norm(rf)
+    T = np.diag(Hf[:, 1]) + np.diag(Hf[1:, 0], 1) + np.diag(Hf[1:, 0], -1)
+    R = A @ Vf - Vf @ T
+    assert np.allclose(R[:, :-1], 0, atol=1e-12) and np.allclose(R[:, -1], rf, atol=1e-12)
+    st, so = ctx.stats(), ora.stats()
+    assert st["nopx"] == so["nopx"] == ncv
+    assert st["nrorth"] == so["nrorth"] and st["nitref"] == so["nitref"] and st["nrstrt"] == 0
+    ctx.close()
+
+
+def test_lanczos_identity_restart(pkg, O):
+    """test/dsaitr_simple.jl:140-178: identity operator -> invariant subspace after one step ->
+    dgetv0 restart inside the call; resid stays ~0; counters agree with the oracle."""
+    n = 10
+    A = sp.identity(n, format="csr")
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), 3)
+    ora = O.Oracle(A, 3)
+    x = np.arange(1.0, n + 1)
+    ctx.upload_resid(x)
+    ora.resid[:] = x
+    ora.rnorm = np.linalg.norm(x)
+    H = np.zeros((3, 2))
+    info, rn = ctx.lanczos(0, 2, H, np.linalg.norm(x))
+    oinfo = ora.dsaitr(0, 2)
+    assert info == oinfo == 0
+    assert ctx.stats()["nrstrt"] == ora.stats()["nrstrt"] > 0
+    assert np.linalg.norm(ctx.download_resid()) <= n * np.finfo(float).eps
+    V = ctx.download_v(0, 2)
+    assert np.allclose(V.T @ V, np.eye(2), atol=1e-14)
+    assert tuple(ctx.iseed) == tuple(ora.iseed)              # same dlarnv stream consumed
+    assert np.allclose(V, ora.Vt[:2].T, atol=1e-14)
+    assert H[1, 0] == 0.0                                    # H[j,1] = 0 after a restart (:1259-1263)
+    ctx.close()
+
+
+def test_lanczos_zero_initial_resid(pkg, O):
+    """test/dsaitr_simple.jl:180-212."""
+    n = 10
+    A = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), 3)
+    ctx.upload_resid(np.random.default_rng(0).standard_normal(n))
+    H = np.zeros((3, 2))
+    info, rn = ctx.lanczos(0, 3, H, 0.0)
+    assert info == 0
+    V = ctx.download_v()
+    st = ctx.stats()
+    assert st["nrstrt"] > 0 and st["nopx"] == 3
+    assert np.allclose(V.T @ V, np.eye(3), atol=1e-14)
+    assert np.linalg.norm(V.T @ ctx.download_resid()) <= 1e-14
+    ctx.close()
+
+
+def test_getv0_restart_failure(pkg):
+    """test/dgetv0_simple.jl:149-196."""
+    n = 5
+    A = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), 6 if False else 5)
+    ctx.upload_v(np.eye(n)[:, :4], 0)
+    x = np.zeros(n)
+    x[:4] = [0.3, -0.2, 0.9, 0.5]
+    ctx.upload_resid(x)                                      # lies entirely in span(V[:,1:4])
+    ierr, rn = ctx.getv0(initv=True, j=5)
+    assert ierr == -1 and rn == 0.0 and np.all(ctx.download_resid() == 0)
+    ctx2 = pkg.Context(pkg.ArpackSimpleOp(A), 3)
+    V = np.zeros((n, 1))
+    V[:, 0] = 1 / np.sqrt(n)
+    ctx2.upload_v(V, 0)
+    ctx2.upload_resid(2 * np.random.default_rng(1).random(n) - 1)
+    ierr, rn = ctx2.getv0(initv=True, j=2)
+    r = ctx2.download_resid()
+    assert ierr == 0 and abs(np.sum(r)) <= n * np.finfo(float).eps and rn > 0
+    ctx.close()
+    ctx2.close()
+
+
+# ---------------------------------------------------------------- dsapps tail / dseupd tail
+@pytest.mark.parametrize("dtype", ["f64", "c64", "dd"])
+def test_apply_shifts_parity(pkg, syn, O, dtype):
+    """device tail of dsapps! vs the oracle's dsapps! fed the same factorisation."""
+    A = syn.to_scipy(syn.hermitian_stencil(30) if dtype == "c64" else syn.laplacian2d(30))
+    ncv, kev = 20, 7
+    np_ = ncv - kev
+    ctx, ora, H, rn, infos = _run_both(pkg, O, A, ncv, dtype, [(0, ncv)])
+    # make the device state identical to the oracle's before the shifts
+    Vo = np.swapaxes(np.asarray(ora.Vt), 0, 1).copy()
+    ctx.upload_v(pkg.as_dd(Vo) if dtype == "dd" else Vo, 0)
+    ctx.upload_resid(pkg.as_dd(np.asarray(ora.resid).copy()) if dtype == "dd" else np.asarray(ora.resid).copy())
+    Hd = np.asarray(ora.H)
+    Hf = _dd_float(Hd) if dtype == "dd" else Hd
+    T = np.diag(Hf[:, 1]) + np.diag(Hf[1:, 0], 1) + np.diag(Hf[1:, 0], -1)
+    shifts = np.sort(np.linalg.eigvalsh(T))[:np_]            # unwanted = smallest (which = LM-like)
+    sh = np.zeros((np_, 2)) if dtype == "dd" else shifts
+    if dtype == "dd":
+        sh[:, 0] = shifts
+    ora.dsapps(kev, np_, sh)
+    Q = np.asarray(ora.Q).copy()
+    beta = np.asarray(ora.H)[kev, 0]
+    rnorm = ctx.apply_shifts(kev, np_, Q, beta)
+    V = np.asarray(ctx.download_v(0, kev + 1))
+    r = np.asarray(ctx.download_resid())
+    Vn = np.swapaxes(np.asarray(ora.Vt), 0, 1)[:, : kev + 1]
+    rno = O.norm2(np.asarray(ora.resid), DT[dtype])
+    if dtype == "dd":
+        assert np.max(np.abs((V[..., 0] - Vn[..., 0]) + (V[..., 1] - Vn[..., 1]))) <= 1e-28
+        assert np.max(np.abs((r[..., 0] - ora.resid[..., 0]) + (r[..., 1] - ora.resid[..., 1]))) <= 1e-28 * (1 + abs(rno[0]))
+        assert abs((rnorm[0] - rno[0]) + (rnorm[1] - rno[1])) <= 1e-28 * rno[0]
+    else:
+        assert np.allclose(V, Vn, atol=1e-14)
+        assert np.allclose(r, np.asarray(ora.resid), atol=1e-14 * (1 + abs(rno)))
+        assert abs(rnorm - rno) <= 4 * np.spacing(rno)
+    ctx.close()
+
+
+def test_ritz_vectors_parity(pkg, syn):
+    A = syn.to_scipy(syn.laplacian2d(20))
+    n, ncv, nconv = A.shape[0], 12, 5
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), ncv)
+    rng = np.random.default_rng(2)
+    V0 = rng.standard_normal((n, ncv))
+    Qh = np.linalg.qr(rng.standard_normal((ncv, ncv)))[0]
+    ctx.upload_v(V0, 0)
+    Z = ctx.ritz_vectors(nconv, Qh)
+    assert np.allclose(Z, (V0 @ Qh)[:, :nconv], atol=1e-13)
+    assert np.allclose(ctx.download_v(), V0 @ Qh, atol=1e-13)   # V <- V*Q like the reference (:1431)
+    ctx.close()
+
+
+# ---------------------------------------------------------------- whole solves (KATs)
+def _top(w, k, which="LM"):
+    if which == "LM":
+        return np.sort(w[np.argsort(-np.abs(w))[:k]])
+    if which == "LA":
+        return np.sort(np.sort(w)[-k:])
+    if which == "SA":
+        return np.sort(np.sort(w)[:k])
+    raise ValueError(which)
+
+
+def _check_against_oracle(pkg, O, A, nev, ncv, which="LM", dtype="f64", v0=None, rtol=1e-10):
+    res = pkg.eigs(pkg.ArpackSimpleOp(A, dtype=dtype), nev, ncv=ncv, which=which, v0=v0)
+    ora = O.Oracle(A, ncv, dtype=DT[dtype]).symeigs(nev, which=which, v0=v0)
+    vals, ovals = np.asarray(res.values), np.asarray(ora["values"])
+    if dtype == "dd":
+        d = np.abs((vals[:, 0] - ovals[:, 0]) + (vals[:, 1] - ovals[:, 1]))
+        assert np.max(d / np.abs(ovals[:, 0])) <= 1e-26
+    else:
+        assert np.max(np.abs(vals - ovals) / np.abs(ovals)) <= rtol
+    assert res.info == ora["info"] == 0
+    assert abs(int(res.iparam[2]) - ora["niter"]) <= 1          # restart count within +-1
+    assert int(res.iparam[4]) == ora["nconv"]
+    return res, ora
+
+
+def test_eigs_kat_15x15(pkg, O):
+    """test/interface_simple.jl:7-11 and test/dsaupd_arpackjll.jl:232-241."""
+    A = kat15()
+    w = np.linalg.eigvalsh(A.toarray())
+    for ncv in (15, 6):
+        res, _ = _check_against_oracle(pkg, O, A, 3, ncv)
+        assert np.allclose(res.values, _top(w, 3), rtol=1e-12)
+        Z = res.vectors
+        assert np.allclose(A @ Z, Z * res.values, atol=1e-11)
+        assert np.allclose(Z.T @ Z, np.eye(3), atol=1e-12)
+    res = pkg.eigs(A, 3, which="LA", ritzvec=False)
+    assert np.allclose(res.values, _top(w, 3, "LA"), rtol=1e-12) and res.vectors is None
+    res = pkg.eigs(A, 3, which="SA")
+    assert np.allclose(res.values, _top(w, 3, "SA"), rtol=1e-12)
+    res = pkg.eigs(A, 4, which="BE", ncv=10)
+    assert np.allclose(res.values, np.sort(np.concatenate([np.sort(w)[:2], np.sort(w)[-2:]])), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,nev,ncv", [(10, 3, 6), (30, 4, 10), (1000, 6, 12)])
+def test_eigs_kat_diagonal(pkg, O, n, nev, ncv):
+    A = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    v0 = np.ones(n) / np.sqrt(n)
+    res, ora = _check_against_oracle(pkg, O, A, nev, ncv, v0=v0)
+    assert np.allclose(res.values, np.arange(n - nev + 1, n + 1), rtol=1e-12)
+
+
+def test_eigs_kat_issue5(pkg):
+    A = sp.lil_matrix((10, 10))
+    for i in (0, 1, 4, 5):
+        A[i, i] = 1.0
+    A = A.tocsr()
+    res = pkg.eigs(A, 5, ncv=8)
+    Z, lam = res.vectors, res.values
+    assert np.allclose(A @ Z, Z * lam, atol=1e-12)
+    assert np.allclose(Z.T @ Z, np.eye(5), atol=1e-12)
+    assert np.sum(lam) == pytest.approx(4.0, rel=1e-12)
+
+
+def test_eigs_laplacian_analytic(pkg, syn, O):
+    """C2 at reduced size: eigs(A, 10; ncv=40) on the 2-D Laplacian vs the analytic spectrum, the
+    oracle, Ritz estimates (bounds <= tol*|lambda|) and true residuals."""
+    m = 120
+    csr = syn.laplacian2d(m)
+    A = syn.to_scipy(csr)
+    res, ora = _check_against_oracle(pkg, O, A, 10, 40)
+    exact = syn.laplacian2d_eigs(m, 10)
+    assert np.max(np.abs(res.values - exact) / exact) <= 1e-10
+    tol = np.finfo(float).eps / 2
+    assert np.all(res.bounds <= tol * np.maximum(np.finfo(float).eps ** (2 / 3), np.abs(res.values)) * (1 + 1e-12))
+    Z = res.vectors
+    R = A @ Z - Z * res.values
+    assert np.max(np.linalg.norm(R, axis=0) / np.abs(res.values)) <= 1e-10
+    assert np.allclose(Z.T @ Z, np.eye(10), atol=1e-12)
+    assert abs(res.stats["nopx"] - ora["stats"]["nopx"]) <= 40
+
+
+def test_eigs_sprand_c1(pkg, syn, O):
+    """C1 (README example shape) at n = 20000: nev = 2, ncv = 12."""
+    A = syn.to_scipy(syn.sprand_sym(20000, 5.0, seed=1234))
+    res, ora = _check_against_oracle(pkg, O, A, 2, 12)
+    Z = res.vectors
+    assert np.max(np.linalg.norm(A @ Z - Z * res.values, axis=0) / np.abs(res.values)) <= 1e-10
+
+
+def test_eigs_complex_hermitian(pkg, syn, O):
+    """C4 at reduced size + test/dsaupd_complex.jl:78-80."""
+    n = 20
+    H = (sp.diags([1j * np.ones(n - 1), 2 * np.ones(n) + 0j, -1j * np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
+    w = np.linalg.eigvalsh(H.toarray())
+    res, _ = _check_against_oracle(pkg, O, H, 4, 12, dtype="c64")
+    assert np.allclose(res.values, _top(w, 4), rtol=1e-12)
+    A = syn.to_scipy(syn.hermitian_stencil(60))
+    res, _ = _check_against_oracle(pkg, O, A, 6, 30, dtype="c64")
+    Z = res.vectors
+    assert np.allclose(Z.conj().T @ Z, np.eye(6), atol=1e-12)
+    assert np.max(np.linalg.norm(A @ Z - Z * res.values, axis=0) / np.abs(res.values)) <= 1e-10
+
+
+def test_eigs_double64(pkg, syn, O):
+    """C3 + test/interface_high.jl:60-66: Double64 eigenvalues to 1e-26 (oracle and exact)."""
+    import mpmath as mp
+
+    mp.mp.prec = 250
+    n = 100
+    A = (sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
+    res, ora = _check_against_oracle(pkg, O, A, 4, 20, dtype="dd")
+    exact = [(n + 1) * (2 - 2 * mp.cos(k * mp.pi / (n + 1))) for k in range(n - 3, n + 1)]
+    got = [mp.mpf(float(v[0])) + mp.mpf(float(v[1])) for v in np.asarray(res.values)]
+    assert max(abs(g - e) / e for g, e in zip(got, exact)) < mp.mpf(10) ** -26
+    A2 = syn.to_scipy(syn.sprand_sym(3000, 5.0, seed=1234))
+    res2, ora2 = _check_against_oracle(pkg, O, A2, 2, 12, dtype="dd")
+    # the Double64 run refines the Float64 one
+    f = pkg.eigs(A2, 2, ncv=12)
+    assert np.allclose(_dd_float(np.asarray(res2.values)), f.values, rtol=1e-12)
+
+
+def test_svds_normal(pkg, syn):
+    """C5 at reduced size: svds via the normal operator (src/interface.jl:304-337)."""
+    A = syn.to_scipy(syn.tall_sparse(4000, 200, 8))
+    S, V, info = pkg.svds(A, 5, ncv=20)
+    s = np.linalg.svd(A.toarray(), compute_uv=False)
+    assert np.allclose(S, s[:5], rtol=1e-9)
+    assert np.allclose(V.T @ V, np.eye(5), atol=1e-10)
+
+
+def test_maxiter_exception(pkg, syn):
+    """src/interface.jl:269-270: info == 1 with failonmaxiter raises ArpackException."""
+    A = syn.to_scipy(syn.laplacian2d(60))
+    with pytest.raises(pkg.ArpackException):
+        pkg.eigs(A, 6, ncv=14, maxiter=2)
+    res = pkg.eigs(A, 6, ncv=14, maxiter=2, failonmaxiter=False)
+    assert res.info == 1 and int(res.iparam[2]) == 3 and len(res.values) == int(res.iparam[4]) < 6
+
+
+# ---------------------------------------------------------------- full size (BASELINE config C2)
+def test_full_size_properties(pkg, syn):
+    """n = 16M 2-D Laplacian, ncv = 40: two restart cycles on the device, then size-independent
+    checks on downloaded columns: unit norms, orthogonality of sampled pairs, and the Lanczos
+    three-term relation A v_j = b_{j-1} v_{j-1} + a_j v_j + b_j v_{j+1} for sampled j."""
+    m = 4000
+    csr = syn.laplacian2d(m)
+    A = syn.to_scipy(csr)
+    ncv, nev = 40, 10
+    ctx = pkg.Context(pkg.ArpackSimpleOp(csr), ncv)
+    assert ctx.getv0()[0] == 0
+    rn = ctx.norm2_resid()
+    H = np.zeros((ncv, 2))
+    info, rn = ctx.lanczos(0, ncv, H, rn)
+    assert info == 0 and rn > 0
+    for j in (1, 17, 38):
+        Vj = ctx.download_v(j - 1, 3)
+        nrm = np.linalg.norm(Vj, axis=0)
+        assert np.allclose(nrm, 1.0, atol=1e-13)
+        G = Vj.T @ Vj
+        assert np.allclose(G, np.eye(3), atol=1e-12)
+        lhs = A @ Vj[:, 1]
+        rhs = H[j, 0] * Vj[:, 0] + H[j, 1] * Vj[:, 1] + H[j + 1, 0] * Vj[:, 2]
+        assert np.linalg.norm(lhs - rhs) <= 1e-12 * np.linalg.norm(lhs)
+    v_first, v_last = ctx.download_v(0, 1)[:, 0], ctx.download_v(ncv - 1, 1)[:, 0]
+    assert abs(v_first @ v_last) <= 1e-12
+    r = ctx.download_resid()
+    assert abs(np.linalg.norm(r) - rn) <= 1e-13 * rn
+    assert abs(v_first @ r) <= 1e-12 * rn and abs(v_last @ r) <= 1e-12 * rn
+    st = ctx.stats()
+    assert st["nopx"] == ncv
+    # Ritz values of the 40-step factorisation lie inside the analytic spectrum (0, 8)
+    T = np.diag(H[:, 1]) + np.diag(H[1:, 0], 1) + np.diag(H[1:, 0], -1)
+    w = np.linalg.eigvalsh(T)
+    assert w.min() > 0 and w.max() < 8
+    ctx.close()

@@ -1,0 +1,327 @@
+"""CPU tests that PIN the oracle (oracle/) against the reference's own golden vectors, known
+answer tests and invariants.  Citations: /root/reference/test/*.jl."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN_V0, kat15
+
+
+# ---------------------------------------------------------------- LCG / start vector (bit-exact)
+def test_golden_start_vector(O):
+    """test/dgetv0_simple.jl:6-35: resid == v0 for seed (1,3,5,7), n = 10; seed must change."""
+    x, seed = O.dlarnv(10)
+    assert np.array_equal(x, np.array(GOLDEN_V0))
+    assert seed != (1, 3, 5, 7)
+    o = O.Oracle(sp.diags(np.arange(1.0, 11.0)).tocsr(), 2)
+    assert o.dgetv0(itry=1, initv=False, j=1) == 0
+    assert np.array_equal(o.resid, np.array(GOLDEN_V0))
+    assert tuple(o.iseed) != (1, 3, 5, 7)
+    assert o.rnorm == pytest.approx(np.linalg.norm(GOLDEN_V0), rel=1e-15)
+
+
+def test_lcg_table_rows(O):
+    """rows 1, 2, 3, 64, 128 of _dlaruv_mm (src/arpack-blas.jl:281-408) given literally."""
+    t = O.lcg_table()
+    assert tuple(t[0]) == (494, 322, 2508, 2549)
+    assert tuple(t[1]) == (2637, 789, 3754, 1145)
+    assert tuple(t[2]) == (255, 1440, 1766, 2253)
+    assert tuple(t[63]) == (2770, 1238, 1956, 2817)
+    assert tuple(t[127]) == (545, 2366, 3801, 1537)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 255, 256, 257, 1000, 4097])
+def test_lcg_closed_form(O, n):
+    """X_g = seed * a^g mod 2^48 (what test/dlarnv_arpackjll.jl:26-57 checks against LAPACK,
+    including the seed left behind)."""
+    a = (494 << 36) | (322 << 24) | (2508 << 12) | 2549
+    X0 = (1 << 36) | (3 << 24) | (5 << 12) | 7
+    x, seed = O.dlarnv(n)
+    g = np.arange(1, n + 1)
+    exp = np.array([2 * (((X0 * pow(a, int(k), 1 << 48)) % (1 << 48)) / 2.0 ** 48) - 1 for k in g])
+    assert np.array_equal(x, exp)
+    if n > 0:
+        Xn = (X0 * pow(a, n, 1 << 48)) % (1 << 48)
+        assert seed == ((Xn >> 36) & 4095, (Xn >> 24) & 4095, (Xn >> 12) & 4095, Xn & 4095)
+    else:
+        assert seed == (1, 3, 5, 7)
+
+
+def test_lcg_complex_and_double64(O):
+    """complex: element i = (value 2i+1, value 2i+2) (src/arpack-blas.jl:531-536); Double64: lo = 0."""
+    xr, _ = O.dlarnv(20)
+    xc, seedc = O.dlarnv(10, dtype=O.C64)
+    assert np.array_equal(xc.real, xr[0::2]) and np.array_equal(xc.imag, xr[1::2])
+    xd, seedd = O.dlarnv(20, dtype=O.DD)
+    assert np.array_equal(xd[:, 0], xr) and np.all(xd[:, 1] == 0)
+    assert seedc == seedd
+
+
+# ---------------------------------------------------------------- norm2
+def test_norm2(O):
+    """test/runtests.jl:164-166 (zeros) and test/dnrm2_openblas.jl (<= 1 ulp of the exact norm)."""
+    assert O.norm2(np.zeros(5)) == 0.0
+    rng = np.random.default_rng(0)
+    import mpmath as mp
+
+    mp.mp.prec = 200
+    for n in [1, 2, 7, 8, 9, 100, 1001]:
+        x = rng.standard_normal(n)
+        exact = mp.sqrt(sum(mp.mpf(float(v)) ** 2 for v in x))
+        got = O.norm2(x)
+        assert abs(mp.mpf(got) - exact) <= abs(exact) * 2.0 ** -52
+    big = np.array([1e200, 1e200, 3e-200])  # x87 range: no overflow
+    assert O.norm2(big) == pytest.approx(np.sqrt(2) * 1e200, rel=1e-15)
+    z = rng.standard_normal(9) + 1j * rng.standard_normal(9)
+    assert O.norm2(z) == pytest.approx(np.linalg.norm(z), rel=1e-15)
+
+
+# ---------------------------------------------------------------- host pieces
+def test_dsconv_dsortr_dsgets(O):
+    """test/runtests.jl:113-140, test/dsgets_simple.jl."""
+    assert O.dsconv(np.ones(10), np.zeros(10), 1e-4) == 10
+    assert O.dsconv(np.ones(10), np.ones(10), 1e-4) == 0
+    x1, x2 = O.dsortr("LA", True, [3.0, 1.0, 2.0], [30.0, 10.0, 20.0])
+    assert list(x1) == [1.0, 2.0, 3.0] and list(x2) == [10.0, 20.0, 30.0]
+    x1, _ = O.dsortr("SA", False, [3.0, 1.0, 2.0], [0.0, 0.0, 0.0])
+    assert list(x1) == [3.0, 2.0, 1.0]
+    x1, _ = O.dsortr("LM", False, [-3.0, 1.0, 2.0], [0.0, 0.0, 0.0])
+    assert list(np.abs(x1)) == [1.0, 2.0, 3.0]
+    ritz, bounds, shifts = O.dsgets(1, "LM", 2, 3, [1.0, -5.0, 3.0, 2.0, -4.0], [0.1, 0.5, 0.3, 0.2, 0.4])
+    assert sorted(np.abs(ritz[3:])) == [4.0, 5.0]          # wanted in the last kev slots
+    assert list(bounds[:3]) == sorted(bounds[:3], reverse=True)  # shifts: largest bounds first
+    assert np.array_equal(shifts, ritz[:3])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11, 13, 16, 17, 99, 127, 128, 129, 500, 513, 1000, 1025])
+def test_dstqrb_laplacian(O, n):
+    """test/dstqrb.jl:104-112."""
+    d, z = O.dstqrb(2 * np.ones(n), -np.ones(max(n - 1, 0)))
+    k = np.arange(1, n + 1)
+    lams = np.sort(-2 * np.cos(np.pi * k / (n + 1)) + 2.0)
+    assert np.max(np.abs(lams - d)) <= 2 * np.sqrt(n) * np.finfo(float).eps
+    zexp = np.abs(np.sqrt(2 / (n + 1)) * np.sin(n * k * np.pi / (n + 1)))
+    assert np.linalg.norm(np.abs(z) - zexp) <= 2 * n * np.finfo(float).eps
+
+
+@pytest.mark.parametrize("n", [2, 8, 16, 128, 500, 1024, 3, 9, 127, 129, 1001, 2001])
+def test_dstqrb_ones(O, n):
+    """test/dstqrb.jl:87-103."""
+    d, z = O.dstqrb(np.zeros(n), np.ones(n - 1))
+    k = np.arange(1, n + 1)
+    if n % 2 == 0:
+        lams = np.sort(2 * np.cos(np.pi * k / (n + 1)))
+        assert np.max(np.abs(d - lams) / np.spacing(np.abs(lams))) <= 2 * n
+    else:
+        assert abs(d[n // 2]) <= 10 * np.finfo(float).eps
+    zexp = np.abs(np.sqrt(2 / (n + 1)) * np.sin(n * k * np.pi / (n + 1)))
+    assert np.linalg.norm(np.abs(z) - zexp) <= 2 * n * np.finfo(float).eps
+
+
+def test_dstqrb_zeros_and_dsteqr(O):
+    """test/dstqrb.jl:80-86 and test/dsteqr-simple.jl (eigenvector matrix is orthogonal, T Z = Z D)."""
+    for n in range(1, 8):
+        d, z = O.dstqrb(np.zeros(n), np.zeros(max(n - 1, 0)))
+        assert np.all(d == 0) and z[-1] == 1.0 and np.all(z[:-1] == 0)
+    rng = np.random.default_rng(3)
+    n = 12
+    dd, ee = rng.standard_normal(n), rng.standard_normal(n - 1)
+    ee[5] = 0.0  # split case (test/dsteqr-compare.jl)
+    T = np.diag(dd) + np.diag(ee, 1) + np.diag(ee, -1)
+    lam, Z = O.dsteqr(dd, ee)
+    assert np.allclose(Z.T @ Z, np.eye(n), atol=1e-14)
+    assert np.allclose(T @ Z, Z * lam, atol=1e-13)
+    assert np.allclose(lam, np.linalg.eigvalsh(T), atol=1e-13)
+
+
+def test_dseigt(O):
+    """test/runtests.jl:141-162: tridiagonal Laplacian through dseigt!, bounds = rnorm |last row|."""
+    n = 30
+    H = np.zeros((n, 2))
+    H[:, 1] = 2.0
+    H[1:, 0] = -1.0
+    eig, bounds = O.dseigt(0.5, H)
+    k = np.arange(1, n + 1)
+    assert np.allclose(eig, np.sort(2 - 2 * np.cos(np.pi * k / (n + 1))), atol=1e-14)
+    assert np.allclose(np.sort(bounds), np.sort(0.5 * np.abs(np.sqrt(2 / (n + 1)) * np.sin(n * k * np.pi / (n + 1)))), atol=1e-14)
+
+
+# ---------------------------------------------------------------- dsaitr / dgetv0 invariants
+def test_dsaitr_orthogonality(O):
+    """test/dsaitr_simple.jl:95-137: V'V = I, ||V'r|| ~ 0 after 3 and then 6 more steps."""
+    n = 10
+    o = O.Oracle(sp.diags(np.arange(1.0, n + 1)).tocsr(), 9)
+    rng = np.random.default_rng(1)
+    r0 = rng.standard_normal(n)
+    o.resid[:] = r0
+    o.rnorm = np.linalg.norm(r0)
+    assert o.dsaitr(0, 3) == 0
+    V = o.Vt[:3].T
+    assert np.allclose(V.T @ V, np.eye(3), atol=1e-14)
+    assert np.linalg.norm(V.T @ o.resid) <= 5e-15
+    assert o.dsaitr(3, 6) == 0
+    V = o.Vt[:9].T
+    assert np.allclose(V.T @ V, np.eye(9), atol=1e-13)
+    assert np.linalg.norm(V.T @ o.resid) <= 1e-13
+    st = o.stats()
+    assert st["nrstrt"] == 0 and st["nopx"] == 9
+    # Lanczos relation A V = V T + r e_k'
+    H = o.H
+    T = np.diag(H[:9, 1]) + np.diag(H[1:9, 0], 1) + np.diag(H[1:9, 0], -1)
+    A = np.diag(np.arange(1.0, n + 1))
+    R = A @ V - V @ T
+    assert np.allclose(R[:, :8], 0, atol=1e-12) and np.allclose(R[:, 8], o.resid, atol=1e-12)
+
+
+def test_dsaitr_identity_restart(O):
+    """test/dsaitr_simple.jl:140-178: identity operator -> invariant subspace -> restart, resid ~ 0."""
+    n = 10
+    o = O.Oracle(sp.identity(n).tocsr(), 3)
+    o.resid[:] = np.arange(1.0, n + 1)
+    o.rnorm = np.linalg.norm(o.resid)
+    o.dsaitr(0, 1)
+    assert o.stats()["nrstrt"] == 0
+    assert np.linalg.norm(o.resid) <= n * np.finfo(float).eps
+    o.resid[:] = np.arange(1.0, n + 1)
+    o.rnorm = np.linalg.norm(o.resid)
+    o.dsaitr(0, 2)
+    assert o.stats()["nrstrt"] > 0
+    assert np.linalg.norm(o.resid) <= n * np.finfo(float).eps
+
+
+def test_dsaitr_zero_initial_resid(O):
+    """test/dsaitr_simple.jl:180-212: rnorm = 0 on entry -> dgetv0 restart, still orthonormal."""
+    n = 10
+    o = O.Oracle(sp.diags(np.arange(1.0, n + 1)).tocsr(), 3)
+    o.resid[:] = np.random.default_rng(0).standard_normal(n)
+    o.rnorm = 0.0
+    assert o.dsaitr(0, 3) == 0
+    V = o.Vt[:3].T
+    st = o.stats()
+    assert st["nrstrt"] > 0 and st["nopx"] > 0
+    assert np.allclose(V.T @ V, np.eye(3), atol=1e-14)
+    assert np.linalg.norm(V.T @ o.resid) <= 4 * np.finfo(float).eps * max(1.0, np.linalg.norm(o.resid))
+
+
+def test_dgetv0_restart_failure(O):
+    """test/dgetv0_simple.jl:149-196: V = I spans everything -> ierr = -1, resid = 0; then a case
+    that works (orthogonalise against the constant vector)."""
+    n = 5
+    o = O.Oracle(sp.diags(np.arange(1.0, n + 1)).tocsr(), 6)
+    o.Vt[:5] = np.eye(n)
+    o.resid[:] = 2 * np.random.default_rng(0).random(n) - 1
+    ierr = o.dgetv0(itry=1, initv=True, j=6)
+    assert ierr == -1 and np.all(o.resid == 0) and o.rnorm == 0.0
+    o = O.Oracle(sp.diags(np.arange(1.0, n + 1)).tocsr(), 3)
+    o.Vt[0] = 1 / np.sqrt(n)
+    o.resid[:] = 2 * np.random.default_rng(1).random(n) - 1
+    ierr = o.dgetv0(itry=1, initv=True, j=2)
+    assert ierr == 0 and abs(np.sum(o.resid)) <= n * np.finfo(float).eps and o.rnorm > 0
+
+
+# ---------------------------------------------------------------- eigenvalue KATs
+def _top(w, k, which="LM"):
+    if which == "LM":
+        return np.sort(w[np.argsort(-np.abs(w))[:k]])
+    return np.sort(np.sort(w)[-k:])
+
+
+def test_kat_15x15(O):
+    """test/interface_simple.jl:7-11 (default ncv) and test/dsaupd_arpackjll.jl:232-241 (ncv=6, nev=3:
+    'needs early shift and deflation')."""
+    A = kat15()
+    w = np.linalg.eigvalsh(A.toarray())
+    for ncv in (15, 6):
+        r = O.Oracle(A, ncv).symeigs(3)
+        assert r["info"] == 0 and r["nconv"] == 3
+        assert np.allclose(r["values"], _top(w, 3), rtol=1e-12)
+        Z = r["vectors"]
+        assert np.allclose(A @ Z, Z * r["values"], atol=1e-11)
+        assert np.allclose(Z.T @ Z, np.eye(3), atol=1e-12)
+    r = O.Oracle(A, 15).symeigs(3, which="LA", ritzvec=False)
+    assert np.allclose(r["values"], _top(w, 3, "LA"), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,nev,ncv", [(10, 3, 6), (30, 4, 10), (1000, 6, 12)])
+def test_kat_diagonal(O, n, nev, ncv):
+    """test/dsaupd_simple.jl:61-64, test/dsaupd_idonow.jl:3-15, test/dsaupd_arpackjll.jl:134-149."""
+    A = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    r = O.Oracle(A, ncv).symeigs(nev, v0=np.ones(n) / np.sqrt(n))
+    assert r["info"] == 0
+    assert np.allclose(r["values"], np.arange(n - nev + 1, n + 1), rtol=1e-12)
+
+
+def test_kat_issue5(O):
+    """test/interface_simple.jl:15-24: rank-deficient 10 x 10, nev = 5, ncv = 8."""
+    A = sp.lil_matrix((10, 10))
+    for i in (0, 1, 4, 5):
+        A[i, i] = 1.0
+    A = A.tocsr()
+    r = O.Oracle(A, 8).symeigs(5)
+    Z, lam = r["vectors"], r["values"]
+    assert np.allclose(A @ Z, Z * lam, atol=1e-12)
+    assert np.allclose(Z.T @ Z, np.eye(5), atol=1e-12)
+    assert np.sum(lam) == pytest.approx(4.0, rel=1e-12)
+
+
+def test_kat_complex(O):
+    """test/dsaupd_complex.jl:78-80 / docs example: Hermitian tridiagonal, Ritz values vs dense eigvals."""
+    n = 20
+    H = (sp.diags([1j * np.ones(n - 1), 2 * np.ones(n) + 0j, -1j * np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
+    w = np.linalg.eigvalsh(H.toarray())
+    r = O.Oracle(H, 12).symeigs(4)
+    assert r["info"] == 0
+    assert np.allclose(r["values"], _top(w, 4), rtol=1e-12)
+    Z = r["vectors"]
+    assert np.allclose(Z.conj().T @ Z, np.eye(4), atol=1e-12)
+
+
+def test_kat_double64(O):
+    """test/interface_high.jl:60-66: tridiagonal Laplacian (dsdrv3's A) in Double64 to ~1e-28."""
+    import mpmath as mp
+
+    mp.mp.prec = 250
+    n = 100
+    A = (sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
+    r = O.Oracle(A, 20, dtype=O.DD).symeigs(4)
+    assert r["info"] == 0
+    exact = [(n + 1) * (2 - 2 * mp.cos(k * mp.pi / (n + 1))) for k in range(n - 3, n + 1)]
+    got = [mp.mpf(float(v[0])) + mp.mpf(float(v[1])) for v in r["values"]]
+    assert max(abs(g - e) / e for g, e in zip(got, exact)) < mp.mpf(10) ** -28
+
+
+def test_svds_normal_op(O):
+    """test/interface_simple.jl:100-105 style: ArpackNormalOp eigenvalues = squared singular values."""
+    rng = np.random.default_rng(5)
+    A = sp.random(60, 25, density=0.2, random_state=np.random.RandomState(5), format="csr")
+    o = O.Oracle(A, 12, normal=True)
+    assert o.n == 25
+    r = o.symeigs(3)
+    s = np.linalg.svd(A.toarray(), compute_uv=False)
+    assert np.allclose(np.sqrt(r["values"]), np.sort(s[:3]), rtol=1e-10)
+    o2 = O.Oracle(A.T.tocsr(), 12, normal=True)
+    assert o2.n == 25
+    r2 = o2.symeigs(3)
+    assert np.allclose(r2["values"], r["values"], rtol=1e-10)
+
+
+def test_vs_scipy_arpack(O, syn):
+    """Independent implementation of the same algorithm (SciPy's ARPACK): same eigenvalues and a
+    comparable amount of work on the 2-D Laplacian."""
+    import scipy.sparse.linalg as sla
+
+    m = 60
+    A = syn.to_scipy(syn.laplacian2d(m))
+    cnt = [0]
+
+    def mv(x):
+        cnt[0] += 1
+        return A @ x
+
+    v0, _ = O.dlarnv(m * m)
+    w = sla.eigsh(sla.LinearOperator(A.shape, matvec=mv, dtype=float), k=10, ncv=40, which="LM", v0=v0, tol=0,
+                  return_eigenvectors=False)
+    r = O.Oracle(A, 40).symeigs(10)
+    assert np.allclose(np.sort(w), r["values"], rtol=1e-12)
+    assert np.allclose(r["values"], syn.laplacian2d_eigs(m, 10), rtol=1e-12)
+    assert abs(r["stats"]["nopx"] - cnt[0]) <= 0.15 * cnt[0]

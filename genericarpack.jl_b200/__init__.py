@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = [
     "ArpackException", "ArpackSimpleOp", "ArpackNormalOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
-    "Context", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD",
+    "Context", "comm_unique_id", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init",
     "ga_set_csr", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -110,6 +110,10 @@ def lib():
         L.ga_norm2_resid.argtypes = [vp, vp]
         L.ga_get_stats.argtypes = [vp, ctypes.POINTER(ga_stats)]
         L.ga_reset_stats.argtypes = [vp]
+        L.ga_timer_start.argtypes = [vp]
+        L.ga_timer_stop.argtypes = [vp, vp]
+        L.ga_profile.argtypes = [vp, i32]
+        L.ga_profile_read.argtypes = [vp, vp, vp, vp, vp]
         L.ga_symeigs.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
         L.ga_symeigs_begin.argtypes = [vp, i32, i32, vp, i32, vp]
         L.ga_symeigs_iterate.argtypes = [vp, i32]
@@ -284,8 +288,7 @@ class Context:
 
     def upload_v(self, V, col0=0):
         """V: n x k (column j of the basis = V[:, j])."""
-        V = np.asarray(V)
-        k = V.shape[1]
+        k = np.shape(V)[1]
         Vt = np.ascontiguousarray(np.swapaxes(to_elem(V, self.dtype), 0, 1))  # [col][row](,2)
         self._ck(lib().ga_upload_v(self.h, col0, k, _p(Vt), self.n))
 
@@ -347,6 +350,31 @@ class Context:
     def reset_stats(self):
         lib().ga_reset_stats(self.h)
 
+    # --- multi-GPU plumbing (rendezvous is the caller's: torch.distributed / MPI)
+    def comm_init(self, id128):
+        buf = np.ascontiguousarray(id128, dtype=np.uint8)
+        assert buf.size == 128
+        self._ck(lib().ga_comm_init(self.h, _p(buf)))
+
+    # --- measurement hooks
+    def timer_start(self):
+        self._ck(lib().ga_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double(0.0)
+        self._ck(lib().ga_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        self._ck(lib().ga_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        ms = ctypes.c_double(0.0)
+        runs, units, launches = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        self._ck(lib().ga_profile_read(self.h, ctypes.byref(ms), ctypes.byref(runs), ctypes.byref(units),
+                                       ctypes.byref(launches)))
+        return {"gs_ms": ms.value, "gs_runs": runs.value, "gs_units": units.value, "launches": launches.value}
+
     # --- whole solve
     def symeigs_begin(self, nev, which="LM", tol=0.0, maxiter=300, v0=None):
         t = self._real(tol)
@@ -366,6 +394,16 @@ class Context:
         nconv = int(iparam[4])
         vecs = np.swapaxes(Zt[:nconv], 0, 1) if ritzvec else None
         return rc, values[:nconv], bounds[:nconv], vecs, iparam
+
+
+def comm_unique_id(buf=None):
+    """128-byte NCCL unique id (rank 0 creates it, the caller broadcasts it)."""
+    if buf is None:
+        buf = np.zeros(128, dtype=np.uint8)
+    rc = lib().ga_comm_unique_id(_p(buf))
+    if rc != 0:
+        raise ArpackException("ga_comm_unique_id failed (%d): is libnccl.so.2 loadable?" % rc)
+    return buf
 
 
 class ArpackEigen:

@@ -114,6 +114,9 @@ void ga_destroy(ga_ctx* c) {
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->tm0) cudaEventDestroy(c->tm0);
+  if (c->tm1) cudaEventDestroy(c->tm1);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -446,6 +449,52 @@ int ga_norm2_resid(ga_ctx* c, double* out) {
   if ((rc = launch_norm_resid(c, DK_NORM))) return rc;
   if ((rc = sync_ctl(c))) return rc;
   pair_to_host_real(c, c->ctl_host->rnorm, out);
+  return 0;
+}
+
+int ga_timer_start(ga_ctx* c) {
+  if (!c) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  if (!c->tm0) { GA_CUDA(c, cudaEventCreate(&c->tm0)); GA_CUDA(c, cudaEventCreate(&c->tm1)); }
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  GA_CUDA(c, cudaEventRecord(c->tm0, c->stream));
+  return 0;
+}
+int ga_timer_stop(ga_ctx* c, double* ms) {
+  if (!c || !ms || !c->tm0) return GA_ERR_ARG;
+  GA_CUDA(c, cudaEventRecord(c->tm1, c->stream));
+  GA_CUDA(c, cudaEventSynchronize(c->tm1));
+  float f = 0.f;
+  GA_CUDA(c, cudaEventElapsedTime(&f, c->tm0, c->tm1));
+  *ms = (double)f;
+  return 0;
+}
+int ga_profile(ga_ctx* c, int enable) {
+  if (!c) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->prof = enable != 0;
+  c->prof_used = 0;
+  c->launches = 0;
+  GA_CUDA(c, cudaMemsetAsync(&c->ctl->prof_runs, 0, sizeof(unsigned int), c->stream));
+  GA_CUDA(c, cudaMemsetAsync(&c->ctl->prof_units, 0, sizeof(unsigned long long), c->stream));
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int ga_profile_read(ga_ctx* c, double* gs_ms, int64_t* gs_runs, int64_t* gs_units, int64_t* launches) {
+  if (!c) return GA_ERR_ARG;
+  int rc = sync_ctl(c);
+  if (rc) return rc;
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+    float f = 0.f;
+    GA_CUDA(c, cudaEventElapsedTime(&f, c->prof_ev[i], c->prof_ev[i + 1]));
+    tot += (double)f;
+  }
+  if (gs_ms) *gs_ms = tot;
+  if (gs_runs) *gs_runs = (int64_t)c->ctl_host->prof_runs;
+  if (gs_units) *gs_units = (int64_t)c->ctl_host->prof_units;
+  if (launches) *launches = (int64_t)c->launches;
   return 0;
 }
 

@@ -40,6 +40,8 @@ struct DevCtl {
   int nrorth, nitref;
   int zero_resid;    // dsaitr set resid = 0, rnorm = 0 (src/dsaitr.jl:1442-1443)
   unsigned int ticket;  // last-block counter
+  unsigned int prof_runs;        // executed (not phase-gated) Gram-Schmidt sweep launches
+  unsigned long long prof_units; // n-vector passes those launches moved: (j+1) reads + 1 write when updating
   double rnorm[2], wnorm[2], rnorm0[2], rnorm1[2];
   double2 red[kMaxSlots];    // reduced slots of the last reduction kernel
   double2 hbuf[kMaxNcv];     // coefficient vector h / s (element type T, padded to 16 B)
@@ -96,6 +98,13 @@ struct ga_ctx {
   void* solve = nullptr;
 
   ga_stats stats{};
+
+  // measurement hooks (bench.py): CUDA events around every Gram-Schmidt sweep launch
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+  size_t prof_used = 0;
+  long long launches = 0;            // kernels launched by this context
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   std::string err;
 };
 

@@ -23,6 +23,9 @@
 
 namespace ga {
 
+// dynamic shared memory per CTA (the SM has 227 KiB for one CTA incl. ~1 KiB static)
+constexpr size_t kGsSmemBytes = 224 * 1024;
+
 template <class T> struct GsCfg {
   static constexpr int R = 1024 / (int)sizeof(T);     // rows per tile: 128 (F64) / 64 (C64, DD)
   static constexpr int TG = (sizeof(T) == 8) ? 4 : 8; // thread groups
@@ -163,6 +166,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
     partial[(size_t)blockIdx.x * kMaxSlots + s] = a;
   }
   if (last_block_reduce<CPLX>(ctl, partial, j, nslots, sh_flag)) {
+    if (tid == 0) { ctl->prof_runs += 1u; ctl->prof_units += (unsigned long long)(j + 1 + (MODE != 0 ? 1 : 0)); }
     if (single_rank) gs_decide<T>(ctl, ctl->red, j, ncv, decide_kind);
   }
 }
@@ -193,24 +197,35 @@ static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
   typedef GsCfg<T> C;
   const i64 ntiles = c->n_pad / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * 1024;
-  const size_t budget = 227 * 1024 - C::FIXED_SMEM;
+  const size_t budget = kGsSmemBytes - C::FIXED_SMEM;
   int nstages = (int)(budget / stage_bytes);
   if (nstages > C::MAX_STAGES) nstages = C::MAX_STAGES;
   if (nstages < 2) return set_err(c, GA_ERR_ARG, "gs: too many columns for the shared-memory pipeline");
   const size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
   static bool attr_set = false;
   if (!attr_set) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
     attr_set = true;
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
   if (grid > kMaxCtas) grid = kMaxCtas;
   const T* V = (const T*)c->V;
   T* r = (T*)c->resid;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->prof) {
+    if (c->prof_used + 2 > c->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; GA_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e); }
+    }
+    e0 = c->prof_ev[c->prof_used]; e1 = c->prof_ev[c->prof_used + 1];
+    c->prof_used += 2;
+    GA_CUDA(c, cudaEventRecord(e0, c->stream));
+  }
   k_gs<T, MODE><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
                                                       gate_phase, c->world == 1 ? decide_kind : DK_NONE, c->ncv,
                                                       c->world == 1 ? 1 : 0);
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
   return 0;
 }
 
@@ -249,6 +264,7 @@ int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind) {
     default: k_decide<ddbl><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
   }
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
   return 0;
 }
 

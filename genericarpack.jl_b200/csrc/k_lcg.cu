@@ -95,6 +95,7 @@ int launch_lcg_fill(ga_ctx* c, const i64 iseed[4]) {
     default: k_lcg_fill<ddbl, 1><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->resid, c->n, c->row0, seed, tab); break;
   }
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
   return 0;
 }
 

@@ -79,6 +79,7 @@ static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool 
     default: spmv_launch_t<ddbl>(c, M, x, y, gated); break;
   }
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
   return 0;
 }
 

@@ -133,6 +133,7 @@ static int launch_vq_t(ga_ctx* c, int kplusp, int nout, bool do_resid, int kev) 
                                                     kplusp, nout, (T*)c->resid, do_resid ? 1 : 0, kev, c->ctl,
                                                     c->partial, single ? DK_NORM : DK_NONE, c->ncv, single);
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
   if (do_resid && !single) return launch_decide(c, 0, -1, DK_NORM);
   return 0;
 }

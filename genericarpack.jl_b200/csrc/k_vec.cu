@@ -79,6 +79,7 @@ int launch_normalize(ga_ctx* c, int jcol) {
       break;
   }
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
   return 0;
 }
 
@@ -126,6 +127,7 @@ int launch_norm_resid(ga_ctx* c, int decide_kind) {
     default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
   }
   GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
   if (!single) return launch_decide(c, 0, -1, decide_kind);
   return 0;
 }

@@ -119,6 +119,18 @@ int ga_norm2_resid(ga_ctx* ctx, double* out);
 int ga_get_stats(const ga_ctx* ctx, ga_stats* out);
 int ga_reset_stats(ga_ctx* ctx);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * ga_timer_start/stop: CUDA events recorded on the library's own stream (the stream every kernel of
+ * this context is launched on); stop synchronises and returns milliseconds.
+ * ga_profile(ctx, 1): additionally bracket every Gram-Schmidt sweep launch with CUDA events.
+ * ga_profile_read: gs_ms = summed device time of those launches, gs_runs = launches that were not
+ * phase-gated off, gs_units = n-vector passes they moved (algorithmic bytes = units * n * sizeof(T)),
+ * launches = kernels launched by this context since ga_profile(ctx, *). */
+int ga_timer_start(ga_ctx* ctx);
+int ga_timer_stop(ga_ctx* ctx, double* ms);
+int ga_profile(ga_ctx* ctx, int enable);
+int ga_profile_read(ga_ctx* ctx, double* gs_ms, int64_t* gs_runs, int64_t* gs_units, int64_t* launches);
+
 /* ---- whole solve: symeigs (src/interface.jl:215-290) = dsaupd! + simple_dseupd! -----------------
  * Host control (dsaup2 loop, dsgets, dsconv, dseigt/dstqrb, dsapps bulge chase, dseupd's small
  * eigenproblem) runs on the host inside this call and drives the entry points above; it exists

@@ -85,11 +85,12 @@ def elem_shape(dtype):
 
 
 def to_dtype(x, dtype):
-    """Convert a float/complex numpy array into the oracle's element layout."""
+    """Convert a numpy VECTOR into the oracle's element layout.  Double64: a (n, 2) float64 array
+    is taken as (hi, lo) pairs, a (n,) array is widened to (x, 0)."""
     x = np.asarray(x)
     if dtype == DD:
-        if x.ndim >= 1 and x.shape[-1] == 2 and x.dtype == np.float64 and getattr(x, "_is_dd", False):
-            return np.ascontiguousarray(x)
+        if x.ndim == 2 and x.shape[-1] == 2:
+            return np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros(x.shape + (2,), dtype=np.float64)
         out[..., 0] = x
         return out

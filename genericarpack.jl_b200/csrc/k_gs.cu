@@ -27,14 +27,21 @@ namespace ga {
 constexpr size_t kGsSmemBytes = 224 * 1024;
 
 template <class T> struct GsCfg {
-  static constexpr int R = 1024 / (int)sizeof(T);     // rows per tile: 128 (F64) / 64 (C64, DD)
-  static constexpr int TG = (sizeof(T) == 8) ? 4 : 8; // thread groups
+  // A tile is R rows of (j columns + the vector being orthogonalised).  One TMA bulk copy moves
+  // one column segment of the tile; measured on B200 (profiles/microbench/tma_bulk_rate.cu) the
+  // per-SM bulk-copy issue rate caps 1 KiB copies at ~4.3 TB/s chip-wide while 2 KiB copies reach
+  // ~6.8 TB/s, hence 2 KiB segments: R = 256 rows (F64) / 128 rows (C64, DD).
+  static constexpr int SEG_BYTES = 2048;
+  static constexpr int R = SEG_BYTES / (int)sizeof(T);
+  static constexpr int RPT = 2;                       // adjacent rows per thread
+  static constexpr int ROWL = R / RPT;                // row lanes: 128 (F64) / 64 (C64, DD)
+  static constexpr int TG = (sizeof(T) == 8) ? 4 : 8; // thread groups (column interleave)
   static constexpr int NC = kMaxNcv / TG;             // columns per thread (register accumulators)
-  static constexpr int SLICES = R / 32;
+  static constexpr int SLICES = ROWL / 32;
   static constexpr int CWARPS = SLICES * TG;          // consumer warps
   static constexpr int THREADS = CWARPS * 32 + 32;    // + producer warp
   static constexpr int MAX_STAGES = 8;
-  static constexpr int FIXED_SMEM = kMaxNcv * 16 /*hs*/ + 2 * TG * 1024 /*pr*/ + CWARPS * (NC + 3) * 16 /*red*/ +
+  static constexpr int FIXED_SMEM = kMaxNcv * 16 /*hs*/ + 2 * TG * SEG_BYTES /*pr*/ + CWARPS * (NC + 3) * 16 /*red*/ +
                                     2 * MAX_STAGES * 8 /*mbar*/ + 64;
 };
 
@@ -43,17 +50,18 @@ __global__ void __launch_bounds__(GsCfg<T>::THREADS, 1)
 k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
      int nstages, int gate_phase, int decide_kind, int ncv, int single_rank) {
   typedef GsCfg<T> C;
-  constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS;
+  constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS, RPT = C::RPT, ROWL = C::ROWL;
+  constexpr uint32_t SEG = C::SEG_BYTES;
   constexpr bool CPLX = Elem<T>::is_complex;
 
   if (ctl->status != ST_OK) return;
   if (gate_phase >= 0 && ctl->phase != gate_phase) return;
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t stage_bytes = (uint32_t)(j + 1) * 1024u;
+  const uint32_t stage_bytes = (uint32_t)(j + 1) * SEG;
   unsigned char* p = smem + (size_t)nstages * stage_bytes;
   T* hs = reinterpret_cast<T*>(p);                  p += kMaxNcv * 16;
-  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * 1024;
+  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * SEG;
   double2* redw = reinterpret_cast<double2*>(p);    p += CWARPS * (NC + 3) * 16;
   uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += C::MAX_STAGES * 8;
   uint64_t* empty = reinterpret_cast<uint64_t*>(p); p += C::MAX_STAGES * 8;
@@ -89,43 +97,60 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       const i64 row0 = t * R;
       for (int c = lane; c <= j; c += 32) {
         const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (w + row0);
-        bulk_g2s(st + (size_t)c * 1024, src, 1024u, &full[s]);
+        bulk_g2s(st + (size_t)c * SEG, src, SEG, &full[s]);
       }
     }
   } else {
-    // ---------------- consumers
-    const int slice = warp % SLICES, g = warp / SLICES, row = slice * 32 + lane;
+    // ---------------- consumers: thread (rl, g) owns rows 2rl, 2rl+1 and columns g, g+TG, ...
+    const int slice = warp % SLICES, g = warp / SLICES, rl = slice * 32 + lane;
     int it = 0;
     for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       mbar_wait(&full[s], ph);
       const T* tile = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
-      T rr = tile[(size_t)j * R + row];  // w
-      if (MODE != 0) {
-        T p0 = Elem<T>::zero(), p1 = Elem<T>::zero();
+      T rr[RPT];
 #pragma unroll
-        for (int i = 0; i < NC; i += 2) {
-          const int c0 = g + TG * i, c1 = c0 + TG;
-          if (c0 < j) Elem<T>::sub_mul(p0, tile[(size_t)c0 * R + row], hs[c0]);
-          if (c1 < j) Elem<T>::sub_mul(p1, tile[(size_t)c1 * R + row], hs[c1]);
+      for (int q = 0; q < RPT; ++q) rr[q] = tile[(size_t)j * R + rl * RPT + q];  // w
+      if (MODE != 0) {
+        T p0[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) p0[q] = Elem<T>::zero();
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int c = g + TG * i;
+          if (c >= j) break;
+          const T hc = hs[c];
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) Elem<T>::sub_mul(p0[q], tile[(size_t)c * R + rl * RPT + q], hc);
         }
-        Elem<T>::add(p0, p1);
         T* prb = pr + (size_t)(it & 1) * TG * R;
-        prb[g * R + row] = p0;
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) prb[g * R + rl * RPT + q] = p0[q];
         named_bar_sync(1 + slice, TG * 32);
 #pragma unroll
-        for (int g2 = 0; g2 < TG; ++g2) Elem<T>::add(rr, prb[g2 * R + row]);
-        if (g == 0) r[t * R + row] = rr;
+        for (int g2 = 0; g2 < TG; ++g2) {
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) Elem<T>::add(rr[q], prb[g2 * R + rl * RPT + q]);
+        }
+        if (g == 0) {
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) r[t * R + rl * RPT + q] = rr[q];
+        }
       }
       if (MODE != 2) {
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
           const int c = g + TG * i;
-          if (c < j) Elem<T>::acc_conj_mul(acc[i], tile[(size_t)c * R + row], rr);
+          if (c >= j) break;
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) Elem<T>::acc_conj_mul(acc[i], tile[(size_t)c * R + rl * RPT + q], rr[q]);
         }
       }
-      if (g == 0) nacc.add(rr);
+      if (g == 0) {
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) nacc.add(rr[q]);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -196,7 +221,7 @@ template <class T, int MODE>
 static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
   typedef GsCfg<T> C;
   const i64 ntiles = c->n_pad / C::R;
-  const size_t stage_bytes = (size_t)(j + 1) * 1024;
+  const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
   const size_t budget = kGsSmemBytes - C::FIXED_SMEM;
   int nstages = (int)(budget / stage_bytes);
   if (nstages > C::MAX_STAGES) nstages = C::MAX_STAGES;

@@ -169,12 +169,14 @@ def test_lanczos_parity_small(pkg, syn, O, dtype):
 
 def test_lanczos_identity_restart(pkg, O):
     """test/dsaitr_simple.jl:140-178: identity operator -> invariant subspace after one step ->
-    dgetv0 restart inside the call; resid stays ~0; counters agree with the oracle."""
-    n = 10
+    dgetv0 restart inside the call; resid stays ~0; counters agree with the oracle.  The start
+    vector is ones(16): v = 1/4 exactly and sum(v^2) = 1 exactly in ANY summation order, so the
+    residual is exactly zero on both sides and the restart is taken deterministically."""
+    n = 16
     A = sp.identity(n, format="csr")
     ctx = pkg.Context(pkg.ArpackSimpleOp(A), 3)
     ora = O.Oracle(A, 3)
-    x = np.arange(1.0, n + 1)
+    x = np.ones(n)
     ctx.upload_resid(x)
     ora.resid[:] = x
     ora.rnorm = np.linalg.norm(x)

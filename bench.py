@@ -127,10 +127,15 @@ def run_b200(args):
     pins += [t0_, t1_, t2_]
     op = pkg.ArpackSimpleOp((rowptr, col, val, (r1 - r0, n)))
 
+    plan = None
+    if world > 1:
+        gdist = importlib.import_module(entry.PKG_NAME + ".dist")
+        plan = gdist.halo_plan(csr[1], n, rank, world)
+
     def make_ctx():
         if world == 1:
             return pkg.Context(op, ncv, device=local)
-        ctx = pkg.Context(op, ncv, device=local, rank=rank, world_size=world, n_global=n, row_offset=r0)
+        ctx = pkg.Context(op, ncv, device=local, rank=rank, world_size=world, n_global=n, row_offset=r0, plan=plan)
         import torch
 
         idbuf = np.zeros(128, dtype=np.uint8)

@@ -40,7 +40,7 @@ _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 # every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init",
-    "ga_set_csr", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
+    "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
@@ -97,6 +97,7 @@ def lib():
         L.ga_comm_unique_id.argtypes = [vp]
         L.ga_comm_init.argtypes = [vp, vp]
         L.ga_set_csr.argtypes = [vp, vp, vp, vp]
+        L.ga_set_csr_dist.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
         L.ga_set_normal_csr.argtypes = [vp, i64, i64, vp, vp, vp]
         L.ga_opx.argtypes = [vp, vp, vp]
         L.ga_upload_resid.argtypes = [vp, vp]
@@ -226,7 +227,9 @@ class Context:
     """One device problem instance = the arrays symeigs allocates (src/interface.jl:245-251) on
     the GPU, plus the operator.  Thin, 1:1 over the C ABI; used by the tests and by eigs."""
 
-    def __init__(self, op, ncv, device=0, rank=0, world_size=1, n_global=None, row_offset=0):
+    def __init__(self, op, ncv, device=0, rank=0, world_size=1, n_global=None, row_offset=0, plan=None):
+        """world_size > 1: `op` holds this rank's rows (global columns) and `plan` is the halo plan
+        of dist.halo_plan(...) for them."""
         L = lib()
         self.op = op
         self.dtype = op.dtype
@@ -242,6 +245,12 @@ class Context:
         if op.normal:
             m, n = op.shape
             self._ck(L.ga_set_normal_csr(self.h, m, n, _p(op.rowptr), _p(op.col), _p(op.val)))
+        elif world_size > 1:
+            if plan is None:
+                raise ValueError("a multi-GPU context needs the halo plan (dist.halo_plan)")
+            self.plan = plan
+            self._ck(L.ga_set_csr_dist(self.h, _p(op.rowptr), _p(plan["col_local"]), _p(op.val), int(plan["nhalo"]),
+                                       _p(plan["recv_counts"]), _p(plan["send_counts"]), _p(plan["send_idx"])))
         else:
             self._ck(L.ga_set_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val)))
         self.iseed = np.array([1, 3, 5, 7], dtype=np.int64)  # src/macros.jl:291

@@ -83,11 +83,6 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   CK(cudaMalloc(&c->resid, (size_t)c->n_pad * c->esize));
   CK(cudaMemsetAsync(c->V, 0, (size_t)c->n_pad * ncv * c->esize, c->stream));
   CK(cudaMemsetAsync(c->resid, 0, (size_t)c->n_pad * c->esize, c->stream));
-  if (world_size > 1) {
-    c->xfull_len = c->n_pad * world_size;
-    CK(cudaMalloc(&c->xfull, (size_t)c->xfull_len * c->esize));
-    CK(cudaMemsetAsync(c->xfull, 0, (size_t)c->xfull_len * c->esize, c->stream));
-  }
   CK(cudaMalloc(&c->ctl, sizeof(DevCtl)));
   CK(cudaMemsetAsync(c->ctl, 0, sizeof(DevCtl), c->stream));
   CK(cudaMallocHost(&c->ctl_host, sizeof(DevCtl)));
@@ -111,6 +106,7 @@ void ga_destroy(ga_ctx* c) {
   c->At.free_all();
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev);
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -132,21 +128,38 @@ int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void*
   if (!c || !rowptr || !col || !val) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
   c->op_kind = 0;
-  int rc;
-  if (c->world == 1) {
-    rc = csr_upload(c, c->A, c->n, c->n_global, rowptr, col, val, 0);
-  } else {
-    // remap global column g (owned by rank q = g / blk) to its slot in the gathered vector
-    const i64 blk = (c->n_global + c->world - 1) / c->world;
-    const i64 nnz = rowptr[c->n] - rowptr[0];
-    std::vector<int32_t> cc((size_t)rowptr[c->n]);
-    for (i64 k = rowptr[0]; k < rowptr[0] + nnz; ++k) {
-      const i64 g = col[k], q = g / blk;
-      cc[(size_t)k] = (int32_t)(q * c->n_pad + (g - q * blk));
-    }
-    rc = csr_upload(c, c->A, c->n, c->xfull_len, rowptr, cc.data(), val, 0);
-  }
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "multi-GPU contexts take ga_set_csr_dist (local columns + halo plan)");
+  int rc = csr_upload(c, c->A, c->n, c->n_global, rowptr, col, val, 0);
   if (rc) return rc;
+  c->op_kind = 1;
+  return 0;
+}
+
+// Row-sharded operator: this rank's rows with columns already remapped by the caller:
+//   own column g (row0 <= g < row0 + n_local)  ->  g - row0
+//   remote column                               ->  n_pad + position in the halo
+// where the halo lists the needed remote columns in ascending global order (= grouped by owner
+// rank), recv_counts[q] of them owned by rank q; send_idx (grouped by destination rank, send_counts[q]
+// each) are the LOCAL row indices whose x entries rank q needs from this rank.
+int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, const void* val, int32_t nhalo,
+                    const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx) {
+  if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  c->op_kind = 0;
+  int rc = csr_upload(c, c->A, c->n, c->n_pad + nhalo, rowptr, col_local, val, 0);
+  if (rc) return rc;
+  c->send_counts.assign(send_counts, send_counts + c->world);
+  c->recv_counts.assign(recv_counts, recv_counts + c->world);
+  int nsend = 0, nrecv = 0;
+  for (int q = 0; q < c->world; ++q) { nsend += send_counts[q]; nrecv += recv_counts[q]; }
+  if (nrecv != nhalo || (nsend > 0 && !send_idx)) return set_err(c, GA_ERR_ARG, "halo plan is inconsistent");
+  c->nhalo = nhalo; c->nsend = nsend;
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo);
+  c->send_idx = nullptr; c->send_buf = nullptr; c->halo = nullptr;
+  GA_CUDA(c, cudaMalloc(&c->send_idx, sizeof(int) * (size_t)(nsend > 0 ? nsend : 1)));
+  GA_CUDA(c, cudaMalloc(&c->send_buf, c->esize * (size_t)(nsend > 0 ? nsend : 1)));
+  GA_CUDA(c, cudaMalloc(&c->halo, c->esize * (size_t)(nhalo > 0 ? nhalo : 1)));
+  if (nsend > 0) GA_CUDA(c, cudaMemcpy(c->send_idx, send_idx, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
   c->op_kind = 1;
   return 0;
 }

@@ -5,7 +5,9 @@
 //   - per Gram-Schmidt sweep: the (j+3) 16-byte reduction slots of every rank are ALL-GATHERED and
 //     summed in rank order by every rank (bit-identical results on all ranks, and a correct
 //     double-double sum, which a NCCL sum of hi/lo words would not be);
-//   - per OP*x: the operand vector is all-gathered (general sparsity).
+//   - per OP*x: only the HALO of the operand vector moves: each rank packs the entries its peers'
+//     rows reference and one grouped ncclSend/ncclRecv round delivers them (32 KB per neighbour for
+//     the 2-D Laplacian at n = 16M); the plan comes from the caller (ga_set_csr_dist).
 // libnccl is opened at run time (the one torch already loaded, if any) so the library has no
 // link-time dependency and a single-GPU user never touches NCCL.
 #include <dlfcn.h>
@@ -21,6 +23,10 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -38,8 +44,13 @@ static NcclApi& nccl() {
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
   api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+  api.Send = (decltype(api.Send))dlsym(api.lib, "ncclSend");
+  api.Recv = (decltype(api.Recv))dlsym(api.lib, "ncclRecv");
+  api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Send && api.Recv &&
+           api.GroupStart && api.GroupEnd && api.GetErrorString;
   return api;
 }
 
@@ -87,12 +98,40 @@ int comm_allgather_slots(ga_ctx* c, int nslots) {
   return 0;
 }
 
-// xfull[rank * n_pad_uniform ...] <- every rank's x (all ranks use the same padded block length)
-int comm_allgather_x(ga_ctx* c, const void* x_local) {
+// pack kernel: sendbuf[i] = x[send_idx[i]]
+template <class T>
+__global__ void k_pack(const T* __restrict__ x, const int* __restrict__ idx, T* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[idx[i]];
+}
+
+// Halo exchange of the row-sharded SpMV: every rank packs the entries of its local x that its
+// peers' rows reference, then one grouped ncclSend/ncclRecv round moves them over NVLink.
+int comm_halo_exchange(ga_ctx* c, const void* x_local) {
   if (c->world <= 1) return 0;
   if (!c->nccl_comm) return set_err(c, GA_ERR_COMM, "ga_comm_init was not called");
-  const size_t cnt = (size_t)c->n_pad * (c->esize / 8);
-  GA_NCCL(c, nccl().AllGather(x_local, c->xfull, cnt, ncclFloat64, (ncclComm_t)c->nccl_comm, c->stream));
+  NcclApi& a = nccl();
+  if (c->nsend > 0) {
+    const int threads = 256, blocks = (c->nsend + threads - 1) / threads;
+    if (c->esize == 8) k_pack<double><<<blocks, threads, 0, c->stream>>>((const double*)x_local, c->send_idx, (double*)c->send_buf, c->nsend);
+    else k_pack<double2><<<blocks, threads, 0, c->stream>>>((const double2*)x_local, c->send_idx, (double2*)c->send_buf, c->nsend);
+    GA_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+  }
+  const size_t per = c->esize / 8;
+  GA_NCCL(c, a.GroupStart());
+  size_t soff = 0, roff = 0;
+  for (int q = 0; q < c->world; ++q) {
+    if (c->send_counts[q] > 0)
+      GA_NCCL(c, a.Send((const char*)c->send_buf + soff * c->esize, (size_t)c->send_counts[q] * per, ncclFloat64, q,
+                        (ncclComm_t)c->nccl_comm, c->stream));
+    if (c->recv_counts[q] > 0)
+      GA_NCCL(c, a.Recv((char*)c->halo + roff * c->esize, (size_t)c->recv_counts[q] * per, ncclFloat64, q,
+                        (ncclComm_t)c->nccl_comm, c->stream));
+    soff += (size_t)c->send_counts[q];
+    roff += (size_t)c->recv_counts[q];
+  }
+  GA_NCCL(c, a.GroupEnd());
   return 0;
 }
 

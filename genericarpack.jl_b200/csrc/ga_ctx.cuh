@@ -76,7 +76,7 @@ struct ga_ctx {
   // big arrays (element type T), all n_pad long with zero padding rows
   void* V = nullptr;       // n_pad x ncv, column-major, ld = n_pad
   void* resid = nullptr;   // n_pad   (also holds w = OP v_j before orthogonalisation, like the reference)
-  void* xfull = nullptr;   // multi-GPU: gathered x of length n_global (padded); normal op: scratch of length m
+  void* xfull = nullptr;   // normal operator: scratch vector of length max(m, n)
   ga::i64 xfull_len = 0;
 
   ga::DevCtl* ctl = nullptr;       // device
@@ -93,6 +93,14 @@ struct ga_ctx {
 
   // collectives (NCCL, loaded at run time)
   void* nccl_comm = nullptr;
+  // halo plan of the row-sharded SpMV (multi-GPU): which local entries each peer needs from me
+  // (send_idx grouped by peer) and how many entries I receive from each peer (halo = concatenation
+  // in peer order = ascending global column order).
+  int nhalo = 0, nsend = 0;
+  std::vector<int> send_counts, recv_counts;
+  int* send_idx = nullptr;       // device, nsend local row indices
+  void* send_buf = nullptr;      // device, nsend elements of T
+  void* halo = nullptr;          // device, nhalo elements of T (x entries owned by peers)
 
   // host-side solve state for ga_symeigs_begin/iterate/end
   void* solve = nullptr;

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
                                                               const int* __restrict__ rowptr,
                                                               const int* __restrict__ col,
                                                               const T* __restrict__ val, const T* __restrict__ x,
+                                                              const T* __restrict__ xh, int nsplit,
                                                               T* __restrict__ y, const DevCtl* ctl, int gated) {
   typedef SpmvCfg<T> C;
   if (gated && ctl->status != ST_OK) return;
@@ -32,19 +33,22 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
   const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
   const int k0 = rowptr[r0], k1 = rowptr[r1];
   const int tid = threadIdx.x;
+  // x entry for (remapped) column c: own rows live in x[0, nsplit), halo entries received from
+  // the peers in xh (single GPU: nsplit = INT_MAX, xh unused)
+  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
   if (k1 - k0 <= C::CAP) {
     // coalesced segment pass, 4 independent gathers in flight per thread
     int k = k0 + tid;
     for (; k + 3 * C::THREADS < k1; k += 4 * C::THREADS) {
       const int c0 = col[k], c1 = col[k + C::THREADS], c2 = col[k + 2 * C::THREADS], c3 = col[k + 3 * C::THREADS];
       const T v0 = val[k], v1 = val[k + C::THREADS], v2 = val[k + 2 * C::THREADS], v3 = val[k + 3 * C::THREADS];
-      const T x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+      const T x0 = xat(c0), x1 = xat(c1), x2 = xat(c2), x3 = xat(c3);
       prod[k - k0] = Elem<T>::mul(v0, x0);
       prod[k - k0 + C::THREADS] = Elem<T>::mul(v1, x1);
       prod[k - k0 + 2 * C::THREADS] = Elem<T>::mul(v2, x2);
       prod[k - k0 + 3 * C::THREADS] = Elem<T>::mul(v3, x3);
     }
-    for (; k < k1; k += C::THREADS) prod[k - k0] = Elem<T>::mul(val[k], x[col[k]]);
+    for (; k < k1; k += C::THREADS) prod[k - k0] = Elem<T>::mul(val[k], xat(col[k]));
     __syncthreads();
     for (int r = r0 + tid; r < r1; r += C::THREADS) {
       const int a = rowptr[r] - k0, b = rowptr[r + 1] - k0;
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
   } else {
     // one long row for the whole CTA (r1 == r0 + 1 by construction)
     T s = Elem<T>::zero();
-    for (int k = k0 + tid; k < k1; k += C::THREADS) Elem<T>::add(s, Elem<T>::mul(val[k], x[col[k]]));
+    for (int k = k0 + tid; k < k1; k += C::THREADS) Elem<T>::add(s, Elem<T>::mul(val[k], xat(col[k])));
     prod[tid] = s;
     __syncthreads();
     for (int off = C::THREADS / 2; off > 0; off >>= 1) {
@@ -69,7 +73,9 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
 template <class T>
 static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) {
   if (M.nblk <= 0) return;
+  const bool split = c->world > 1 && &M == &c->A && c->op_kind == 1;
   k_spmv<T><<<M.nblk, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
+                                                          (const T*)c->halo, split ? (int)c->n_pad : 2147483647,
                                                           (T*)y, c->ctl, gated ? 1 : 0);
 }
 static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) {
@@ -83,16 +89,16 @@ static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool 
   return 0;
 }
 
-int comm_allgather_x(ga_ctx* c, const void* x_local);  // ga_comm.cu
+int comm_halo_exchange(ga_ctx* c, const void* x_local);  // ga_comm.cu
 
 // y = OP x for device vectors of the (local) problem size.
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
   const void* xin = x;
   if (c->world > 1) {
-    int rc = comm_allgather_x(c, x);
+    // halo entries of x travel over NVLink (NCCL send/recv) before the local row-segment kernel
+    int rc = comm_halo_exchange(c, x);
     if (rc) return rc;
-    xin = c->xfull;
   }
   if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated);
   // normal operator (single GPU): left: y = A^H (A x); right: y = A (A^H x)

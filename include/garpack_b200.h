@@ -74,6 +74,16 @@ int ga_comm_init(ga_ctx* ctx, const void* id128);
  * ga_set_normal_csr: ArpackNormalOp(A) for svds (src/idonow_ops.jl:216-277): A is m x n CSR,
  * OP = A^H A (m > n, problem size n) or A A^H (m <= n, problem size m). */
 int ga_set_csr(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col, const void* val);
+/* Row-sharded ArpackSimpleOp (world_size > 1).  The caller (who owns rendezvous) remaps the
+ * columns of this rank's rows: own column g -> g - row_offset; remote column -> n_pad + its
+ * position in the halo, n_pad = n_block rounded up to 256 rows, n_block = ceil(n_global/world).
+ * The halo lists the needed remote columns in ascending global order; recv_counts[q] of them are
+ * owned by rank q.  send_idx (grouped by destination, send_counts[q] each) are the LOCAL row
+ * indices whose x entries rank q needs.  Per OP*x the library packs and exchanges exactly these
+ * entries with one grouped ncclSend/ncclRecv round (NVLink), then runs the local SpMV. */
+int ga_set_csr_dist(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col_local, const void* val,
+                    int32_t nhalo, const int32_t* recv_counts, const int32_t* send_counts,
+                    const int32_t* send_idx);
 int ga_set_normal_csr(ga_ctx* ctx, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
                       const void* val);
 /* y = OP*x on host vectors of the problem size (test / svds post-processing helper). */

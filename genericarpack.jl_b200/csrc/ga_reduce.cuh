@@ -139,14 +139,27 @@ __device__ __forceinline__ bool last_block_reduce(DevCtl* ctl, const double2* pa
   __syncthreads();
   if (!*sh_flag) return false;
   __threadfence();
-  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
-    double2 acc = make_double2(0.0, 0.0);
+  // One warp per slot: lane l sums CTAs l, l+32, ... (independent loads in flight), then a fixed
+  // xor-shuffle tree combines the 32 lanes -> same order every run, ~2 us instead of a serial
+  // chain of gridDim.x dependent L2 loads per slot.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < nslots; s += nwarps) {
     const bool cplx = CPLX_DOT && s < ndot;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
-      double2 v = __ldcg(&partial[(size_t)b * kMaxSlots + s]);
-      acc = cplx ? slot_add<true>(acc, v) : slot_add<false>(acc, v);
+    double2 v[8];
+    int cnt = 0;
+    for (unsigned int b = lane; b < gridDim.x && cnt < 8; b += 32) v[cnt++] = __ldcg(&partial[(size_t)b * kMaxSlots + s]);
+    double2 acc = make_double2(0.0, 0.0);
+    for (int i = 0; i < cnt; ++i) acc = cplx ? slot_add<true>(acc, v[i]) : slot_add<false>(acc, v[i]);
+    for (unsigned int b = lane + 256; b < gridDim.x; b += 32) {  // grids larger than 256 CTAs
+      double2 u = __ldcg(&partial[(size_t)b * kMaxSlots + s]);
+      acc = cplx ? slot_add<true>(acc, u) : slot_add<false>(acc, u);
     }
-    ctl->red[s] = acc;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      double2 o = make_double2(shfl_xor_d(acc.x, m), shfl_xor_d(acc.y, m));
+      acc = cplx ? slot_add<true>(acc, o) : slot_add<false>(acc, o);
+    }
+    if (lane == 0) ctl->red[s] = acc;
   }
   if (threadIdx.x == 0) ctl->ticket = 0u;
   __syncthreads();

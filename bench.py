@@ -136,14 +136,7 @@ def run_b200(args):
         if world == 1:
             return pkg.Context(op, ncv, device=local)
         ctx = pkg.Context(op, ncv, device=local, rank=rank, world_size=world, n_global=n, row_offset=r0, plan=plan)
-        import torch
-
-        idbuf = np.zeros(128, dtype=np.uint8)
-        if rank == 0:
-            pkg.comm_unique_id(idbuf)
-        t = torch.from_numpy(idbuf).cuda()
-        dist.broadcast(t, 0)
-        ctx.comm_init(t.cpu().numpy())
+        gdist.setup_comm(ctx, pkg.comm_unique_id, rank, world, fused=not args.nccl_only)
         return ctx
 
     def barrier():
@@ -374,6 +367,7 @@ def main():
     ap.add_argument("--tts", action="store_true", help="also run the full solve (time to solution)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="multi-GPU: NCCL all-gather/send-recv instead of the fused peer-memory path")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

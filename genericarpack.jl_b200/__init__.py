@@ -39,7 +39,7 @@ _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 
 # every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
-    "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init",
+    "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
@@ -97,7 +97,9 @@ def lib():
         L.ga_comm_unique_id.argtypes = [vp]
         L.ga_comm_init.argtypes = [vp, vp]
         L.ga_set_csr.argtypes = [vp, vp, vp, vp]
-        L.ga_set_csr_dist.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+        L.ga_comm_ipc_export.argtypes = [vp, vp]
+        L.ga_comm_ipc_import.argtypes = [vp, vp]
+        L.ga_set_csr_dist.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
         L.ga_set_normal_csr.argtypes = [vp, i64, i64, vp, vp, vp]
         L.ga_opx.argtypes = [vp, vp, vp]
         L.ga_upload_resid.argtypes = [vp, vp]
@@ -250,7 +252,8 @@ class Context:
                 raise ValueError("a multi-GPU context needs the halo plan (dist.halo_plan)")
             self.plan = plan
             self._ck(L.ga_set_csr_dist(self.h, _p(op.rowptr), _p(plan["col_local"]), _p(op.val), int(plan["nhalo"]),
-                                       _p(plan["recv_counts"]), _p(plan["send_counts"]), _p(plan["send_idx"])))
+                                       _p(plan["recv_counts"]), _p(plan["send_counts"]), _p(plan["send_idx"]),
+                                       _p(plan["send_dest_off"])))
         else:
             self._ck(L.ga_set_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val)))
         self.iseed = np.array([1, 3, 5, 7], dtype=np.int64)  # src/macros.jl:291
@@ -364,6 +367,15 @@ class Context:
         buf = np.ascontiguousarray(id128, dtype=np.uint8)
         assert buf.size == 128
         self._ck(lib().ga_comm_init(self.h, _p(buf)))
+
+    def ipc_export(self):
+        buf = np.zeros(128, dtype=np.uint8)
+        self._ck(lib().ga_comm_ipc_export(self.h, _p(buf)))
+        return buf
+
+    def ipc_import(self, all_handles):
+        buf = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        self._ck(lib().ga_comm_ipc_import(self.h, _p(buf)))
 
     # --- measurement hooks
     def timer_start(self):

@@ -9,6 +9,8 @@
 namespace ga {
 int comm_unique_id(void* id128);
 int comm_init(ga_ctx* c, const void* id128);
+int comm_ipc_export(ga_ctx* c, void* out128);
+int comm_ipc_import(ga_ctx* c, const void* all_handles);
 void comm_destroy(ga_ctx* c);
 void solve_free(ga_ctx* c);  // ga_host.cu
 
@@ -122,6 +124,8 @@ int ga_device_sm_count(const ga_ctx* c) { return c ? c->sm_count : 0; }
 
 int ga_comm_unique_id(void* id128) { return comm_unique_id(id128); }
 int ga_comm_init(ga_ctx* c, const void* id128) { return c ? comm_init(c, id128) : GA_ERR_ARG; }
+int ga_comm_ipc_export(ga_ctx* c, void* out128) { return (c && out128) ? comm_ipc_export(c, out128) : GA_ERR_ARG; }
+int ga_comm_ipc_import(ga_ctx* c, const void* all) { return (c && all) ? comm_ipc_import(c, all) : GA_ERR_ARG; }
 
 // ------------------------------------------------------------------ operator
 int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void* val) {
@@ -142,7 +146,8 @@ int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void*
 // rank), recv_counts[q] of them owned by rank q; send_idx (grouped by destination rank, send_counts[q]
 // each) are the LOCAL row indices whose x entries rank q needs from this rank.
 int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, const void* val, int32_t nhalo,
-                    const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx) {
+                    const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx,
+                    const int32_t* send_dest_off) {
   if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
   c->op_kind = 0;
@@ -150,6 +155,8 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
   if (rc) return rc;
   c->send_counts.assign(send_counts, send_counts + c->world);
   c->recv_counts.assign(recv_counts, recv_counts + c->world);
+  if (send_dest_off) c->dest_off.assign(send_dest_off, send_dest_off + c->world);
+  else c->dest_off.assign(c->world, 0);
   int nsend = 0, nrecv = 0;
   for (int q = 0; q < c->world; ++q) { nsend += send_counts[q]; nrecv += recv_counts[q]; }
   if (nrecv != nhalo || (nsend > 0 && !send_idx)) return set_err(c, GA_ERR_ARG, "halo plan is inconsistent");

@@ -81,7 +81,61 @@ int comm_init(ga_ctx* c, const void* id128) {
   return 0;
 }
 
+// ---- peer-memory (cudaIpc) setup for the fused collectives --------------------------------------
+// export: 2 x 64-byte handles (mailbox, halo buffer); import: world x 128 bytes from every rank.
+int comm_ipc_export(ga_ctx* c, void* out128) {
+  GA_CUDA(c, cudaSetDevice(c->device));
+  if (!c->mbox) {
+    GA_CUDA(c, cudaMalloc(&c->mbox, sizeof(Mailbox)));
+    GA_CUDA(c, cudaMemset(c->mbox, 0, sizeof(Mailbox)));
+  }
+  if (!c->halo) {  // a rank without remote columns still needs a valid allocation to export
+    GA_CUDA(c, cudaMalloc(&c->halo, 256));
+  }
+  cudaIpcMemHandle_t h[2];
+  GA_CUDA(c, cudaIpcGetMemHandle(&h[0], c->mbox));
+  GA_CUDA(c, cudaIpcGetMemHandle(&h[1], c->halo));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out128, h, 128);
+  return 0;
+}
+
+int comm_ipc_import(ga_ctx* c, const void* all_handles) {
+  if (c->world <= 1) return 0;
+  if (c->world > kMaxWorld) return set_err(c, GA_ERR_ARG, "fused collectives support at most 8 GPUs (one node)");
+  if (!c->mbox) return set_err(c, GA_ERR_ARG, "call ga_comm_ipc_export first");
+  GA_CUDA(c, cudaSetDevice(c->device));
+  DevComm& hc = c->hostcomm;
+  memset(&hc, 0, sizeof(hc));
+  hc.rank = c->rank; hc.world = c->world;
+  for (int q = 0; q < c->world; ++q) {
+    if (q == c->rank) { hc.peer[q] = c->mbox; hc.peer_halo[q] = c->halo; continue; }
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, (const char*)all_handles + (size_t)q * 128, 128);
+    void *pm = nullptr, *ph = nullptr;
+    GA_CUDA(c, cudaIpcOpenMemHandle(&pm, h[0], cudaIpcMemLazyEnablePeerAccess));
+    GA_CUDA(c, cudaIpcOpenMemHandle(&ph, h[1], cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_mapped[2 * q] = pm; c->ipc_mapped[2 * q + 1] = ph;
+    hc.peer[q] = (Mailbox*)pm; hc.peer_halo[q] = ph;
+  }
+  int off = 0;
+  for (int q = 0; q < c->world; ++q) {
+    hc.send_off[q] = off;
+    off += c->send_counts.empty() ? 0 : c->send_counts[q];
+    hc.dest_off[q] = c->dest_off.empty() ? 0 : c->dest_off[q];
+    hc.recv_counts[q] = c->recv_counts.empty() ? 0 : c->recv_counts[q];
+  }
+  hc.send_off[c->world] = off;
+  if (!c->devcomm) GA_CUDA(c, cudaMalloc(&c->devcomm, sizeof(DevComm)));
+  GA_CUDA(c, cudaMemcpy(c->devcomm, &hc, sizeof(DevComm), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 void comm_destroy(ga_ctx* c) {
+  for (int i = 0; i < 2 * kMaxWorld; ++i)
+    if (c->ipc_mapped[i]) { cudaIpcCloseMemHandle(c->ipc_mapped[i]); c->ipc_mapped[i] = nullptr; }
+  if (c->devcomm) { cudaFree(c->devcomm); c->devcomm = nullptr; }
+  if (c->mbox) { cudaFree(c->mbox); c->mbox = nullptr; }
   if (c->nccl_comm) {
     nccl().CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;

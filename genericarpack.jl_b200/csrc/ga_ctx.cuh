@@ -14,10 +14,11 @@ constexpr int kMaxNcv = GA_MAX_NCV;
 constexpr int kRowPad = 256;  // n_local is padded to a multiple of this many rows (rows beyond n stay 0)
 constexpr int kMaxSlots = kMaxNcv + 4;  // dots + 3 norm accumulators (+1 spare)
 constexpr int kMaxCtas = 1024;
+constexpr int kMaxWorld = 8;  // one NVSwitch node
 
 // Step phases written by the on-device decision logic (dsaitr's flags, src/dsaitr.jl:1324-1447)
 enum : int { PH_DONE = 0, PH_ORTH1 = 1, PH_ORTH2 = 2 };
-enum : int { ST_OK = 0, ST_BREAKDOWN = 1, ST_NUMERIC = 2 };
+enum : int { ST_OK = 0, ST_BREAKDOWN = 1, ST_NUMERIC = 2, ST_COMM = 3 };
 
 // What the last CTA of a reduction kernel does with the reduced slots.
 enum : int {
@@ -40,12 +41,31 @@ struct DevCtl {
   int nrorth, nitref;
   int zero_resid;    // dsaitr set resid = 0, rnorm = 0 (src/dsaitr.jl:1442-1443)
   unsigned int ticket;  // last-block counter
+  unsigned int seq;              // sequence number of the fused cross-GPU slot exchange
+  unsigned int hseq;             // sequence number of the fused halo push
   unsigned int prof_runs;        // executed (not phase-gated) Gram-Schmidt sweep launches
   unsigned long long prof_units; // n-vector passes those launches moved: (j+1) reads + 1 write when updating
   double rnorm[2], wnorm[2], rnorm0[2], rnorm1[2];
   double2 red[kMaxSlots];    // reduced slots of the last reduction kernel
   double2 hbuf[kMaxNcv];     // coefficient vector h / s (element type T, padded to 16 B)
   double2 H[2 * kMaxNcv];    // H(:,1) sub-diagonal [0..ncv), H(:,2) diagonal [ncv..2ncv), real type
+};
+
+// Peer-memory mailbox (one per GPU, IPC-mapped into every peer): the fused compute+collective
+// path writes reduction slots / halo entries straight into the peers' memory over NVLink and
+// signals with a sequence-numbered flag; no NCCL kernel, no extra launch.
+struct Mailbox {
+  double2 slots[2][kMaxWorld][kMaxSlots];   // [parity][source rank][slot]
+  unsigned int flags[2][kMaxWorld];         // [parity][source rank] = seq when the slots are complete
+  unsigned int hflags[kMaxWorld];           // [source rank] = hseq when that peer's halo entries landed
+};
+struct DevComm {
+  int rank, world;
+  Mailbox* peer[kMaxWorld];                 // peer[rank] = own mailbox
+  void* peer_halo[kMaxWorld];               // halo receive buffers of the peers
+  int send_off[kMaxWorld + 1];              // my send list, grouped by destination rank
+  int dest_off[kMaxWorld];                  // where my entries start in peer q's halo buffer
+  int recv_counts[kMaxWorld];
 };
 
 struct CsrDev {
@@ -101,6 +121,12 @@ struct ga_ctx {
   int* send_idx = nullptr;       // device, nsend local row indices
   void* send_buf = nullptr;      // device, nsend elements of T
   void* halo = nullptr;          // device, nhalo elements of T (x entries owned by peers)
+  std::vector<int> dest_off;     // where my entries start in each peer's halo
+  // fused peer-memory collectives (cudaIpc): own mailbox, device-side descriptor, mapped peers
+  ga::Mailbox* mbox = nullptr;
+  ga::DevComm* devcomm = nullptr;   // device copy; nullptr -> NCCL fallback (or single GPU)
+  ga::DevComm hostcomm{};
+  void* ipc_mapped[2 * ga::kMaxWorld] = {nullptr};
 
   // host-side solve state for ga_symeigs_begin/iterate/end
   void* solve = nullptr;

@@ -166,4 +166,68 @@ __device__ __forceinline__ bool last_block_reduce(DevCtl* ctl, const double2* pa
   return true;
 }
 
+// ---- fused cross-GPU reduction of the slots (multi-GPU, peer memory over NVLink) ----------------
+__device__ __forceinline__ void st_sys_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_sys_d2(const double2* p) {
+  double2 v;
+  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_d2(double2* p, double2 v) {
+  asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+// bounded spin: ~seconds; on expiry the status word flags a communication failure instead of hanging
+__device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int want) {
+  for (long long it = 0; it < (1LL << 25); ++it) {
+    if (ld_sys_u32(p) == want) return true;
+    if (it > 1024) __nanosleep(64);
+  }
+  return false;
+}
+
+// Called by all threads of the last CTA after last_block_reduce left this GPU's sums in
+// ctl->red.  Every rank stores its slots into every peer's mailbox (P2P stores), publishes a
+// sequence-numbered flag, waits for the peers' flags and sums the world's slots in rank order,
+// so ctl->red ends up bit-identical on all GPUs.  This is the collective of the Gram-Schmidt
+// sweep, executed inside the sweep kernel itself.
+template <bool CPLX_DOT>
+__device__ __forceinline__ void comm_exchange_slots(DevCtl* ctl, const DevComm* cm, int ndot, int nslots) {
+  __shared__ unsigned int sh_seq;
+  if (threadIdx.x == 0) sh_seq = ctl->seq + 1u;
+  __syncthreads();
+  const unsigned int seq = sh_seq, par = seq & 1u;
+  const int rank = cm->rank, world = cm->world;
+  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
+    const double2 v = ctl->red[s];
+    for (int q = 0; q < world; ++q) st_sys_d2(&cm->peer[q]->slots[par][rank][s], v);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    st_sys_u32(&cm->peer[threadIdx.x]->flags[par][rank], seq);
+    if (!spin_until(&cm->peer[rank]->flags[par][threadIdx.x], seq)) ctl->status = ST_COMM;
+  }
+  __threadfence_system();
+  __syncthreads();
+  const Mailbox* me = cm->peer[rank];
+  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
+    const bool cplx = CPLX_DOT && s < ndot;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int q = 0; q < world; ++q) {
+      const double2 v = ld_sys_d2(&me->slots[par][q][s]);
+      acc = cplx ? slot_add<true>(acc, v) : slot_add<false>(acc, v);
+    }
+    ctl->red[s] = acc;
+  }
+  if (threadIdx.x == 0) ctl->seq = seq;
+  __syncthreads();
+}
+
 }  // namespace ga

@@ -48,7 +48,7 @@ template <class T> struct GsCfg {
 template <class T, int MODE>
 __global__ void __launch_bounds__(GsCfg<T>::THREADS, 1)
 k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
-     int nstages, int gate_phase, int decide_kind, int ncv, int single_rank) {
+     int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm) {
   typedef GsCfg<T> C;
   constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS, RPT = C::RPT, ROWL = C::ROWL;
   constexpr uint32_t SEG = C::SEG_BYTES;
@@ -192,7 +192,8 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
   }
   if (last_block_reduce<CPLX>(ctl, partial, j, nslots, sh_flag)) {
     if (tid == 0) { ctl->prof_runs += 1u; ctl->prof_units += (unsigned long long)(j + 1 + (MODE != 0 ? 1 : 0)); }
-    if (single_rank) gs_decide<T>(ctl, ctl->red, j, ncv, decide_kind);
+    if (cm) comm_exchange_slots<CPLX>(ctl, cm, j, nslots);
+    gs_decide<T>(ctl, ctl->red, j, ncv, decide_kind);
   }
 }
 
@@ -236,6 +237,7 @@ static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
   if (grid > kMaxCtas) grid = kMaxCtas;
   const T* V = (const T*)c->V;
   T* r = (T*)c->resid;
+  const bool fused = c->world == 1 || c->devcomm != nullptr;  // decide inside the sweep kernel
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->prof) {
     if (c->prof_used + 2 > c->prof_ev.size()) {
@@ -246,8 +248,8 @@ static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
   k_gs<T, MODE><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
-                                                      gate_phase, c->world == 1 ? decide_kind : DK_NONE, c->ncv,
-                                                      c->world == 1 ? 1 : 0);
+                                                      gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
+                                                      c->world > 1 ? c->devcomm : nullptr);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
@@ -274,7 +276,7 @@ int launch_gs(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind) {
     default: rc = launch_gs_mode<ddbl>(c, mode, j, gate_phase, decide_kind); break;
   }
   if (rc) return rc;
-  if (c->world > 1) return launch_decide(c, j, gate_phase, decide_kind);
+  if (c->world > 1 && !c->devcomm) return launch_decide(c, j, gate_phase, decide_kind);  // NCCL fallback
   return 0;
 }
 

@@ -8,6 +8,7 @@
 // and a block-wide reduction.  Row blocks are computed once on the host when the matrix is
 // uploaded.  No atomics: results are bit-reproducible.
 #include "ga_decide.cuh"
+#include "ga_reduce.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -26,9 +27,17 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
                                                               const int* __restrict__ col,
                                                               const T* __restrict__ val, const T* __restrict__ x,
                                                               const T* __restrict__ xh, int nsplit,
-                                                              T* __restrict__ y, const DevCtl* ctl, int gated) {
+                                                              T* __restrict__ y, const DevCtl* ctl, int gated,
+                                                              const DevComm* cm) {
   typedef SpmvCfg<T> C;
   if (gated && ctl->status != ST_OK) return;
+  if (cm) {
+    // fused multi-GPU path: the peers' normalisation kernels push our halo entries; wait for their
+    // sequence flags (set after a system-scope fence) before touching xh
+    if (threadIdx.x < (unsigned)cm->world && cm->recv_counts[threadIdx.x] > 0)
+      spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq);
+    __syncthreads();
+  }
   __shared__ T prod[C::CAP];
   const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
   const int k0 = rowptr[r0], k1 = rowptr[r1];
@@ -71,18 +80,19 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
 }
 
 template <class T>
-static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) {
+static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
   if (M.nblk <= 0) return;
   const bool split = c->world > 1 && &M == &c->A && c->op_kind == 1;
   k_spmv<T><<<M.nblk, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
                                                           (const T*)c->halo, split ? (int)c->n_pad : 2147483647,
-                                                          (T*)y, c->ctl, gated ? 1 : 0);
+                                                          (T*)y, c->ctl, gated ? 1 : 0,
+                                                          (split && wait_halo) ? c->devcomm : nullptr);
 }
-static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) {
+static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo = false) {
   switch (c->dtype) {
-    case GA_F64: spmv_launch_t<double>(c, M, x, y, gated); break;
-    case GA_C64: spmv_launch_t<cdbl>(c, M, x, y, gated); break;
-    default: spmv_launch_t<ddbl>(c, M, x, y, gated); break;
+    case GA_F64: spmv_launch_t<double>(c, M, x, y, gated, wait_halo); break;
+    case GA_C64: spmv_launch_t<cdbl>(c, M, x, y, gated, wait_halo); break;
+    default: spmv_launch_t<ddbl>(c, M, x, y, gated, wait_halo); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
@@ -95,12 +105,14 @@ int comm_halo_exchange(ga_ctx* c, const void* x_local);  // ga_comm.cu
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
   const void* xin = x;
-  if (c->world > 1) {
-    // halo entries of x travel over NVLink (NCCL send/recv) before the local row-segment kernel
+  // Lanczos steps (gated) on the fused path: the normalisation kernel already pushed the halo and
+  // the SpMV waits on the peers' flags.  Otherwise the halo travels by NCCL send/recv first.
+  const bool fused = gated && c->world > 1 && c->devcomm != nullptr;
+  if (c->world > 1 && !fused) {
     int rc = comm_halo_exchange(c, x);
     if (rc) return rc;
   }
-  if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated);
+  if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated, fused);
   // normal operator (single GPU): left: y = A^H (A x); right: y = A (A^H x)
   if (c->normal_left) {
     int rc = spmv_launch(c, c->A, xin, c->xfull, gated);

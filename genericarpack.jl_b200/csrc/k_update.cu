@@ -25,7 +25,7 @@ template <class T> struct VqCfg {
 template <class T>
 __global__ void __launch_bounds__(VqCfg<T>::THREADS)
 k_vq(T* V, i64 ld, i64 ntiles, const typename Elem<T>::real_t* __restrict__ Qg, int ldq, int kplusp, int nout,
-     T* resid, int do_resid, int kev, DevCtl* ctl, double2* partial, int decide_kind, int ncv, int single_rank) {
+     T* resid, int do_resid, int kev, DevCtl* ctl, double2* partial, int decide_kind, int ncv, const DevComm* cm) {
   typedef typename Elem<T>::real_t TR;
   typedef VqCfg<T> C;
   constexpr int R = C::R, OG = C::OG, OB = C::OB;
@@ -104,7 +104,8 @@ k_vq(T* V, i64 ld, i64 ntiles, const typename Elem<T>::real_t* __restrict__ Qg, 
     partial[(size_t)blockIdx.x * kMaxSlots + tid] = acc;
   }
   if (last_block_reduce<false>(ctl, partial, 0, 3, &sh_flag)) {
-    if (single_rank) gs_decide<T>(ctl, ctl->red, 0, ncv, decide_kind);
+    if (cm) comm_exchange_slots<false>(ctl, cm, 0, 3);
+    gs_decide<T>(ctl, ctl->red, 0, ncv, decide_kind);
   }
 }
 
@@ -128,10 +129,10 @@ static int launch_vq_t(ga_ctx* c, int kplusp, int nout, bool do_resid, int kev) 
   if (grid > ntiles) grid = ntiles;
   if (grid > kMaxCtas) grid = kMaxCtas;
   if (grid < 1) grid = 1;
-  const int single = c->world == 1 ? 1 : 0;
+  const bool single = c->world == 1 || c->devcomm != nullptr;  // decide inside the kernel
   k_vq<T><<<(int)grid, C::THREADS, smem, c->stream>>>((T*)c->V, c->n_pad, ntiles, (const TR*)c->qdev, c->ncv_pad,
                                                     kplusp, nout, (T*)c->resid, do_resid ? 1 : 0, kev, c->ctl,
-                                                    c->partial, single ? DK_NORM : DK_NONE, c->ncv, single);
+                                                    c->partial, single ? DK_NORM : DK_NONE, c->ncv, c->world > 1 ? c->devcomm : nullptr);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (do_resid && !single) return launch_decide(c, 0, -1, DK_NORM);

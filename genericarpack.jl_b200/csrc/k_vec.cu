@@ -23,9 +23,29 @@ __device__ __forceinline__ void lascl_factor(TR cfrom, TR cto, TR& mul, TR& cfro
   }
 }
 
+template <class T, class TR>
+__device__ __forceinline__ T scaled_by_inv_norm(T x, TR rnorm, TR temp1, bool safe) {
+  if (safe) return Elem<T>::mul_real(x, temp1);                  // src/dsaitr.jl:1099-1101
+  TR mul, cf, ct; bool done;                                       // :1103 (_scale_from_to)
+  lascl_factor<TR>(rnorm, Real<TR>::from(1.0), mul, cf, ct, done);
+  x = Elem<T>::mul_real(x, mul);
+  int guard = 0;
+  while (!done && guard++ < 8) {
+    TR f = cf, t = ct;
+    lascl_factor<TR>(f, t, mul, cf, ct, done);
+    x = Elem<T>::mul_real(x, mul);
+  }
+  return x;
+}
+
+// Multi-GPU fused path: besides v_j the kernel PUSHES the entries of v_j that the peers' rows
+// reference straight into the peers' halo buffers (P2P stores over NVLink) and the last CTA raises
+// a sequence flag in each peer's mailbox; the peers' SpMV waits on that flag.  No pack kernel, no
+// NCCL send/recv on the per-step path.
 template <class T>
 __global__ void __launch_bounds__(256) k_normalize(T* __restrict__ vj, const T* __restrict__ resid, i64 n,
-                                                   DevCtl* ctl, int jstep) {
+                                                   DevCtl* ctl, int jstep, const DevComm* cm,
+                                                   const int* __restrict__ send_idx) {
   typedef typename Elem<T>::real_t TR;
   if (ctl->status != ST_OK) return;
   const TR rnorm = load_real<TR>(ctl->rnorm);
@@ -36,26 +56,33 @@ __global__ void __launch_bounds__(256) k_normalize(T* __restrict__ vj, const T* 
     }
     return;
   }
+  const unsigned int hseq = cm ? ctl->hseq + 1u : 0u;
   const i64 stride = (i64)gridDim.x * blockDim.x;
-  if (rnorm >= Real<TR>::floatmin()) {
-    const TR temp1 = Real<TR>::from(1.0) / rnorm;  // :1099
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-      vj[i] = Elem<T>::mul_real(resid[i], temp1);
-  } else {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      T x = resid[i];
-      TR mul, cf, ct; bool done;
-      lascl_factor<TR>(rnorm, Real<TR>::from(1.0), mul, cf, ct, done);
-      x = Elem<T>::mul_real(x, mul);
-      int guard = 0;
-      while (!done && guard++ < 8) {
-        TR f = cf, t = ct;
-        lascl_factor<TR>(f, t, mul, cf, ct, done);
-        x = Elem<T>::mul_real(x, mul);
-      }
-      vj[i] = x;
-    }
+  const bool safe = rnorm >= Real<TR>::floatmin();
+  const TR temp1 = Real<TR>::from(1.0) / rnorm;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    vj[i] = scaled_by_inv_norm<T, TR>(resid[i], rnorm, temp1, safe);
+  if (!cm) return;
+  const int nsend = cm->send_off[cm->world];
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nsend; i += stride) {
+    int q = 0;
+    while (i >= cm->send_off[q + 1]) ++q;
+    T* dst = reinterpret_cast<T*>(cm->peer_halo[q]) + cm->dest_off[q] + (i - cm->send_off[q]);
+    *dst = scaled_by_inv_norm<T, TR>(resid[send_idx[i]], rnorm, temp1, safe);
   }
+  __shared__ int sh_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(&ctl->ticket, 1u);
+    sh_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < cm->world && cm->send_off[threadIdx.x + 1] > cm->send_off[threadIdx.x])
+    st_sys_u32(&cm->peer[threadIdx.x]->hflags[cm->rank], hseq);
+  if (threadIdx.x == 0) { ctl->hseq = hseq; ctl->ticket = 0u; }
 }
 
 int launch_normalize(ga_ctx* c, int jcol) {
@@ -64,18 +91,19 @@ int launch_normalize(ga_ctx* c, int jcol) {
   const i64 maxb = (i64)c->sm_count * 8;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
+  const DevComm* cm = c->world > 1 ? c->devcomm : nullptr;
   switch (c->dtype) {
     case GA_F64:
       k_normalize<double><<<(int)blocks, threads, 0, c->stream>>>((double*)c->V + (size_t)jcol * c->n_pad,
-                                                                 (const double*)c->resid, c->n, c->ctl, jcol + 1);
+                                                                 (const double*)c->resid, c->n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
     case GA_C64:
       k_normalize<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)c->V + (size_t)jcol * c->n_pad,
-                                                               (const cdbl*)c->resid, c->n, c->ctl, jcol + 1);
+                                                               (const cdbl*)c->resid, c->n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
     default:
       k_normalize<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->V + (size_t)jcol * c->n_pad,
-                                                               (const ddbl*)c->resid, c->n, c->ctl, jcol + 1);
+                                                               (const ddbl*)c->resid, c->n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
   }
   GA_CUDA(c, cudaGetLastError());
@@ -87,7 +115,7 @@ int launch_normalize(ga_ctx* c, int jcol) {
 // src/dsaup2.jl:1414, src/dgetv0.jl:630) ------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(256) k_norm(const T* __restrict__ x, i64 n, DevCtl* ctl, double2* partial,
-                                              int decide_kind, int ncv, int single_rank) {
+                                              int decide_kind, int ncv, const DevComm* cm) {
   if (ctl->status != ST_OK && ctl->status != ST_BREAKDOWN) return;
   __shared__ double2 sw[8 * 3];
   __shared__ int sh_flag;
@@ -109,7 +137,8 @@ __global__ void __launch_bounds__(256) k_norm(const T* __restrict__ x, i64 n, De
     partial[(size_t)blockIdx.x * kMaxSlots + threadIdx.x] = acc;
   }
   if (last_block_reduce<false>(ctl, partial, 0, 3, &sh_flag)) {
-    if (single_rank) gs_decide<T>(ctl, ctl->red, 0, ncv, decide_kind);
+    if (cm) comm_exchange_slots<false>(ctl, cm, 0, 3);
+    gs_decide<T>(ctl, ctl->red, 0, ncv, decide_kind);
   }
 }
 
@@ -119,12 +148,13 @@ int launch_norm_resid(ga_ctx* c, int decide_kind) {
   const i64 maxb = (i64)c->sm_count * 4;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
-  const int single = c->world == 1 ? 1 : 0;
+  const bool single = c->world == 1 || c->devcomm != nullptr;  // decide inside the kernel
   const int dk = single ? decide_kind : DK_NONE;
+  const DevComm* cm = c->world > 1 ? c->devcomm : nullptr;
   switch (c->dtype) {
-    case GA_F64: k_norm<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
-    case GA_C64: k_norm<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
-    default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, single); break;
+    case GA_F64: k_norm<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, cm); break;
+    case GA_C64: k_norm<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, cm); break;
+    default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, cm); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;

@@ -52,11 +52,13 @@ def halo_plan(col, n, rank, world, all_gather_object=None):
             return out
     needs = all_gather_object(need)
     send_counts = np.zeros(world, dtype=np.int32)
+    send_dest_off = np.zeros(world, dtype=np.int32)   # where my entries start in rank q's halo
     send_idx = []
     for q in range(world):
         nq = np.asarray(needs[q], dtype=np.int64)
         mine = nq[(nq >= r0) & (nq < r1)]
         send_counts[q] = len(mine)
+        send_dest_off[q] = int(np.searchsorted(nq, r0))
         send_idx.append((mine - r0).astype(np.int32))
     send_idx = np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.int32)
     # column remap: own -> g - r0 ; remote -> n_pad + position in `need`
@@ -65,9 +67,26 @@ def halo_plan(col, n, rank, world, all_gather_object=None):
     col_local[own] = col[own] - r0
     col_local[~own] = n_pad + np.searchsorted(need, col[~own])
     return {"col_local": np.ascontiguousarray(col_local, dtype=np.int32), "nhalo": int(len(need)),
-            "recv_counts": recv_counts, "send_counts": send_counts,
+            "recv_counts": recv_counts, "send_counts": send_counts, "send_dest_off": send_dest_off,
             "send_idx": np.ascontiguousarray(send_idx, dtype=np.int32), "need": need, "n_pad": n_pad,
             "row_range": (r0, r1)}
+
+
+def setup_comm(ctx, comm_unique_id, rank, world, fused=True):
+    """Rendezvous for one context (torch.distributed must be initialised): broadcast the NCCL unique
+    id, then (fused=True) all-gather the cudaIpc handles so that the per-step collectives run inside
+    the compute kernels over NVSwitch peer memory.  `comm_unique_id` = the package's function."""
+    import torch.distributed as dist
+
+    ids = [comm_unique_id().tobytes() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(np.frombuffer(ids[0], dtype=np.uint8).copy())
+    if fused:
+        mine = ctx.ipc_export().tobytes()
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        ctx.ipc_import(np.frombuffer(b"".join(allh), dtype=np.uint8).copy())
+    return ctx
 
 
 def emulate_sharded_spmv(csr_rows, plan, x_blocks, rank):

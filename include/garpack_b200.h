@@ -67,6 +67,14 @@ int ga_device_sm_count(const ga_ctx* ctx);
  * Collectives are then issued by the library on its own stream (NCCL over NVLink 5 / NVSwitch). */
 int ga_comm_unique_id(void* id128);
 int ga_comm_init(ga_ctx* ctx, const void* id128);
+/* Fused compute+collective path over NVSwitch peer memory (optional, <= 8 GPUs of one node):
+ * every rank exports 128 bytes (two cudaIpc handles: its mailbox and its halo buffer; call after
+ * ga_set_csr_dist), the caller all-gathers them, every rank imports the world's handles.  From then
+ * on the Gram-Schmidt sweep kernel itself writes its reduction slots into the peers' mailboxes and
+ * the normalisation kernel pushes the halo entries into the peers' halo buffers (P2P stores +
+ * sequence flags); NCCL is no longer on the per-step path. */
+int ga_comm_ipc_export(ga_ctx* ctx, void* out128);
+int ga_comm_ipc_import(ga_ctx* ctx, const void* all_handles /* world x 128 bytes */);
 
 /* ---- operator (OP*x of dsaitr step 3: src/dsaitr.jl:1120-1133 -> opx!, src/idonow_ops.jl:74-76)
  * ga_set_csr: ArpackSimpleOp(A) (src/idonow_ops.jl:115-123).  Full (both triangles) CSR of the
@@ -83,7 +91,8 @@ int ga_set_csr(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col, const voi
  * entries with one grouped ncclSend/ncclRecv round (NVLink), then runs the local SpMV. */
 int ga_set_csr_dist(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col_local, const void* val,
                     int32_t nhalo, const int32_t* recv_counts, const int32_t* send_counts,
-                    const int32_t* send_idx);
+                    const int32_t* send_idx, const int32_t* send_dest_off /* [world]: where my entries
+                    start in peer q's halo; may be NULL when the fused path is not used */);
 int ga_set_normal_csr(ga_ctx* ctx, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
                       const void* val);
 /* y = OP*x on host vectors of the problem size (test / svds post-processing helper). */

@@ -38,12 +38,8 @@ def main():
     op = pkg.ArpackSimpleOp((csr[0], csr[1], csr[2], (r1 - r0, n)))
     plan = gd.halo_plan(csr[1], n, rank, world)
     ctx = pkg.Context(op, ncv, device=local, rank=rank, world_size=world, n_global=n, row_offset=r0, plan=plan)
-    idbuf = np.zeros(128, dtype=np.uint8)
-    if rank == 0:
-        pkg.comm_unique_id(idbuf)
-    t = torch.from_numpy(idbuf).cuda()
-    dist.broadcast(t, 0)
-    ctx.comm_init(t.cpu().numpy())
+    fused = os.environ.get("GA_NCCL_ONLY", "0") != "1"
+    gd.setup_comm(ctx, pkg.comm_unique_id, rank, world, fused=fused)
     ok = {}
     # 1. start vector: every shard is its slice of the reference's dlarnv stream, bit for bit
     ierr, rn = ctx.getv0()
@@ -76,7 +72,7 @@ def main():
         single = pkg.eigs(pkg.ArpackSimpleOp(syn.laplacian2d(m)), nev, ncv=ncv, device=local)
         ok["vs_single_gpu_values"] = bool(np.max(np.abs(single.values - values) / np.abs(values)) <= 1e-12)
         ok["vs_single_gpu_restarts"] = bool(abs(int(single.iparam[2]) - int(iparam[2])) <= max(2, int(iparam[2]) // 8))  # exactly double eigenvalues: count is sensitive to summation order
-        out = {"world": world, "n": n, "checks": ok, "restarts": int(iparam[2]), "restarts_single_gpu": int(single.iparam[2]),
+        out = {"world": world, "n": n, "fused_peer_memory": fused, "checks": ok, "restarts": int(iparam[2]), "restarts_single_gpu": int(single.iparam[2]),
                "nopx": int(ctx.stats()["nopx"]), "halo": int(plan["nhalo"])}
         print(json.dumps(out))
     allok = [None] * world

@@ -162,7 +162,8 @@ def run_b200(args):
     for _ in range(args.warmup):
         assert ctx.symeigs_iterate(1) == 0
     ctx.profile(True)
-    nopx0 = ctx.stats()["nopx"]
+    st0 = ctx.stats()
+    nopx0 = st0["nopx"]
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     ctx.timer_start()
@@ -266,7 +267,9 @@ def run_b200(args):
                                    % (nev, ncv, m, m, n, nnz_global, world),
                        "step": "one implicit-restart cycle (np Lanczos steps + tridiagonal host work + V*Q)",
                        "lanczos_steps_timed": int(lanczos_steps), "l2": "inputs larger than L2 (V is %.1f GB per GPU)" % (n_pad * ncv * 8 / 1e9),
-                       "nrorth": int(st["nrorth"]), "nitref": int(st["nitref"])},
+                       "nrorth": int(st["nrorth"] - st0["nrorth"]), "nitref": int(st["nitref"] - st0["nitref"]),
+                       "ms_per_cycle_breakdown": {k: round((st[k] - st0[k]) * 1e3 / max(done_steps, 1), 3)
+                                                  for k in ("taitr", "tapps", "teigt", "tgets", "tconv")}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if tts is not None:

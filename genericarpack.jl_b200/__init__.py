@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_debug_trace", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -117,6 +117,7 @@ def lib():
         L.ga_timer_stop.argtypes = [vp, vp]
         L.ga_profile.argtypes = [vp, i32]
         L.ga_profile_read.argtypes = [vp, vp, vp, vp, vp]
+        L.ga_debug_trace.argtypes = [vp, vp]
         L.ga_symeigs.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
         L.ga_symeigs_begin.argtypes = [vp, i32, i32, vp, i32, vp]
         L.ga_symeigs_iterate.argtypes = [vp, i32]
@@ -385,6 +386,14 @@ class Context:
         ms = ctypes.c_double(0.0)
         self._ck(lib().ga_timer_stop(self.h, ctypes.byref(ms)))
         return ms.value
+
+    def debug_trace(self, read=False):
+        if not read:
+            self._ck(lib().ga_debug_trace(self.h, None))
+            return None
+        out = np.zeros(16, dtype=np.uint64)
+        self._ck(lib().ga_debug_trace(self.h, _p(out)))
+        return out
 
     def profile(self, enable=True):
         self._ck(lib().ga_profile(self.h, int(enable)))

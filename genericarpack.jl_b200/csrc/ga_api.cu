@@ -108,7 +108,7 @@ void ga_destroy(ga_ctx* c) {
   c->At.free_all();
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev);
-  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo);
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -161,7 +161,7 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
   for (int q = 0; q < c->world; ++q) { nsend += send_counts[q]; nrecv += recv_counts[q]; }
   if (nrecv != nhalo || (nsend > 0 && !send_idx)) return set_err(c, GA_ERR_ARG, "halo plan is inconsistent");
   c->nhalo = nhalo; c->nsend = nsend;
-  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo);
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace);
   c->send_idx = nullptr; c->send_buf = nullptr; c->halo = nullptr;
   GA_CUDA(c, cudaMalloc(&c->send_idx, sizeof(int) * (size_t)(nsend > 0 ? nsend : 1)));
   GA_CUDA(c, cudaMalloc(&c->send_buf, c->esize * (size_t)(nsend > 0 ? nsend : 1)));
@@ -515,6 +515,22 @@ int ga_profile_read(ga_ctx* c, double* gs_ms, int64_t* gs_runs, int64_t* gs_unit
   if (gs_runs) *gs_runs = (int64_t)c->ctl_host->prof_runs;
   if (gs_units) *gs_units = (int64_t)c->ctl_host->prof_units;
   if (launches) *launches = (int64_t)c->launches;
+  return 0;
+}
+
+// debug: enable (out == NULL) or read back (out = 16 x uint64 ns) the in-kernel timeline of the
+// most recent Gram-Schmidt sweep launch
+int ga_debug_trace(ga_ctx* c, uint64_t* out16) {
+  if (!c) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  if (!c->trace) {
+    GA_CUDA(c, cudaMalloc(&c->trace, 16 * sizeof(unsigned long long)));
+    GA_CUDA(c, cudaMemset(c->trace, 0, 16 * sizeof(unsigned long long)));
+  }
+  if (out16) {
+    GA_CUDA(c, cudaStreamSynchronize(c->stream));
+    GA_CUDA(c, cudaMemcpy(out16, c->trace, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

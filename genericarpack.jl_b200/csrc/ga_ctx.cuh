@@ -139,6 +139,7 @@ struct ga_ctx {
   size_t prof_used = 0;
   long long launches = 0;            // kernels launched by this context
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  unsigned long long* trace = nullptr;  // device, 16 globaltimer samples of the last traced sweep (debug)
   std::string err;
 };
 

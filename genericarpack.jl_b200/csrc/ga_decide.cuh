@@ -33,37 +33,57 @@ __device__ void gs_decide(DevCtl* ctl, const double2* red, int j, int ncv, int k
   T* hb = hbuf_ptr<T>(ctl);
   TR* H = H_ptr<TR>(ctl);
   const int jc = j - 1;
-  __shared__ double sh_prev[2];
+  // Everything the scalar logic needs is fetched by different threads at once (one global-memory
+  // latency instead of a chain of dependent loads in thread 0; this sits on the critical path
+  // between two sweeps).
+  __shared__ double sh[16];
+  __shared__ int sh_rstart;
   if (kind == DK_NONE) return;
-  // the previous coefficient vector's j-th entry is needed before hbuf is overwritten
-  if (threadIdx.x == 0) {
-    TR hj = (j >= 1 && kind != DK_NORM) ? Elem<T>::re(hb[jc < 0 ? 0 : jc]) : TR(0.0);
-    store_real(sh_prev, hj);
+  {
+    const int t = threadIdx.x;
+    if (t == 0) {  // the previous coefficient vector's j-th entry, before hbuf is overwritten
+      TR hj = (j >= 1 && kind != DK_NORM) ? Elem<T>::re(hb[jc < 0 ? 0 : jc]) : TR(0.0);
+      store_real(&sh[0], hj);
+    } else if (t == 1) {
+      sh_rstart = ctl->rstart_j;
+    } else if (t == 2) {
+      sh[2] = ctl->rnorm[0]; sh[3] = ctl->rnorm[1];
+    } else if (t == 3) {
+      sh[4] = ctl->wnorm[0]; sh[5] = ctl->wnorm[1];
+    } else if (t == 4) {
+      TR hd = (j >= 1 && (kind == DK_ORTH1 || kind == DK_ORTH2)) ? H[ncv + jc] : TR(0.0);
+      store_real(&sh[6], hd);
+    } else if (t >= 5 && t < 8) {
+      const double2 v = red[j + (t - 5)];
+      sh[8 + 2 * (t - 5)] = v.x; sh[9 + 2 * (t - 5)] = v.y;
+    }
   }
   __syncthreads();
-  const ddbl nrm_dd = norm_finalize(ddbl(red[j].x, red[j].y), ddbl(red[j + 1].x, red[j + 1].y),
-                                    ddbl(red[j + 2].x, red[j + 2].y));
-  const TR nrm = real_from_dd<TR>(nrm_dd);
   bool take_dots = false;
   if (threadIdx.x == 0) {
-    const TR hj = load_real<TR>(sh_prev);
-    const bool first = (jc == 0) || (ctl->rstart_j == j);
+    const ddbl nrm_dd = norm_finalize(ddbl(sh[8], sh[9]), ddbl(sh[10], sh[11]), ddbl(sh[12], sh[13]));
+    const TR nrm = real_from_dd<TR>(nrm_dd);
+    const TR hj = load_real<TR>(&sh[0]);
+    const TR rnorm_in = load_real<TR>(&sh[2]);
+    const TR wnorm_in = load_real<TR>(&sh[4]);
+    const TR hdiag_in = load_real<TR>(&sh[6]);
+    const bool first = (jc == 0) || (sh_rstart == j);
     switch (kind) {
       case DK_DOT:  // wnorm = ||OP v_j|| (:1208); h = V_j^T w (:1227)
         store_real(ctl->wnorm, nrm);
         break;
       case DK_CGS: {  // r = w - V h done (:1240)
         H[ncv + jc] = hj;                                             // :1243
-        H[jc] = first ? TR(0.0) : load_real<TR>(ctl->rnorm);          // :1259-1263
+        H[jc] = first ? TR(0.0) : rnorm_in;                          // :1259-1263
         store_real(ctl->rnorm, nrm);                                  // :1304
-        const TR wn = load_real<TR>(ctl->wnorm);
+        const TR wn = wnorm_in;
         if (nrm > TR(0.717) * wn) ctl->phase = PH_DONE;               // :1324
         else { ctl->phase = PH_ORTH1; ctl->nrorth += 1; }             // :1328,1335
       } break;
       case DK_ORTH1: {  // r -= V s done (:1363)
         if (first) H[jc] = TR(0.0);                                   // :1364-1366
-        H[ncv + jc] = H[ncv + jc] + hj;                               // :1367
-        const TR rn = load_real<TR>(ctl->rnorm);
+        H[ncv + jc] = hdiag_in + hj;                                  // :1367
+        const TR rn = rnorm_in;
         store_real(ctl->rnorm1, nrm);                                 // :1410
         store_real(ctl->rnorm, nrm);                                  // :1425 / :1431
         if (nrm > TR(0.717) * rn) ctl->phase = PH_DONE;               // :1424
@@ -71,8 +91,8 @@ __device__ void gs_decide(DevCtl* ctl, const double2* red, int j, int ncv, int k
       } break;
       case DK_ORTH2: {
         if (first) H[jc] = TR(0.0);
-        H[ncv + jc] = H[ncv + jc] + hj;
-        const TR rn = load_real<TR>(ctl->rnorm);
+        H[ncv + jc] = hdiag_in + hj;
+        const TR rn = rnorm_in;
         store_real(ctl->rnorm1, nrm);
         if (nrm > TR(0.717) * rn) store_real(ctl->rnorm, nrm);
         else {                                                        // :1440-1446

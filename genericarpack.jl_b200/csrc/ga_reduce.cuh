@@ -116,6 +116,17 @@ __device__ __forceinline__ double2 warp_sum_slot(cdbl v) {  // (re, im), plain t
   return make_double2(v.re, v.im);
 }
 
+// In-warp tree for the dot accumulators: plain adds for double/complex (32 partials of equal
+// magnitude; the compensated arithmetic is kept for the cross-warp / cross-CTA / cross-GPU
+// levels where it is free), double-double adds for Double64.
+__device__ __forceinline__ double2 warp_sum_slot_fast(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
+  return make_double2(v, 0.0);
+}
+__device__ __forceinline__ double2 warp_sum_slot_fast(cdbl v) { return warp_sum_slot(v); }
+__device__ __forceinline__ double2 warp_sum_slot_fast(ddbl v) { return warp_sum_slot(v); }
+
 // slot kinds: pair = (hi,lo) compensated sum; cplx = independent (re,im)
 template <bool CPLX>
 __device__ __forceinline__ double2 slot_add(double2 a, double2 b) {

@@ -48,8 +48,15 @@ template <class T> struct GsCfg {
 template <class T, int MODE>
 __global__ void __launch_bounds__(GsCfg<T>::THREADS, 1)
 k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
-     int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm) {
+     int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm, unsigned long long* trace) {
   typedef GsCfg<T> C;
+#define GA_TRACE(slot, cond)                                                        \
+  if (trace != nullptr && (cond)) {                                                 \
+    unsigned long long t_;                                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
+    trace[slot] = t_;                                                               \
+  }
+  GA_TRACE(0, blockIdx.x == 0 && threadIdx.x == 0)
   constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS, RPT = C::RPT, ROWL = C::ROWL;
   constexpr uint32_t SEG = C::SEG_BYTES;
   constexpr bool CPLX = Elem<T>::is_complex;
@@ -77,6 +84,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
     for (int c = tid; c < j; c += blockDim.x) hs[c] = hb[c];
   }
   __syncthreads();
+  GA_TRACE(1, blockIdx.x == 0 && threadIdx.x == 0)
 
   T acc[NC];
 #pragma unroll
@@ -108,6 +116,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       const int s = it % nstages;
       const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       mbar_wait(&full[s], ph);
+      GA_TRACE(2, blockIdx.x == 0 && tid == 0 && it == 0)
       const T* tile = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
       T rr[RPT];
 #pragma unroll
@@ -154,12 +163,15 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
-    // warp-level reduction of this warp's accumulators
+    GA_TRACE(3, blockIdx.x == 0 && tid == 0)
+    // warp-level reduction of this warp's accumulators (only the columns this group owns)
     if (MODE != 2) {
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
-        double2 sl = warp_sum_slot(acc[i]);
-        if (lane == 0) redw[warp * (NC + 3) + i] = sl;
+        if (g + TG * i < j) {
+          double2 sl = warp_sum_slot_fast(acc[i]);
+          if (lane == 0) redw[warp * (NC + 3) + i] = sl;
+        }
       }
     }
     if (g == 0) {
@@ -171,7 +183,9 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       }
     }
   }
+  GA_TRACE(4, blockIdx.x == 0 && tid == 0)
   __syncthreads();
+  GA_TRACE(5, blockIdx.x == 0 && tid == 0)
   // CTA partials -> global
   const int nslots = j + 3;
   for (int s = tid; s < nslots; s += blockDim.x) {
@@ -191,10 +205,13 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
     partial[(size_t)blockIdx.x * kMaxSlots + s] = a;
   }
   if (last_block_reduce<CPLX>(ctl, partial, j, nslots, sh_flag)) {
+    GA_TRACE(6, tid == 0)
     if (tid == 0) { ctl->prof_runs += 1u; ctl->prof_units += (unsigned long long)(j + 1 + (MODE != 0 ? 1 : 0)); }
     if (cm) comm_exchange_slots<CPLX>(ctl, cm, j, nslots);
     gs_decide<T>(ctl, ctl->red, j, ncv, decide_kind);
+    GA_TRACE(7, tid == 0)
   }
+#undef GA_TRACE
 }
 
 // One-CTA kernel that sums the gathered per-rank slots and runs the decision logic (multi GPU).
@@ -249,7 +266,7 @@ static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
   }
   k_gs<T, MODE><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
                                                       gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
-                                                      c->world > 1 ? c->devcomm : nullptr);
+                                                      c->world > 1 ? c->devcomm : nullptr, c->trace);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));

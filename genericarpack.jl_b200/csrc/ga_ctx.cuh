@@ -139,6 +139,7 @@ struct ga_ctx {
   size_t prof_used = 0;
   long long launches = 0;            // kernels launched by this context
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  unsigned int gs_flip = 0;             // consecutive sweeps traverse the row tiles in opposite directions (L2 reuse)
   unsigned long long* trace = nullptr;  // device, 16 globaltimer samples of the last traced sweep (debug)
   std::string err;
 };

@@ -48,7 +48,7 @@ template <class T> struct GsCfg {
 template <class T, int MODE>
 __global__ void __launch_bounds__(GsCfg<T>::THREADS, 1)
 k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
-     int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm, unsigned long long* trace) {
+     int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm, unsigned long long* trace, int reverse) {
   typedef GsCfg<T> C;
 #define GA_TRACE(slot, cond)                                                        \
   if (trace != nullptr && (cond)) {                                                 \
@@ -102,7 +102,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       if (lane == 0) mbar_arrive_expect_tx(&full[s], stage_bytes);
       __syncwarp();
       unsigned char* st = smem + (size_t)s * stage_bytes;
-      const i64 row0 = t * R;
+      const i64 row0 = (reverse ? (ntiles - 1 - t) : t) * R;
       for (int c = lane; c <= j; c += 32) {
         const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (w + row0);
         bulk_g2s(st + (size_t)c * SEG, src, SEG, &full[s]);
@@ -144,7 +144,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
         }
         if (g == 0) {
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) r[t * R + rl * RPT + q] = rr[q];
+          for (int q = 0; q < RPT; ++q) r[(reverse ? (ntiles - 1 - t) : t) * R + rl * RPT + q] = rr[q];
         }
       }
       if (MODE != 2) {
@@ -266,7 +266,7 @@ static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
   }
   k_gs<T, MODE><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
                                                       gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
-                                                      c->world > 1 ? c->devcomm : nullptr, c->trace);
+                                                      c->world > 1 ? c->devcomm : nullptr, c->trace, (int)(c->gs_flip++ & 1));
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));

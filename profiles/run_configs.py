@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Runs BASELINE.json's other configs (C1, C3, C4, reduced C5) plus C2's full time-to-solution on one
+B200 and writes gpurun_out/configs.json.  bench.py stays the C2 steps/s contract; this script is
+where the remaining configs' numbers in profiles/RESULTS.md come from.
+
+    python profiles/run_configs.py [c1] [c3] [c4] [c5] [c2tts] [--oracle]
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def solve(pkg, op, nev, ncv, which="LM", dtype_size=8):
+    t0 = time.perf_counter()
+    ctx = pkg.Context(op, ncv)
+    t_up = time.perf_counter() - t0
+    n = op.size()
+    ctx.profile(True)
+    ctx.timer_start()
+    rc = ctx.symeigs_begin(nev, which, 0.0, max(300, int(np.ceil(np.sqrt(n)))), None)
+    rcit = ctx.symeigs_iterate(-1)
+    ms = ctx.timer_stop()
+    info, values, bounds, vecs, iparam = ctx.symeigs_end(nev, ritzvec=True)
+    st = ctx.stats()
+    prof = ctx.profile_read()
+    n_pad = ((n + 255) // 256) * 256
+    gs_gbps = prof["gs_units"] * n_pad * dtype_size / max(prof["gs_ms"], 1e-9) / 1e6
+    out = {"rc": [int(rc), int(rcit), int(info)], "n": int(n), "nev": nev, "ncv": ncv, "solve_s": round(ms / 1e3, 4),
+           "upload_s": round(t_up, 3), "restarts": int(iparam[2]), "nconv": int(iparam[4]), "lanczos_steps": int(st["nopx"]),
+           "steps_per_s": round(st["nopx"] / (ms / 1e3), 1), "nrorth": int(st["nrorth"]), "nitref": int(st["nitref"]),
+           "gs_GBps": round(gs_gbps, 1), "gs_share": round(prof["gs_ms"] / ms, 3), "launches": int(prof["launches"])}
+    ctx.close()
+    return out, values, vecs
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c3", "c4", "c5"]
+    with_oracle = "--oracle" in sys.argv
+    pkg = entry.load_package()
+    syn = importlib.import_module(entry.PKG_NAME + ".synthetic")
+    O = entry.load_oracle() if with_oracle else None
+    res = {}
+    if "c1" in which or "c3" in which:
+        csr = syn.sprand_sym(100000, 5.0, seed=1234)
+        A = syn.to_scipy(csr)
+    if "c1" in which:
+        out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr), 2, 12)
+        out["values"] = [float(v) for v in vals]
+        out["max_ritz_residual_rel"] = float(np.max(np.linalg.norm(A @ vecs - vecs * vals, axis=0) / np.abs(vals)))
+        if O:
+            t0 = time.perf_counter(); r = O.Oracle(A, 12).symeigs(2); out["oracle_s"] = round(time.perf_counter() - t0, 3)
+            out["oracle_restarts"] = r["niter"]; out["oracle_steps"] = r["stats"]["nopx"]
+            out["rel_err_vs_oracle"] = float(np.max(np.abs(vals - r["values"]) / np.abs(r["values"])))
+        res["C1 sprand-symmetric n=1e5 nev=2 ncv=12 Float64"] = out
+    if "c3" in which:
+        out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr, dtype="dd"), 2, 12, dtype_size=16)
+        vals = np.asarray(vals)
+        out["values_hi"] = [float(v) for v in vals[:, 0]]
+        out["values_lo"] = [float(v) for v in vals[:, 1]]
+        if O:
+            t0 = time.perf_counter(); r = O.Oracle(A, 12, dtype=O.DD).symeigs(2); out["oracle_s"] = round(time.perf_counter() - t0, 3)
+            out["oracle_restarts"] = r["niter"]; out["oracle_steps"] = r["stats"]["nopx"]
+            ov = np.asarray(r["values"])
+            out["rel_err_vs_oracle"] = float(np.max(np.abs((vals[:, 0] - ov[:, 0]) + (vals[:, 1] - ov[:, 1])) / np.abs(ov[:, 0])))
+        res["C3 same matrix in Double64"] = out
+    if "c4" in which:
+        csr4 = syn.hermitian_stencil(2000)
+        out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr4, dtype="c64"), 6, 30, dtype_size=16)
+        A4 = syn.to_scipy(csr4)
+        out["values"] = [float(v) for v in vals]
+        out["max_ritz_residual_rel"] = float(np.max(np.linalg.norm(A4 @ vecs - vecs * vals, axis=0) / np.abs(vals)))
+        out["orthonormality"] = float(np.max(np.abs(vecs.conj().T @ vecs - np.eye(vecs.shape[1]))))
+        res["C4 complex Hermitian stencil n=4M nev=6 ncv=30 ComplexF64"] = out
+    if "c5" in which:
+        scale = float(os.environ.get("C5_SCALE", "0.1"))
+        m5, n5 = int(50_000_000 * scale), int(2_000_000 * scale)
+        t0 = time.perf_counter()
+        csr5 = syn.tall_sparse(m5, n5, 10)
+        tgen = time.perf_counter() - t0
+        S, V, einfo = pkg.svds(pkg.ArpackNormalOp(csr5), 20, ncv=60, keep_context=False)
+        A5 = syn.to_scipy(csr5)
+        resid = float(np.max(np.linalg.norm(A5.T @ (A5 @ V) - V * (S ** 2), axis=0) / (S ** 2)))
+        res["C5 svds tall sparse %dx%d nnz=%d k=20 ncv=60 (scale %.2f of 50Mx2M)" % (m5, n5, len(csr5[1]), scale)] = {
+            "gen_s": round(tgen, 1), "singular_values_top5": [float(s) for s in S[:5]], "restarts": int(einfo.iparam[2]),
+            "lanczos_steps": int(einfo.stats["nopx"]), "taitr_s": round(einfo.stats["taitr"], 3),
+            "steps_per_s": round(einfo.stats["nopx"] / max(einfo.stats["taitr"], 1e-9), 1), "max_normal_eq_residual_rel": resid}
+    if "c2tts" in which:
+        m = int(os.environ.get("C2_M", "4000"))
+        csr2 = syn.laplacian2d(m)
+        out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr2), 10, 40)
+        exact = syn.laplacian2d_eigs(m, 10)
+        out["max_rel_err_vs_analytic"] = float(np.max(np.abs(vals - exact) / exact)) if len(vals) == 10 else None
+        A2 = syn.to_scipy(csr2)
+        out["max_ritz_residual_rel"] = float(np.max(np.linalg.norm(A2 @ vecs - vecs * vals, axis=0) / np.abs(vals)))
+        res["C2 time to solution, 2-D Laplacian n=%d nev=10 ncv=40 Float64, 1 GPU" % (m * m)] = out
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()

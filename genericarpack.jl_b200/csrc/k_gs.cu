@@ -26,14 +26,16 @@ namespace ga {
 // dynamic shared memory per CTA (the SM has 227 KiB for one CTA incl. ~1 KiB static)
 constexpr size_t kGsSmemBytes = 224 * 1024;
 
-template <class T> struct GsCfg {
+template <class T, int SEG> struct GsCfg {
   // A tile is R rows of (j columns + the vector being orthogonalised).  One TMA bulk copy moves
   // one column segment of the tile; measured on B200 (profiles/microbench/tma_bulk_rate.cu) the
   // per-SM bulk-copy issue rate caps 1 KiB copies at ~4.3 TB/s chip-wide while 2 KiB copies reach
   // ~6.8 TB/s, hence 2 KiB segments: R = 256 rows (F64) / 128 rows (C64, DD).
-  static constexpr int SEG_BYTES = 2048;
+  // SEG = 1024 (one row per thread) is the fallback for j > ~47 columns, where 2 KiB segments
+  // would leave fewer than two pipeline stages in shared memory.
+  static constexpr int SEG_BYTES = SEG;
   static constexpr int R = SEG_BYTES / (int)sizeof(T);
-  static constexpr int RPT = 2;                       // adjacent rows per thread
+  static constexpr int RPT = SEG / 1024;              // adjacent rows per thread
   static constexpr int ROWL = R / RPT;                // row lanes: 128 (F64) / 64 (C64, DD)
   static constexpr int TG = (sizeof(T) == 8) ? 4 : 8; // thread groups (column interleave)
   static constexpr int NC = kMaxNcv / TG;             // columns per thread (register accumulators)
@@ -45,11 +47,11 @@ template <class T> struct GsCfg {
                                     2 * MAX_STAGES * 8 /*mbar*/ + 64;
 };
 
-template <class T, int MODE>
-__global__ void __launch_bounds__(GsCfg<T>::THREADS, 1)
+template <class T, int MODE, int SEG>
+__global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
 k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
      int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm, unsigned long long* trace, int reverse) {
-  typedef GsCfg<T> C;
+  typedef GsCfg<T, SEG> C;
 #define GA_TRACE(slot, cond)                                                        \
   if (trace != nullptr && (cond)) {                                                 \
     unsigned long long t_;                                                          \
@@ -58,17 +60,17 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
   }
   GA_TRACE(0, blockIdx.x == 0 && threadIdx.x == 0)
   constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS, RPT = C::RPT, ROWL = C::ROWL;
-  constexpr uint32_t SEG = C::SEG_BYTES;
+  constexpr uint32_t SEGB = C::SEG_BYTES;
   constexpr bool CPLX = Elem<T>::is_complex;
 
   if (ctl->status != ST_OK) return;
   if (gate_phase >= 0 && ctl->phase != gate_phase) return;
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t stage_bytes = (uint32_t)(j + 1) * SEG;
+  const uint32_t stage_bytes = (uint32_t)(j + 1) * SEGB;
   unsigned char* p = smem + (size_t)nstages * stage_bytes;
   T* hs = reinterpret_cast<T*>(p);                  p += kMaxNcv * 16;
-  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * SEG;
+  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * SEGB;
   double2* redw = reinterpret_cast<double2*>(p);    p += CWARPS * (NC + 3) * 16;
   uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += C::MAX_STAGES * 8;
   uint64_t* empty = reinterpret_cast<uint64_t*>(p); p += C::MAX_STAGES * 8;
@@ -105,7 +107,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       const i64 row0 = (reverse ? (ntiles - 1 - t) : t) * R;
       for (int c = lane; c <= j; c += 32) {
         const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (w + row0);
-        bulk_g2s(st + (size_t)c * SEG, src, SEG, &full[s]);
+        bulk_g2s(st + (size_t)c * SEGB, src, SEGB, &full[s]);
       }
     }
   } else {
@@ -235,19 +237,15 @@ __global__ void k_decide(DevCtl* ctl, const double2* gathered, int world, int j,
   gs_decide<T>(ctl, red, j, ncv, decide_kind);
 }
 
-template <class T, int MODE>
-static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
-  typedef GsCfg<T> C;
+template <class T, int MODE, int SEG>
+static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int nstages) {
+  typedef GsCfg<T, SEG> C;
   const i64 ntiles = c->n_pad / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
-  const size_t budget = kGsSmemBytes - C::FIXED_SMEM;
-  int nstages = (int)(budget / stage_bytes);
-  if (nstages > C::MAX_STAGES) nstages = C::MAX_STAGES;
-  if (nstages < 2) return set_err(c, GA_ERR_ARG, "gs: too many columns for the shared-memory pipeline");
   const size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
   static bool attr_set = false;
   if (!attr_set) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
+    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
     attr_set = true;
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
@@ -264,13 +262,30 @@ static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
     c->prof_used += 2;
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
-  k_gs<T, MODE><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
-                                                      gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
-                                                      c->world > 1 ? c->devcomm : nullptr, c->trace, (int)(c->gs_flip++ & 1));
+  k_gs<T, MODE, SEG><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
+                                                           gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
+                                                           c->world > 1 ? c->devcomm : nullptr, c->trace,
+                                                           (int)(c->gs_flip++ & 1));
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
   return 0;
+}
+
+template <class T, int MODE>
+static int launch_gs_t(ga_ctx* c, int j, int gate_phase, int decide_kind) {
+  // 2 KiB segments whenever at least two pipeline stages fit, else 1 KiB segments
+  const size_t budget2 = kGsSmemBytes - GsCfg<T, 2048>::FIXED_SMEM;
+  int nst = (int)(budget2 / ((size_t)(j + 1) * 2048));
+  if (nst >= 2) {
+    if (nst > GsCfg<T, 2048>::MAX_STAGES) nst = GsCfg<T, 2048>::MAX_STAGES;
+    return launch_gs_seg<T, MODE, 2048>(c, j, gate_phase, decide_kind, nst);
+  }
+  const size_t budget1 = kGsSmemBytes - GsCfg<T, 1024>::FIXED_SMEM;
+  nst = (int)(budget1 / ((size_t)(j + 1) * 1024));
+  if (nst > GsCfg<T, 1024>::MAX_STAGES) nst = GsCfg<T, 1024>::MAX_STAGES;
+  if (nst < 2) return set_err(c, GA_ERR_ARG, "gs: too many columns for the shared-memory pipeline");
+  return launch_gs_seg<T, MODE, 1024>(c, j, gate_phase, decide_kind, nst);
 }
 
 template <class T>

@@ -48,6 +48,10 @@ def main():
     syn = importlib.import_module(entry.PKG_NAME + ".synthetic")
     O = entry.load_oracle() if with_oracle else None
     res = {}
+
+    def dump():
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(res, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
     if "c1" in which or "c3" in which:
         csr = syn.sprand_sym(100000, 5.0, seed=1234)
         A = syn.to_scipy(csr)
@@ -60,6 +64,7 @@ def main():
             out["oracle_restarts"] = r["niter"]; out["oracle_steps"] = r["stats"]["nopx"]
             out["rel_err_vs_oracle"] = float(np.max(np.abs(vals - r["values"]) / np.abs(r["values"])))
         res["C1 sprand-symmetric n=1e5 nev=2 ncv=12 Float64"] = out
+        dump()
     if "c3" in which:
         out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr, dtype="dd"), 2, 12, dtype_size=16)
         vals = np.asarray(vals)
@@ -71,6 +76,7 @@ def main():
             ov = np.asarray(r["values"])
             out["rel_err_vs_oracle"] = float(np.max(np.abs((vals[:, 0] - ov[:, 0]) + (vals[:, 1] - ov[:, 1])) / np.abs(ov[:, 0])))
         res["C3 same matrix in Double64"] = out
+        dump()
     if "c4" in which:
         csr4 = syn.hermitian_stencil(2000)
         out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr4, dtype="c64"), 6, 30, dtype_size=16)
@@ -79,6 +85,7 @@ def main():
         out["max_ritz_residual_rel"] = float(np.max(np.linalg.norm(A4 @ vecs - vecs * vals, axis=0) / np.abs(vals)))
         out["orthonormality"] = float(np.max(np.abs(vecs.conj().T @ vecs - np.eye(vecs.shape[1]))))
         res["C4 complex Hermitian stencil n=4M nev=6 ncv=30 ComplexF64"] = out
+        dump()
     if "c5" in which:
         scale = float(os.environ.get("C5_SCALE", "0.1"))
         m5, n5 = int(50_000_000 * scale), int(2_000_000 * scale)
@@ -92,6 +99,7 @@ def main():
             "gen_s": round(tgen, 1), "singular_values_top5": [float(s) for s in S[:5]], "restarts": int(einfo.iparam[2]),
             "lanczos_steps": int(einfo.stats["nopx"]), "taitr_s": round(einfo.stats["taitr"], 3),
             "steps_per_s": round(einfo.stats["nopx"] / max(einfo.stats["taitr"], 1e-9), 1), "max_normal_eq_residual_rel": resid}
+    dump()
     if "c2tts" in which:
         m = int(os.environ.get("C2_M", "4000"))
         csr2 = syn.laplacian2d(m)

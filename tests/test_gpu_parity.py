@@ -462,3 +462,16 @@ def test_full_size_properties(pkg, syn):
     w = np.linalg.eigvalsh(T)
     assert w.min() > 0 and w.max() < 8
     ctx.close()
+
+
+def test_large_ncv_fallback(pkg, syn, O):
+    """ncv up to GA_MAX_NCV = 64 (config C5 uses ncv = 60): the sweep kernel falls back from 2 KiB
+    to 1 KiB TMA segments when fewer than two pipeline stages would fit."""
+    A = syn.to_scipy(syn.laplacian2d(70))
+    res, ora = _check_against_oracle(pkg, O, A, 20, 64)
+    exact = syn.laplacian2d_eigs(70, 20)
+    assert np.max(np.abs(res.values - exact) / exact) <= 1e-10
+    Z = res.vectors
+    assert np.allclose(Z.T @ Z, np.eye(20), atol=1e-12)
+    with pytest.raises(Exception):
+        pkg.eigs(A, 20, ncv=65)          # beyond GA_MAX_NCV: refused, never silently degraded

@@ -35,9 +35,13 @@ template <class T, int SEG> struct GsCfg {
   // would leave fewer than two pipeline stages in shared memory.
   static constexpr int SEG_BYTES = SEG;
   static constexpr int R = SEG_BYTES / (int)sizeof(T);
-  static constexpr int RPT = SEG / 1024;              // adjacent rows per thread
-  static constexpr int ROWL = R / RPT;                // row lanes: 128 (F64) / 64 (C64, DD)
-  static constexpr int TG = (sizeof(T) == 8) ? 4 : 8; // thread groups (column interleave)
+  // Thread layout (16 consumer warps + 1 producer warp; 17 warps are allocated as 20, which caps
+  // the kernel at 96 registers/thread):
+  //   F64 : 128 row lanes x 4 column groups, 2 rows/thread at 2 KiB (1 at 1 KiB), 16 accumulators
+  //   16 B: 64 row lanes x 8 column groups, 2 rows/thread at 2 KiB (1 at 1 KiB), 8 accumulators
+  static constexpr int ROWL = (sizeof(T) == 8) ? 128 : 64;
+  static constexpr int RPT = R / ROWL;
+  static constexpr int TG = 512 / ROWL;
   static constexpr int NC = kMaxNcv / TG;             // columns per thread (register accumulators)
   static constexpr int SLICES = ROWL / 32;
   static constexpr int CWARPS = SLICES * TG;          // consumer warps

@@ -1,12 +1,12 @@
 // OP*x of dsaitr step 3 (src/dsaitr.jl:1120-1133 -> opx!(y, ArpackSimpleOp, x) = mul!(y, A, x),
 // src/idonow_ops.jl:122; ArpackNormalOp: y = A'(A x), :267-276) as a CSR SpMV.
 //
-// Row-segment ("CSR-stream") kernel at WARP granularity: a warp owns a chunk of consecutive rows
-// whose non-zeros form ONE contiguous segment of val/col.  The segment is read with fully
-// coalesced loads, multiplied with the gathered x entries and parked in shared memory; then each
-// lane sums whole (short) rows from shared memory.  A row longer than the segment capacity gets a
-// warp of its own.  Chunk boundaries are computed once on the host when the matrix is uploaded.
-// No atomics: results are bit-reproducible.
+// Row-segment ("CSR-stream") kernel: a CTA owns a block of consecutive rows whose non-zeros form
+// ONE contiguous segment of val/col.  The segment is read with fully coalesced loads, multiplied
+// with the gathered x entries and parked in shared memory; then one thread per row sums its
+// (short) row from shared memory.  Rows longer than the segment capacity get a CTA of their own
+// and a block-wide reduction.  Row blocks are computed once on the host when the matrix is
+// uploaded.  No atomics: results are bit-reproducible.
 #include "ga_decide.cuh"
 #include "ga_reduce.cuh"
 
@@ -16,19 +16,13 @@
 namespace ga {
 
 template <class T> struct SpmvCfg {
-  static constexpr int WARPS = 8;
-  static constexpr int THREADS = WARPS * 32;
-  static constexpr int CAP = (sizeof(T) == 8) ? 512 : 256;  // products parked per WARP (4 KiB)
-  static constexpr int MAXROWS = 256;                        // rows per warp chunk
+  static constexpr int THREADS = 256;
+  static constexpr int CAP = (sizeof(T) == 8) ? 4096 : 2048;  // products parked per CTA
+  static constexpr int MAXROWS = 1024;
 };
 
-// Warp-granular row-segment kernel: every warp owns a chunk of consecutive rows whose non-zeros
-// form one contiguous segment of at most CAP entries.  Phase 1 streams the segment with coalesced
-// loads (4 independent val/col/x chains per lane) and parks the products in the warp's 4 KiB of
-// shared memory; phase 2 lets each lane sum whole rows.  Only __syncwarp between the phases, so
-// the 8 warps of a CTA (and the ~6 CTAs of an SM) overlap their phases freely.
 template <class T>
-__global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restrict__ rowblk, int nchunks,
+__global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restrict__ rowblk,
                                                               const int* __restrict__ rowptr,
                                                               const int* __restrict__ col,
                                                               const T* __restrict__ val, const T* __restrict__ x,
@@ -44,46 +38,44 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
       spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq);
     __syncthreads();
   }
-  __shared__ T prod_all[C::WARPS * C::CAP];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * C::WARPS + warp;
-  if (chunk >= nchunks) return;
-  T* prod = prod_all + warp * C::CAP;
-  const int r0 = rowblk[chunk], r1 = rowblk[chunk + 1];
+  __shared__ T prod[C::CAP];
+  const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
   const int k0 = rowptr[r0], k1 = rowptr[r1];
+  const int tid = threadIdx.x;
   // x entry for (remapped) column c: own rows live in x[0, nsplit), halo entries received from
   // the peers in xh (single GPU: nsplit = INT_MAX, xh unused)
   auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
   if (k1 - k0 <= C::CAP) {
-    int k = k0 + lane;
-    for (; k + 96 < k1; k += 128) {
-      const int c0 = col[k], c1 = col[k + 32], c2 = col[k + 64], c3 = col[k + 96];
-      const T v0 = val[k], v1 = val[k + 32], v2 = val[k + 64], v3 = val[k + 96];
+    // coalesced segment pass, 4 independent gathers in flight per thread
+    int k = k0 + tid;
+    for (; k + 3 * C::THREADS < k1; k += 4 * C::THREADS) {
+      const int c0 = col[k], c1 = col[k + C::THREADS], c2 = col[k + 2 * C::THREADS], c3 = col[k + 3 * C::THREADS];
+      const T v0 = val[k], v1 = val[k + C::THREADS], v2 = val[k + 2 * C::THREADS], v3 = val[k + 3 * C::THREADS];
       const T x0 = xat(c0), x1 = xat(c1), x2 = xat(c2), x3 = xat(c3);
       prod[k - k0] = Elem<T>::mul(v0, x0);
-      prod[k - k0 + 32] = Elem<T>::mul(v1, x1);
-      prod[k - k0 + 64] = Elem<T>::mul(v2, x2);
-      prod[k - k0 + 96] = Elem<T>::mul(v3, x3);
+      prod[k - k0 + C::THREADS] = Elem<T>::mul(v1, x1);
+      prod[k - k0 + 2 * C::THREADS] = Elem<T>::mul(v2, x2);
+      prod[k - k0 + 3 * C::THREADS] = Elem<T>::mul(v3, x3);
     }
-    for (; k < k1; k += 32) prod[k - k0] = Elem<T>::mul(val[k], xat(col[k]));
-    __syncwarp();
-    for (int r = r0 + lane; r < r1; r += 32) {
+    for (; k < k1; k += C::THREADS) prod[k - k0] = Elem<T>::mul(val[k], xat(col[k]));
+    __syncthreads();
+    for (int r = r0 + tid; r < r1; r += C::THREADS) {
       const int a = rowptr[r] - k0, b = rowptr[r + 1] - k0;
       T s = Elem<T>::zero();
       for (int q = a; q < b; ++q) Elem<T>::add(s, prod[q]);
       y[r] = s;
     }
   } else {
-    // one long row for the whole warp (r1 == r0 + 1 by construction): fixed-order lane sums + tree
+    // one long row for the whole CTA (r1 == r0 + 1 by construction)
     T s = Elem<T>::zero();
-    for (int k = k0 + lane; k < k1; k += 32) Elem<T>::add(s, Elem<T>::mul(val[k], xat(col[k])));
-    prod[lane] = s;
-    __syncwarp();
-    if (lane == 0) {
-      T a = prod[0];
-      for (int l = 1; l < 32; ++l) Elem<T>::add(a, prod[l]);
-      y[r0] = a;
+    for (int k = k0 + tid; k < k1; k += C::THREADS) Elem<T>::add(s, Elem<T>::mul(val[k], xat(col[k])));
+    prod[tid] = s;
+    __syncthreads();
+    for (int off = C::THREADS / 2; off > 0; off >>= 1) {
+      if (tid < off) { T a = prod[tid]; Elem<T>::add(a, prod[tid + off]); prod[tid] = a; }
+      __syncthreads();
     }
+    if (tid == 0) y[r0] = prod[0];
   }
 }
 
@@ -91,8 +83,7 @@ template <class T>
 static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
   if (M.nblk <= 0) return;
   const bool split = c->world > 1 && &M == &c->A && c->op_kind == 1;
-  const int grid = (M.nblk + SpmvCfg<T>::WARPS - 1) / SpmvCfg<T>::WARPS;
-  k_spmv<T><<<grid, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.nblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
+  k_spmv<T><<<M.nblk, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
                                                           (const T*)c->halo, split ? (int)c->n_pad : 2147483647,
                                                           (T*)y, c->ctl, gated ? 1 : 0,
                                                           (split && wait_halo) ? c->devcomm : nullptr);

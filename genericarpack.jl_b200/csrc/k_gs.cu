@@ -117,6 +117,10 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
   } else {
     // ---------------- consumers: thread (rl, g) owns rows 2rl, 2rl+1 and columns g, g+TG, ...
     const int slice = warp % SLICES, g = warp / SLICES, rl = slice * 32 + lane;
+    // rows of the tile owned by this thread: adjacent for 8-byte elements (one LDS.128 fetches
+    // both), ROWL apart for 16-byte elements (adjacent rows would be a 32-byte lane stride =
+    // 2-way bank conflicts on every shared-memory access; measured 50 % conflict wavefronts)
+#define ROWIDX(q) ((sizeof(T) == 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
     int it = 0;
     for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it % nstages;
@@ -126,7 +130,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       const T* tile = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
       T rr[RPT];
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) rr[q] = tile[(size_t)j * R + rl * RPT + q];  // w
+      for (int q = 0; q < RPT; ++q) rr[q] = tile[(size_t)j * R + ROWIDX(q)];  // w
       if (MODE != 0) {
         T p0[RPT];
 #pragma unroll
@@ -137,20 +141,20 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
           if (c >= j) break;
           const T hc = hs[c];
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) Elem<T>::sub_mul(p0[q], tile[(size_t)c * R + rl * RPT + q], hc);
+          for (int q = 0; q < RPT; ++q) Elem<T>::sub_mul(p0[q], tile[(size_t)c * R + ROWIDX(q)], hc);
         }
         T* prb = pr + (size_t)(it & 1) * TG * R;
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) prb[g * R + rl * RPT + q] = p0[q];
+        for (int q = 0; q < RPT; ++q) prb[g * R + ROWIDX(q)] = p0[q];
         named_bar_sync(1 + slice, TG * 32);
 #pragma unroll
         for (int g2 = 0; g2 < TG; ++g2) {
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) Elem<T>::add(rr[q], prb[g2 * R + rl * RPT + q]);
+          for (int q = 0; q < RPT; ++q) Elem<T>::add(rr[q], prb[g2 * R + ROWIDX(q)]);
         }
         if (g == 0) {
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) r[(reverse ? (ntiles - 1 - t) : t) * R + rl * RPT + q] = rr[q];
+          for (int q = 0; q < RPT; ++q) r[(reverse ? (ntiles - 1 - t) : t) * R + ROWIDX(q)] = rr[q];
         }
       }
       if (MODE != 2) {
@@ -159,7 +163,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
           const int c = g + TG * i;
           if (c >= j) break;
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) Elem<T>::acc_conj_mul(acc[i], tile[(size_t)c * R + rl * RPT + q], rr[q]);
+          for (int q = 0; q < RPT; ++q) Elem<T>::acc_conj_mul(acc[i], tile[(size_t)c * R + ROWIDX(q)], rr[q]);
         }
       }
       if (g == 0) {
@@ -169,6 +173,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+#undef ROWIDX
     GA_TRACE(3, blockIdx.x == 0 && tid == 0)
     // warp-level reduction of this warp's accumulators (only the columns this group owns)
     if (MODE != 2) {

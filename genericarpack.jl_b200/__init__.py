@@ -391,7 +391,7 @@ class Context:
         if not read:
             self._ck(lib().ga_debug_trace(self.h, None))
             return None
-        out = np.zeros(16, dtype=np.uint64)
+        out = np.zeros(64, dtype=np.uint64)
         self._ck(lib().ga_debug_trace(self.h, _p(out)))
         return out
 

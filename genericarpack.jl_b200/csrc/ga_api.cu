@@ -2,6 +2,7 @@
 // the device tails of dsapps! and simple_dseupd!.  Host logic here is only what the reference
 // routine itself does around its vector operations (loop over steps, restart handling).
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "ga_ctx.cuh"
@@ -78,6 +79,8 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  c->coop = prop.cooperativeLaunch != 0;
+  if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -339,6 +342,11 @@ static int enqueue_steps(ga_ctx* c, int jfirst, int jlast) {
     int rc;
     if ((rc = launch_normalize(c, j - 1))) return rc;                       // STEP 2 (:1097-1105)
     if ((rc = launch_opx(c, (const char*)c->V + (size_t)(j - 1) * c->n_pad * c->esize, c->resid, true))) return rc;  // STEP 3
+    if (c->coop && c->use_step_kernel && (c->world == 1 || c->devcomm != nullptr)) {
+      // all sweeps of the step in one persistent cooperative launch (k_gs_step.cu)
+      if ((rc = launch_gs_step(c, j))) return rc;
+      continue;
+    }
     if ((rc = launch_gs(c, 0, j, -1, DK_DOT))) return rc;                   // wnorm, h = V'w (:1208,1227)
     if ((rc = launch_gs(c, 1, j, -1, DK_CGS))) return rc;                   // r = w - V h, s = V'r, ||r|| (:1240-1324)
     if ((rc = launch_gs(c, 1, j, PH_ORTH1, DK_ORTH1))) return rc;           // DGKS round 1 (:1352-1434)
@@ -520,16 +528,16 @@ int ga_profile_read(ga_ctx* c, double* gs_ms, int64_t* gs_runs, int64_t* gs_unit
 
 // debug: enable (out == NULL) or read back (out = 16 x uint64 ns) the in-kernel timeline of the
 // most recent Gram-Schmidt sweep launch
-int ga_debug_trace(ga_ctx* c, uint64_t* out16) {
+int ga_debug_trace(ga_ctx* c, uint64_t* out16) {  // 64 samples
   if (!c) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
   if (!c->trace) {
-    GA_CUDA(c, cudaMalloc(&c->trace, 16 * sizeof(unsigned long long)));
-    GA_CUDA(c, cudaMemset(c->trace, 0, 16 * sizeof(unsigned long long)));
+    GA_CUDA(c, cudaMalloc(&c->trace, 64 * sizeof(unsigned long long)));
+    GA_CUDA(c, cudaMemset(c->trace, 0, 64 * sizeof(unsigned long long)));
   }
   if (out16) {
     GA_CUDA(c, cudaStreamSynchronize(c->stream));
-    GA_CUDA(c, cudaMemcpy(out16, c->trace, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    GA_CUDA(c, cudaMemcpy(out16, c->trace, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   }
   return 0;
 }

@@ -41,6 +41,7 @@ struct DevCtl {
   int nrorth, nitref;
   int zero_resid;    // dsaitr set resid = 0, rnorm = 0 (src/dsaitr.jl:1442-1443)
   unsigned int ticket;  // last-block counter
+  unsigned int gbar_count, gbar_gen;  // grid barrier of the persistent step kernel
   unsigned int seq;              // sequence number of the fused cross-GPU slot exchange
   unsigned int hseq;             // sequence number of the fused halo push
   unsigned int prof_runs;        // executed (not phase-gated) Gram-Schmidt sweep launches
@@ -139,6 +140,8 @@ struct ga_ctx {
   size_t prof_used = 0;
   long long launches = 0;            // kernels launched by this context
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  bool coop = false;                    // device supports cooperative launches (persistent step kernel)
+  bool use_step_kernel = true;
   unsigned int gs_flip = 0;             // consecutive sweeps traverse the row tiles in opposite directions (L2 reuse)
   unsigned long long* trace = nullptr;  // device, 16 globaltimer samples of the last traced sweep (debug)
   std::string err;
@@ -169,6 +172,8 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
 // k_gs.cu
 int launch_gs(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind);
 int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind);
+// k_gs_step.cu
+int launch_gs_step(ga_ctx* c, int j);
 // k_update.cu
 int launch_vq(ga_ctx* c, int kplusp, int nout, bool do_resid, const void* sigma, const void* beta, int kev);
 

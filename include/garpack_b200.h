@@ -149,7 +149,7 @@ int ga_timer_start(ga_ctx* ctx);
 int ga_timer_stop(ga_ctx* ctx, double* ms);
 int ga_profile(ga_ctx* ctx, int enable);
 /* debug: out16 == NULL enables an in-kernel globaltimer timeline of the Gram-Schmidt sweep; a later
- * call with out16 != NULL reads the 16 samples (ns) of the most recent sweep launch. */
+ * call with out16 != NULL reads the 64 samples (ns) of the most recent sweep launch. */
 int ga_debug_trace(ga_ctx* ctx, uint64_t* out16);
 int ga_profile_read(ga_ctx* ctx, double* gs_ms, int64_t* gs_runs, int64_t* gs_units, int64_t* launches);
 

@@ -190,19 +190,26 @@ def run_b200(args):
     # algorithmic bytes of the whole timed region by SURVEY 8(d): per Lanczos step SpMV + 2nS + GS rounds
     spmv_bytes = (nnz_global * (S + 4) + (n + 1) * 8 + 2 * n * S) / world
     step_bytes_total = lanczos_steps * (spmv_bytes + 2 * blk * S) + gs_bytes
-    traffic = None
+    # DRAM traffic of one captured launch of the same kernel (ncu --set full, profiles/gs_traffic.json)
+    traffic, traffic_note = None, None
     tfile = os.path.join(ROOT, "profiles", "gs_traffic.json")
     if os.path.exists(tfile):
         try:
-            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+            tj = json.load(open(tfile))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = tj.get("note")
         except Exception:
             traffic = None
+    ngs = max(prof.get("gs_launches", 0), 1)
+    step_kernel = ngs < prof["gs_runs"]
     roofline = {
-        "bound": "hbm", "kernel": "k_gs (fused CGS/DGKS sweep, TMA pipeline)",
+        "bound": "hbm",
+        "kernel": ("k_gs_step (all CGS/DGKS sweeps of a Lanczos step in one persistent cooperative launch, TMA pipeline)"
+                   if step_kernel else "k_gs (fused CGS/DGKS sweep, TMA pipeline)"),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "peak_source": peak_src, "traffic": traffic,
-        "bytes_per_launch": round(gs_bytes / max(prof["gs_runs"], 1)), "launches_timed": prof["gs_runs"],
-        "avg_launch_ms": round(gs_ms / max(prof["gs_runs"], 1), 4),
+        "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
+        "bytes_per_launch": round(gs_bytes / ngs), "launches_timed": ngs, "sweeps_timed": prof["gs_runs"],
+        "avg_launch_ms": round(gs_ms / ngs, 4),
         "gs_share_of_step_time": round(gs_ms / ms, 4),
         "whole_step_achieved_GBps": round(step_bytes_total / (ms / 1e3) / 1e9 * world, 1),
         "frac_of_nominal_8TBps": round(achieved / 8000.0, 4),

@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_debug_trace", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_debug_trace", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -117,6 +117,7 @@ def lib():
         L.ga_timer_stop.argtypes = [vp, vp]
         L.ga_profile.argtypes = [vp, i32]
         L.ga_profile_read.argtypes = [vp, vp, vp, vp, vp]
+        L.ga_profile_gs_launches.argtypes = [vp, vp]
         L.ga_debug_trace.argtypes = [vp, vp]
         L.ga_symeigs.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
         L.ga_symeigs_begin.argtypes = [vp, i32, i32, vp, i32, vp]
@@ -403,7 +404,10 @@ class Context:
         runs, units, launches = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
         self._ck(lib().ga_profile_read(self.h, ctypes.byref(ms), ctypes.byref(runs), ctypes.byref(units),
                                        ctypes.byref(launches)))
-        return {"gs_ms": ms.value, "gs_runs": runs.value, "gs_units": units.value, "launches": launches.value}
+        ngs = ctypes.c_int64(0)
+        self._ck(lib().ga_profile_gs_launches(self.h, ctypes.byref(ngs)))
+        return {"gs_ms": ms.value, "gs_runs": runs.value, "gs_units": units.value, "launches": launches.value,
+                "gs_launches": ngs.value}
 
     # --- whole solve
     def symeigs_begin(self, nev, which="LM", tol=0.0, maxiter=300, v0=None):

@@ -164,7 +164,7 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
   for (int q = 0; q < c->world; ++q) { nsend += send_counts[q]; nrecv += recv_counts[q]; }
   if (nrecv != nhalo || (nsend > 0 && !send_idx)) return set_err(c, GA_ERR_ARG, "halo plan is inconsistent");
   c->nhalo = nhalo; c->nsend = nsend;
-  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace);
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo);
   c->send_idx = nullptr; c->send_buf = nullptr; c->halo = nullptr;
   GA_CUDA(c, cudaMalloc(&c->send_idx, sizeof(int) * (size_t)(nsend > 0 ? nsend : 1)));
   GA_CUDA(c, cudaMalloc(&c->send_buf, c->esize * (size_t)(nsend > 0 ? nsend : 1)));
@@ -523,6 +523,12 @@ int ga_profile_read(ga_ctx* c, double* gs_ms, int64_t* gs_runs, int64_t* gs_unit
   if (gs_runs) *gs_runs = (int64_t)c->ctl_host->prof_runs;
   if (gs_units) *gs_units = (int64_t)c->ctl_host->prof_units;
   if (launches) *launches = (int64_t)c->launches;
+  return 0;
+}
+
+int ga_profile_gs_launches(ga_ctx* c, int64_t* n) {
+  if (!c || !n) return GA_ERR_ARG;
+  *n = (int64_t)(c->prof_used / 2);
   return 0;
 }
 

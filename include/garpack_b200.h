@@ -152,6 +152,9 @@ int ga_profile(ga_ctx* ctx, int enable);
  * call with out16 != NULL reads the 64 samples (ns) of the most recent sweep launch. */
 int ga_debug_trace(ga_ctx* ctx, uint64_t* out16);
 int ga_profile_read(ga_ctx* ctx, double* gs_ms, int64_t* gs_runs, int64_t* gs_units, int64_t* launches);
+/* number of Gram-Schmidt kernel launches bracketed since ga_profile(ctx, 1) (the persistent step kernel
+ * runs all sweeps of a Lanczos step in one launch, so this is <= gs_runs). */
+int ga_profile_gs_launches(ga_ctx* ctx, int64_t* n);
 
 /* ---- whole solve: symeigs (src/interface.jl:215-290) = dsaupd! + simple_dseupd! -----------------
  * Host control (dsaup2 loop, dsgets, dsconv, dseigt/dstqrb, dsapps bulge chase, dseupd's small

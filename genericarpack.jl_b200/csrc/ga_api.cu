@@ -81,6 +81,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   c->sm_count = prop.multiProcessorCount;
   c->coop = prop.cooperativeLaunch != 0;
   if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
+  if (const char* e = getenv("GA_SPMV_V1")) c->use_spmv_stream = !(e[0] == '1');
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -523,6 +524,21 @@ int ga_profile_read(ga_ctx* c, double* gs_ms, int64_t* gs_runs, int64_t* gs_unit
   if (gs_runs) *gs_runs = (int64_t)c->ctl_host->prof_runs;
   if (gs_units) *gs_units = (int64_t)c->ctl_host->prof_units;
   if (launches) *launches = (int64_t)c->launches;
+  return 0;
+}
+
+int ga_bench_opx(ga_ctx* c, int reps, double* ms) {
+  if (!c || !ms || reps < 1) return GA_ERR_ARG;
+  if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
+  GA_CUDA(c, cudaSetDevice(c->device));
+  int rc = launch_opx(c, c->V, c->resid, false);  // warm-up
+  if (rc) return rc;
+  if ((rc = ga_timer_start(c))) return rc;
+  for (int i = 0; i < reps; ++i)
+    if ((rc = launch_opx(c, c->V, c->resid, false))) return rc;
+  double t = 0.0;
+  if ((rc = ga_timer_stop(c, &t))) return rc;
+  *ms = t / reps;
   return 0;
 }
 

@@ -74,11 +74,17 @@ struct CsrDev {
   int* rowptr = nullptr;    // nrows+1 (32-bit: nnz < 2^31 per rank)
   int* col = nullptr;       // nnz, local column index into the x vector handed to the kernel
   void* val = nullptr;      // nnz elements of T
-  int* rowblk = nullptr;    // nblk+1 row-block boundaries for the row-segment kernel
+  int* rowblk = nullptr;    // nblk+1 row-block boundaries for the row-segment kernel (v1)
   int nblk = 0;
+  // streamed kernel (k_spmv_stream): row blocks {r0, r1, k0, k1} whose non-zeros fit one pipeline
+  // stage, plus the list of rows that are longer than a stage (handled by the v1 long-row path)
+  int4* desc = nullptr;
+  int ndesc = 0;
+  int* longrow = nullptr;   // nlong row indices
+  int nlong = 0;
   void free_all() {
-    cudaFree(rowptr); cudaFree(col); cudaFree(val); cudaFree(rowblk);
-    rowptr = col = rowblk = nullptr; val = nullptr; nblk = 0; nnz = 0;
+    cudaFree(rowptr); cudaFree(col); cudaFree(val); cudaFree(rowblk); cudaFree(desc); cudaFree(longrow);
+    rowptr = col = rowblk = longrow = nullptr; val = nullptr; desc = nullptr; nblk = 0; nnz = 0; ndesc = 0; nlong = 0;
   }
 };
 
@@ -142,6 +148,7 @@ struct ga_ctx {
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   bool coop = false;                    // device supports cooperative launches (persistent step kernel)
   bool use_step_kernel = true;
+  bool use_spmv_stream = true;          // TMA-staged persistent SpMV (GA_SPMV_V1=1 selects the first kernel)
   unsigned int gs_flip = 0;             // consecutive sweeps traverse the row tiles in opposite directions (L2 reuse)
   unsigned long long* trace = nullptr;  // device, 16 globaltimer samples of the last traced sweep (debug)
   std::string err;

@@ -167,6 +167,17 @@ template <> struct Real<ddbl> {
 // ------------------------------------------------------------------ element traits
 template <class T> struct Elem;
 
+// a product that the compiler may NOT contract with a neighbouring add into an FMA: element
+// products are then the same bits in every kernel that forms them (and in the CPU oracle, which
+// is built with -ffp-contract=off)
+GA_HD double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+
 template <> struct Elem<double> {
   typedef double real_t;
   static constexpr int dtype = 0;
@@ -179,7 +190,7 @@ template <> struct Elem<double> {
   static GA_HD void sub_mul(double& r, double v, double h) { r = fma(-v, h, r); }             // r -= v h
   static GA_HD void add_mul_real(double& y, double v, double q) { y = fma(v, q, y); }         // y += v q (q real)
   static GA_HD double mul_real(double v, double a) { return v * a; }
-  static GA_HD double mul(double a, double b) { return a * b; }
+  static GA_HD double mul(double a, double b) { return mul_rn(a, b); }
 };
 template <> struct Elem<cdbl> {
   typedef double real_t;
@@ -199,7 +210,12 @@ template <> struct Elem<cdbl> {
   }
   static GA_HD void add_mul_real(cdbl& y, cdbl v, double q) { y.re = fma(v.re, q, y.re); y.im = fma(v.im, q, y.im); }
   static GA_HD cdbl mul_real(cdbl v, double a) { cdbl z; z.re = v.re * a; z.im = v.im * a; return z; }
-  static GA_HD cdbl mul(cdbl a, cdbl b) { cdbl z; z.re = a.re * b.re - a.im * b.im; z.im = a.re * b.im + a.im * b.re; return z; }
+  static GA_HD cdbl mul(cdbl a, cdbl b) {
+    cdbl z;
+    z.re = fma(a.re, b.re, -mul_rn(a.im, b.im));
+    z.im = fma(a.re, b.im, mul_rn(a.im, b.re));
+    return z;
+  }
 };
 template <> struct Elem<ddbl> {
   typedef ddbl real_t;

@@ -7,10 +7,21 @@
 // (short) row from shared memory.  Rows longer than the segment capacity get a CTA of their own
 // and a block-wide reduction.  Row blocks are computed once on the host when the matrix is
 // uploaded.  No atomics: results are bit-reproducible.
+//
+// k_spmv_stream (default): the same row-segment idea as a persistent, warp-specialised kernel.  The
+// segment of a row block (col, val and the rowptr slice: three contiguous byte ranges) is pulled
+// into a multi-stage shared-memory ring by TMA bulk copies (cp.async.bulk, UBLKCP) issued by a
+// producer warp, so HBM streaming never waits for the dependent x gathers; four consumer groups
+// of 128 threads take the stages round-robin: gather x, multiply in place, group barrier, one
+// thread per row sums its row.  Identical arithmetic (products rounded, then summed in CSR
+// order), bit-identical to the first kernel.  Measured on B200 (profiles/): k_spmv 3.66 TB/s ->
+// see profiles/RESULTS.md for the streamed kernel.
 #include "ga_decide.cuh"
 #include "ga_reduce.cuh"
+#include "ga_tma.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace ga {
@@ -79,6 +90,192 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Streamed SpMV: persistent CTAs, TMA-staged row blocks.
+template <class T> struct SpmvStreamCfg {
+  static constexpr int CAP = (sizeof(T) == 8) ? 2048 : 1024;  // non-zeros per row block (one pipeline stage)
+  static constexpr int MAXROWS = 512;    // rows per row block
+  static constexpr int GROUPS = 4, GT = 128;
+  static constexpr int THREADS = GROUPS * GT + 32;      // consumer groups + producer warp
+  static constexpr int COL_BYTES = (CAP + 8) * 4;       // +8: 16-byte alignment slack of the segment
+  static constexpr int VAL_BYTES = (CAP + 8) * (int)sizeof(T);
+  static constexpr int RP_BYTES = (MAXROWS + 8) * 4;
+  static constexpr int STAGE_BYTES = COL_BYTES + VAL_BYTES + RP_BYTES;
+  // 6 stages (160 KB / 136 KB): measured on B200, 4 stages lose 20 % on the Laplacian (pipeline too
+  // shallow) while 8 stages (214 KB) leave ~14 KB of L1 and halve the rate of gather-heavy matrices
+  // (the L1 lines double as miss buffers for the x gathers); see profiles/RESULTS.md
+  // The stage count must be >= GROUPS: a consumer group only observes every GROUPS-th phase of the
+  // ring, and mbarrier parity waits are only unambiguous when the awaited phase is at most one
+  // ahead of the last one the group has seen complete.
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int STAGES = 6;
+  static constexpr int smem_bytes(int nst) { return nst * STAGE_BYTES + 2 * MAX_STAGES * 8 + 16; }
+};
+
+template <class T>
+__global__ void __launch_bounds__(SpmvStreamCfg<T>::THREADS, 1)
+k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ rowptr, const int* __restrict__ col,
+              const T* __restrict__ val, const T* __restrict__ x, const T* __restrict__ xh, int nsplit,
+              T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm, int NST) {
+  typedef SpmvStreamCfg<T> C;
+  constexpr int GT = C::GT, GROUPS = C::GROUPS;
+  if (gated && ctl->status != ST_OK) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NST * C::STAGE_BYTES);
+  uint64_t* empty = full + C::MAX_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // contiguous chunk of row blocks per CTA: consecutive blocks share most of their x window, so the
+  // four consumer groups of a CTA (working on adjacent blocks) hit the same L1 lines
+  const int per = ndesc / (int)gridDim.x, rem = ndesc % (int)gridDim.x;
+  const int b_begin = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+  const int b_end = b_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GT / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == GROUPS * GT / 32) {
+    // ---------------- producer warp (one elected lane): three bulk copies per row block
+    if (lane == 0) {
+      int it = 0;
+      int b = b_begin;
+      int4 d = b < b_end ? __ldg(&desc[b]) : make_int4(0, 0, 0, 0);
+      for (; b < b_end; ++b, ++it) {
+        const int bn = b + 1;
+        const int4 dn = bn < b_end ? __ldg(&desc[bn]) : make_int4(0, 0, 0, 0);  // next descriptor in flight
+        const int s = it % NST;
+        const uint32_t ph = (uint32_t)(it / NST) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
+        const int k0a = d.z & ~3, k1a = (d.w + 3) & ~3;
+        const int r0a = d.x & ~3, nrp = (d.y - r0a + 1 + 3) & ~3;
+        const uint32_t nk = (uint32_t)(k1a - k0a);
+        mbar_arrive_expect_tx(&full[s], nk * (4u + (uint32_t)sizeof(T)) + (uint32_t)nrp * 4u);
+        if (nk > 0) {
+          bulk_g2s(st, col + k0a, nk * 4u, &full[s]);
+          bulk_g2s(st + C::COL_BYTES, val + k0a, nk * (uint32_t)sizeof(T), &full[s]);
+        }
+        bulk_g2s(st + C::COL_BYTES + C::VAL_BYTES, rowptr + r0a, (uint32_t)nrp * 4u, &full[s]);
+        d = dn;
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer group g takes row blocks g, g + GROUPS, ... of this CTA's sequence
+  const int g = warp / (GT / 32), gt = tid - g * GT;
+  if (cm) {
+    // fused multi-GPU path: the peers' normalisation kernels push our halo entries; wait for their
+    // sequence flags (set after a system-scope fence) before touching xh (the producer warp is
+    // already streaming the matrix meanwhile)
+    if (gt < cm->world && cm->recv_counts[gt] > 0) spin_until(&cm->peer[cm->rank]->hflags[gt], ctl->hseq);
+    named_bar_sync(1 + g, GT);
+  }
+  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
+  int b = b_begin + g;
+  int4 d = b < b_end ? __ldg(&desc[b]) : make_int4(0, 0, 0, 0);
+  for (int it = g; b < b_end; b += GROUPS, it += GROUPS) {
+    const int bn = b + GROUPS;
+    const int4 dn = bn < b_end ? __ldg(&desc[bn]) : make_int4(0, 0, 0, 0);
+    const int s = it % NST;
+    const uint32_t ph = (uint32_t)(it / NST) & 1u;
+    unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
+    const int k0 = d.z, cnt = d.w - d.z, sh = k0 - (k0 & ~3);
+    const int* cs = reinterpret_cast<const int*>(st) + sh;
+    T* vs = reinterpret_cast<T*>(st + C::COL_BYTES) + sh;
+    const int* rp = reinterpret_cast<const int*>(st + C::COL_BYTES + C::VAL_BYTES) + (d.x - (d.x & ~3));
+    mbar_wait(&full[s], ph);
+    // products in place: vs[k] <- val[k] * x[col[k]], 8 independent gathers in flight per thread
+    for (int k = gt; k < cnt; k += 8 * GT) {
+      int cc[8];
+      T xx[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cc[u] = (k + u * GT < cnt) ? cs[k + u * GT] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xx[u] = cc[u] >= 0 ? xat(cc[u]) : Elem<T>::zero();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (cc[u] >= 0) vs[k + u * GT] = Elem<T>::mul(vs[k + u * GT], xx[u]);
+    }
+    named_bar_sync(1 + g, GT);
+    const int nr = d.y - d.x;
+    for (int r = gt; r < nr; r += GT) {
+      const int a = rp[r] - k0, e = rp[r + 1] - k0;
+      T sum = Elem<T>::zero();
+      for (int q = a; q < e; ++q) Elem<T>::add(sum, vs[q]);
+      y[d.x + r] = sum;
+    }
+    // the stage was written through the generic proxy; the next TMA copy into it is async-proxy
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    d = dn;
+  }
+}
+
+// rows longer than one stage: one CTA per row, block-wide reduction (same order as the v1 path)
+template <class T>
+__global__ void __launch_bounds__(256) k_spmv_long(const int* __restrict__ longrow, const int* __restrict__ rowptr,
+                                                   const int* __restrict__ col, const T* __restrict__ val,
+                                                   const T* __restrict__ x, const T* __restrict__ xh, int nsplit,
+                                                   T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm) {
+  if (gated && ctl->status != ST_OK) return;
+  if (cm) {
+    if (threadIdx.x < (unsigned)cm->world && cm->recv_counts[threadIdx.x] > 0)
+      spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq);
+    __syncthreads();
+  }
+  __shared__ T red[256];
+  const int r = longrow[blockIdx.x], k0 = rowptr[r], k1 = rowptr[r + 1], tid = threadIdx.x;
+  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
+  T s = Elem<T>::zero();
+  for (int k = k0 + tid; k < k1; k += 256) Elem<T>::add(s, Elem<T>::mul(val[k], xat(col[k])));
+  red[tid] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (tid < off) { T a = red[tid]; Elem<T>::add(a, red[tid + off]); red[tid] = a; }
+    __syncthreads();
+  }
+  if (tid == 0) y[r] = red[0];
+}
+
+template <class T>
+static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
+  typedef SpmvStreamCfg<T> C;
+  const bool split = c->world > 1 && &M == &c->A && c->op_kind == 1;
+  const int nsplit = split ? (int)c->n_pad : 2147483647;
+  const DevComm* cm = (split && wait_halo) ? c->devcomm : nullptr;
+  static bool attr_set = false;
+  static int nst = C::STAGES;
+  if (!attr_set) {
+    GA_CUDA(c, cudaFuncSetAttribute(k_spmv_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::smem_bytes(C::MAX_STAGES)));
+    if (const char* e = getenv("GA_SPMV_STAGES")) {  // tuning knob
+      const int v = atoi(e);
+      if (v >= C::GROUPS && v <= C::MAX_STAGES) nst = v;
+    }
+    attr_set = true;
+  }
+  if (M.ndesc > 0) {
+    const int grid = M.ndesc < c->sm_count ? M.ndesc : c->sm_count;
+    k_spmv_stream<T><<<grid, C::THREADS, C::smem_bytes(nst), c->stream>>>(M.desc, M.ndesc, M.rowptr, M.col,
+                                                                         (const T*)M.val, (const T*)x,
+                                                                         (const T*)c->halo, nsplit, (T*)y, c->ctl,
+                                                                         gated ? 1 : 0, cm, nst);
+    GA_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+  }
+  if (M.nlong > 0) {
+    k_spmv_long<T><<<M.nlong, 256, 0, c->stream>>>(M.longrow, M.rowptr, M.col, (const T*)M.val, (const T*)x,
+                                                  (const T*)c->halo, nsplit, (T*)y, c->ctl, gated ? 1 : 0, cm);
+    GA_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+  }
+  return 0;
+}
+
 template <class T>
 static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
   if (M.nblk <= 0) return;
@@ -89,6 +286,13 @@ static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bo
                                                           (split && wait_halo) ? c->devcomm : nullptr);
 }
 static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo = false) {
+  if (c->use_spmv_stream) {
+    switch (c->dtype) {
+      case GA_F64: return spmv_stream_launch_t<double>(c, M, x, y, gated, wait_halo);
+      case GA_C64: return spmv_stream_launch_t<cdbl>(c, M, x, y, gated, wait_halo);
+      default: return spmv_stream_launch_t<ddbl>(c, M, x, y, gated, wait_halo);
+    }
+  }
   switch (c->dtype) {
     case GA_F64: spmv_launch_t<double>(c, M, x, y, gated, wait_halo); break;
     case GA_C64: spmv_launch_t<cdbl>(c, M, x, y, gated, wait_halo); break;
@@ -148,10 +352,37 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
   }
   blk.push_back((int)nrows);
   M.nrows = nrows; M.ncols = ncols; M.nnz = nnz; M.nblk = (int)blk.size() - 1;
-  GA_CUDA(c, cudaMalloc(&M.rowptr, sizeof(int) * ((size_t)nrows + 1)));
-  GA_CUDA(c, cudaMalloc(&M.col, sizeof(int) * (size_t)std::max<i64>(nnz, 1)));
-  GA_CUDA(c, cudaMalloc(&M.val, c->esize * (size_t)std::max<i64>(nnz, 1)));
+  // row blocks of the streamed kernel: <= CAP non-zeros and <= MAXROWS rows; longer rows go to a list
+  std::vector<int4> desc;
+  std::vector<int> longrow;
+  {
+    const int scap = c->esize == 8 ? SpmvStreamCfg<double>::CAP : SpmvStreamCfg<cdbl>::CAP;
+    const int smax = SpmvStreamCfg<double>::MAXROWS;
+    desc.reserve((size_t)(nnz / (scap / 2) + nrows / smax + 16));
+    i64 r0 = 0;
+    while (r0 < nrows) {
+      if (rp[(size_t)r0 + 1] - rp[(size_t)r0] > scap) { longrow.push_back((int)r0); ++r0; continue; }
+      i64 e = r0 + 1;
+      while (e < nrows && (e - r0) < smax && (rp[(size_t)e + 1] - rp[(size_t)r0]) <= scap) ++e;
+      desc.push_back(make_int4((int)r0, (int)e, rp[(size_t)r0], rp[(size_t)e]));
+      r0 = e;
+    }
+  }
+  M.ndesc = (int)desc.size(); M.nlong = (int)longrow.size();
+  // +8 elements: the streamed kernel copies 16-byte aligned supersets of each segment
+  GA_CUDA(c, cudaMalloc(&M.rowptr, sizeof(int) * ((size_t)nrows + 1 + 8)));
+  GA_CUDA(c, cudaMalloc(&M.col, sizeof(int) * (size_t)(std::max<i64>(nnz, 1) + 8)));
+  GA_CUDA(c, cudaMalloc(&M.val, c->esize * (size_t)(std::max<i64>(nnz, 1) + 8)));
+  GA_CUDA(c, cudaMemsetAsync((char*)M.rowptr + sizeof(int) * ((size_t)nrows + 1), 0, sizeof(int) * 8, c->stream));
+  GA_CUDA(c, cudaMemsetAsync((char*)M.col + sizeof(int) * (size_t)std::max<i64>(nnz, 1), 0, sizeof(int) * 8, c->stream));
+  GA_CUDA(c, cudaMemsetAsync((char*)M.val + c->esize * (size_t)std::max<i64>(nnz, 1), 0, c->esize * 8, c->stream));
   GA_CUDA(c, cudaMalloc(&M.rowblk, sizeof(int) * blk.size()));
+  GA_CUDA(c, cudaMalloc(&M.desc, sizeof(int4) * std::max<size_t>(desc.size(), 1)));
+  GA_CUDA(c, cudaMalloc(&M.longrow, sizeof(int) * std::max<size_t>(longrow.size(), 1)));
+  if (!desc.empty())
+    GA_CUDA(c, cudaMemcpyAsync(M.desc, desc.data(), sizeof(int4) * desc.size(), cudaMemcpyHostToDevice, c->stream));
+  if (!longrow.empty())
+    GA_CUDA(c, cudaMemcpyAsync(M.longrow, longrow.data(), sizeof(int) * longrow.size(), cudaMemcpyHostToDevice, c->stream));
   GA_CUDA(c, cudaMemcpyAsync(M.rowptr, rp.data(), sizeof(int) * rp.size(), cudaMemcpyHostToDevice, c->stream));
   GA_CUDA(c, cudaMemcpyAsync(M.rowblk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
   if (col_shift == 0) {

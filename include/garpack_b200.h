@@ -148,6 +148,9 @@ int ga_reset_stats(ga_ctx* ctx);
 int ga_timer_start(ga_ctx* ctx);
 int ga_timer_stop(ga_ctx* ctx, double* ms);
 int ga_profile(ga_ctx* ctx, int enable);
+/* ga_bench_opx: `reps` back-to-back OP*x on device vectors (V[:,0] -> resid), CUDA events on the
+ * library stream; *ms = average per application.  Kernel-level measurement hook only. */
+int ga_bench_opx(ga_ctx* ctx, int reps, double* ms);
 /* debug: out16 == NULL enables an in-kernel globaltimer timeline of the Gram-Schmidt sweep; a later
  * call with out16 != NULL reads the 64 samples (ns) of the most recent sweep launch. */
 int ga_debug_trace(ga_ctx* ctx, uint64_t* out16);

@@ -95,6 +95,50 @@ def test_opx(pkg, syn, O, dtype):
     ctx.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f64", "c64", "dd"])
+def test_opx_stream_vs_first_kernel_bitwise(pkg, O, dtype, monkeypatch):
+    """The TMA-streamed SpMV and the first row-segment kernel do the same arithmetic in the same
+    order: bit-identical on a matrix with empty rows, ragged segment alignment, a dense band and a
+    row that takes the long-row path in both (7001 non-zeros).  Rows with 2049..4096 non-zeros are
+    summed sequentially by the first kernel and by the long-row tree in the streamed one: those
+    agree to rounding only."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    n = 7001
+    A = sp.random(n, n, density=3.0 / n, random_state=rng, format="lil", dtype=np.float64)
+    A[17, :] = rng.standard_normal(n)            # 7001 non-zeros: long-row path
+    A[4000, : 2049] = 1.5                         # just above one stage
+    A[4001, : 2048] = -0.5                        # exactly one stage
+    for r in range(100, 160):                     # empty rows
+        A[r, :] = 0.0
+    for r in range(5000, 5040):                   # dense-ish band: few rows per block
+        A[r, 100:700] = rng.standard_normal(600)
+    A = A.tocsr()
+    A.eliminate_zeros()
+    if dtype == "c64":
+        B = A.copy().astype(np.complex128)
+        B.data = B.data * np.exp(1j * rng.uniform(0, 6.28, B.nnz))
+        A = B
+    x, _ = O.dlarnv(n, dtype=DT[dtype])
+    xin = pkg.as_dd(x) if dtype == "dd" else x
+    outs = []
+    for v1 in ("1", "0"):
+        monkeypatch.setenv("GA_SPMV_V1", v1)
+        ctx = pkg.Context(pkg.ArpackSimpleOp(A, dtype=dtype), 2)
+        outs.append(np.array(ctx.opx(xin)))
+        ctx.close()
+    nnz_row = np.diff(A.indptr)
+    cap = 2048 if dtype == "f64" else 1024          # SpmvStreamCfg<T>::CAP; the first kernel's is 4096 / 2048
+    same_path = (nnz_row <= cap) | (nnz_row > 2 * cap)
+    assert same_path.sum() >= n - 45
+    assert np.array_equal(outs[0][same_path].view(np.uint64), outs[1][same_path].view(np.uint64))
+    yref = A @ (x[:, 0] if dtype == "dd" else x)
+    got = _dd_float(outs[1]) if dtype == "dd" else outs[1]
+    assert np.allclose(got, yref, rtol=1e-12, atol=1e-12)
+
+
 def test_normal_opx(pkg, syn, O):
     A = syn.to_scipy(syn.tall_sparse(5000, 300, 6))
     op = pkg.ArpackNormalOp(A)

@@ -215,18 +215,31 @@ def run_b200(args):
         "frac_of_nominal_8TBps": round(achieved / 8000.0, 4),
     }
     launches = prof["launches"]
+    timeline = None
+    if args.trace:
+        # in-kernel globaltimer timeline (CTA 0) of the last Gram-Schmidt step kernel of one more cycle
+        ctx.debug_trace()
+        ctx.symeigs_iterate(1)
+        t = ctx.debug_trace(read=True).astype(np.int64)
+        names = ["first_tile", "stream_end", "partials_written", "barrier_A", "cta0_reduced", "exchanged_decided", "barrier_B"]
+        timeline = [{nm: round((int(t[1 + 8 * ph + i]) - int(t[0])) / 1e3, 1) for i, nm in enumerate(names)} for ph in range(3)]
     ctx.close()
 
     # ------------------------------------------------------------ end to end through the host-buffer API
     e2e = None
     if not args.no_e2e:
+        # pinned host destinations for the results (allocated outside the timed region, like the inputs)
+        e2e_bufs = [pinned_copy(np.zeros(r1 - r0))[0], pinned_copy(np.zeros((nev, r1 - r0)))[0]]
         barrier()
         t0 = time.perf_counter()
         ctx2 = make_ctx()                       # allocations + H2D of the CSR matrix (pinned host buffers)
+        ta = time.perf_counter()
         rc = ctx2.symeigs_begin(nev, "LM", 0.0, args.steps, None)
+        tb = time.perf_counter()
         rcit = ctx2.symeigs_iterate(args.steps)
-        resid = ctx2.download_resid()           # D2H: residual vector
-        Vk = ctx2.download_v(0, nev)            # D2H: the nev wanted basis columns
+        tc = time.perf_counter()
+        resid = ctx2.download_resid(out=e2e_bufs[0])           # D2H into pinned host buffers: residual vector
+        Vk = ctx2.download_v(0, nev, out=e2e_bufs[1])          # D2H: the nev wanted basis columns
         st2 = ctx2.stats()
         if dist is not None:
             import torch
@@ -238,6 +251,8 @@ def run_b200(args):
         d2h = resid.nbytes + Vk.nbytes
         e2e = {"value": round(st2["nopx"] / dt, 2), "unit": "steps/s", "h2d_bytes_per_step": int(h2d // max(args.steps, 1)),
                "d2h_bytes_per_step": int(d2h // max(args.steps, 1)), "seconds": round(dt, 3), "lanczos_steps": int(st2["nopx"]),
+               "breakdown_s": {"context_and_upload": round(ta - t0, 3), "start_vector_and_first_nev_steps": round(tb - ta, 3),
+                               "restart_cycles": round(tc - tb, 3), "download": round(t1 - tc, 3)},
                "what": "Context(A_host)+symeigs_begin+%d restart cycles+download resid and V[:,1:nev]; per-rank bytes" % args.steps}
         ctx2.close()
         del resid, Vk
@@ -281,6 +296,8 @@ def run_b200(args):
         }
         if tts is not None:
             out["time_to_solution"] = tts
+        if timeline is not None:
+            out["gs_step_timeline_us"] = timeline
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -376,6 +393,7 @@ def main():
     ap.add_argument("--ncv", type=int, default=40)
     ap.add_argument("--tts", action="store_true", help="also run the full solve (time to solution)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="add the in-kernel timeline of one Gram-Schmidt step kernel (debug)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl-only", action="store_true", help="multi-GPU: NCCL all-gather/send-recv instead of the fused peer-memory path")
     ap.add_argument("--cpu-budget", type=float, default=25.0)

@@ -296,8 +296,11 @@ class Context:
         assert x.shape[0] == self.n
         self._ck(lib().ga_upload_resid(self.h, _p(x)))
 
-    def download_resid(self):
-        x = np.zeros((self.n,) + _eshape(self.dtype), dtype=_np_dtype(self.dtype))
+    def download_resid(self, out=None):
+        """out: optional preallocated (e.g. pinned) host array of the result's shape."""
+        shape = (self.n,) + _eshape(self.dtype)
+        x = np.zeros(shape, dtype=_np_dtype(self.dtype)) if out is None else out
+        assert x.shape == shape and x.flags.c_contiguous
         self._ck(lib().ga_download_resid(self.h, _p(x)))
         return x
 
@@ -307,9 +310,12 @@ class Context:
         Vt = np.ascontiguousarray(np.swapaxes(to_elem(V, self.dtype), 0, 1))  # [col][row](,2)
         self._ck(lib().ga_upload_v(self.h, col0, k, _p(Vt), self.n))
 
-    def download_v(self, col0=0, ncols=None):
+    def download_v(self, col0=0, ncols=None, out=None):
+        """out: optional preallocated (e.g. pinned) host array of shape (ncols, n[, 2]) = V columns as rows."""
         ncols = self.ncv - col0 if ncols is None else ncols
-        Vt = np.zeros((ncols, self.n) + _eshape(self.dtype), dtype=_np_dtype(self.dtype))
+        shape = (ncols, self.n) + _eshape(self.dtype)
+        Vt = np.zeros(shape, dtype=_np_dtype(self.dtype)) if out is None else out
+        assert Vt.shape == shape and Vt.flags.c_contiguous
         self._ck(lib().ga_download_v(self.h, col0, ncols, _p(Vt), self.n))
         return np.swapaxes(Vt, 0, 1)
 

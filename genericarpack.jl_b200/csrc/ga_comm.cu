@@ -72,8 +72,19 @@ int comm_init(ga_ctx* c, const void* id128) {
   NcclApi& a = nccl();
   if (!a.ok) return set_err(c, GA_ERR_COMM, "libnccl.so.2 could not be loaded");
   if (c->world <= 1) return 0;
+  // The communicator is created on first use (ncclCommInitRank costs ~1 s and the fused
+  // peer-memory path never needs it on the per-step path); creation is collective, and so is every
+  // code path that reaches it.
+  c->nccl_id.assign((const char*)id128, (const char*)id128 + sizeof(ncclUniqueId));
+  return 0;
+}
+
+static int comm_ensure(ga_ctx* c) {
+  if (c->nccl_comm) return 0;
+  if (c->nccl_id.size() != sizeof(ncclUniqueId)) return set_err(c, GA_ERR_COMM, "ga_comm_init was not called");
+  NcclApi& a = nccl();
   ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
+  memcpy(&id, c->nccl_id.data(), sizeof(id));
   ncclComm_t comm;
   GA_CUDA(c, cudaSetDevice(c->device));
   GA_NCCL(c, a.CommInitRank(&comm, c->world, id, c->rank));
@@ -146,7 +157,7 @@ void comm_destroy(ga_ctx* c) {
 int comm_allgather_slots(ga_ctx* c, int nslots) {
   (void)nslots;
   if (c->world <= 1) return 0;
-  if (!c->nccl_comm) return set_err(c, GA_ERR_COMM, "ga_comm_init was not called");
+  if (int rc = comm_ensure(c)) return rc;
   GA_NCCL(c, nccl().AllGather(c->ctl->red, c->gather, (size_t)kMaxSlots * 2, ncclFloat64, (ncclComm_t)c->nccl_comm,
                               c->stream));
   return 0;
@@ -163,7 +174,7 @@ __global__ void k_pack(const T* __restrict__ x, const int* __restrict__ idx, T* 
 // peers' rows reference, then one grouped ncclSend/ncclRecv round moves them over NVLink.
 int comm_halo_exchange(ga_ctx* c, const void* x_local) {
   if (c->world <= 1) return 0;
-  if (!c->nccl_comm) return set_err(c, GA_ERR_COMM, "ga_comm_init was not called");
+  if (int rc = comm_ensure(c)) return rc;
   NcclApi& a = nccl();
   if (c->nsend > 0) {
     const int threads = 256, blocks = (c->nsend + threads - 1) / threads;

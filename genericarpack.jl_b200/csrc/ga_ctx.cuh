@@ -59,6 +59,10 @@ struct Mailbox {
   double2 slots[2][kMaxWorld][kMaxSlots];   // [parity][source rank][slot]
   unsigned int flags[2][kMaxWorld];         // [parity][source rank] = seq when the slots are complete
   unsigned int hflags[kMaxWorld];           // [source rank] = hseq when that peer's halo entries landed
+  // low-latency slot exchange: every 16-byte slot travels as four 8-byte words {32 data bits, seq};
+  // an aligned 8-byte store is a single NVLink transaction, so data and flag arrive together and the
+  // receiver needs neither a system-scope fence nor a second round trip for a separate flag
+  unsigned long long ll[2][kMaxWorld][4 * kMaxSlots];   // [parity][source rank][4 * slot + word]
 };
 struct DevComm {
   int rank, world;
@@ -120,6 +124,7 @@ struct ga_ctx {
 
   // collectives (NCCL, loaded at run time)
   void* nccl_comm = nullptr;
+  std::string nccl_id;       // 128-byte unique id; the communicator is created on first use
   // halo plan of the row-sharded SpMV (multi-GPU): which local entries each peer needs from me
   // (send_idx grouped by peer) and how many entries I receive from each peer (halo = concatenation
   // in peer order = ascending global column order).

@@ -203,11 +203,23 @@ __device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int w
   return false;
 }
 
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Called by all threads of the last CTA after last_block_reduce left this GPU's sums in
-// ctl->red.  Every rank stores its slots into every peer's mailbox (P2P stores), publishes a
-// sequence-numbered flag, waits for the peers' flags and sums the world's slots in rank order,
-// so ctl->red ends up bit-identical on all GPUs.  This is the collective of the Gram-Schmidt
-// sweep, executed inside the sweep kernel itself.
+// ctl->red.  Every rank stores its slots into every peer's mailbox (P2P stores over NVLink) and
+// sums the world's slots in rank order, so ctl->red ends up bit-identical on all GPUs.  This is
+// the collective of the Gram-Schmidt sweep, executed inside the sweep kernel itself.
+// Low-latency protocol: each 16-byte slot is sent as four 8-byte words {32 data bits, sequence
+// number}; the receiver spins on the words themselves (one warp per slot: lane = 4 * source rank +
+// word), so one one-way NVLink latency separates the last sender from the result -- no
+// system-scope fence, no separate flag round.
 template <bool CPLX_DOT>
 __device__ __forceinline__ void comm_exchange_slots(DevCtl* ctl, const DevComm* cm, int ndot, int nslots) {
   __shared__ unsigned int sh_seq;
@@ -215,28 +227,40 @@ __device__ __forceinline__ void comm_exchange_slots(DevCtl* ctl, const DevComm* 
   __syncthreads();
   const unsigned int seq = sh_seq, par = seq & 1u;
   const int rank = cm->rank, world = cm->world;
-  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
-    const double2 v = ctl->red[s];
-    for (int q = 0; q < world; ++q) st_sys_d2(&cm->peer[q]->slots[par][rank][s], v);
+  const unsigned int* red32 = reinterpret_cast<const unsigned int*>(ctl->red);
+  for (int i = threadIdx.x; i < 4 * nslots; i += blockDim.x) {
+    const unsigned long long w = ((unsigned long long)seq << 32) | (unsigned long long)red32[i];
+    for (int q = 0; q < world; ++q) st_sys_u64(&cm->peer[q]->ll[par][rank][i], w);
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < world) {
-    st_sys_u32(&cm->peer[threadIdx.x]->flags[par][rank], seq);
-    if (!spin_until(&cm->peer[rank]->flags[par][threadIdx.x], seq)) ctl->status = ST_COMM;
-  }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();   // everybody has read ctl->red before it is overwritten below
   const Mailbox* me = cm->peer[rank];
-  for (int s = threadIdx.x; s < nslots; s += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int q = lane >> 2, e = lane & 3;
+  bool ok = true;
+  for (int s = warp; s < nslots; s += nwarps) {
+    unsigned int word = 0u;
+    if (q < world) {
+      const unsigned long long* p = &me->ll[par][q][4 * s + e];
+      unsigned long long w = ld_sys_u64(p);
+      for (long long it = 0; (unsigned int)(w >> 32) != seq; ++it) {
+        if (it > (1LL << 24)) { ok = false; break; }
+        if (it > 4096) __nanosleep(32);
+        w = ld_sys_u64(p);
+      }
+      word = (unsigned int)w;
+    }
+    // lanes 4q..4q+3 hold x.lo32, x.hi32, y.lo32, y.hi32 of source rank q
+    const unsigned int up = __shfl_down_sync(0xffffffffu, word, 1);
+    const double val = __hiloint2double((int)up, (int)word);      // valid in lanes with e = 0 (x) and e = 2 (y)
     const bool cplx = CPLX_DOT && s < ndot;
     double2 acc = make_double2(0.0, 0.0);
-    for (int q = 0; q < world; ++q) {
-      const double2 v = ld_sys_d2(&me->slots[par][q][s]);
-      acc = cplx ? slot_add<true>(acc, v) : slot_add<false>(acc, v);
+    for (int r = 0; r < world; ++r) {                              // rank order: identical on every GPU
+      const double vx = __shfl_sync(0xffffffffu, val, 4 * r), vy = __shfl_sync(0xffffffffu, val, 4 * r + 2);
+      acc = cplx ? slot_add<true>(acc, make_double2(vx, vy)) : slot_add<false>(acc, make_double2(vx, vy));
     }
-    ctl->red[s] = acc;
+    if (lane == 0) ctl->red[s] = acc;
   }
+  if (!ok) ctl->status = ST_COMM;
   if (threadIdx.x == 0) ctl->seq = seq;
   __syncthreads();
 }

@@ -33,6 +33,7 @@ _SO = os.path.join(_HERE, "libgarpack_b200.so")
 _LIB = None
 
 GA_F64, GA_C64, GA_DD = 0, 1, 2
+GA_ERR_CUDA, GA_ERR_ARG, GA_ERR_NOOP, GA_ERR_COMM, GA_ERR_NUMERIC = -100, -101, -102, -103, -104
 _DTYPES = {"f64": GA_F64, "float64": GA_F64, "c64": GA_C64, "complex128": GA_C64, "dd": GA_DD, "double64": GA_DD,
            GA_F64: GA_F64, GA_C64: GA_C64, GA_DD: GA_DD}
 _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
@@ -41,7 +42,7 @@ _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
-    "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_norm2_resid",
+    "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_bench_opx", "ga_debug_trace", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
@@ -111,6 +112,7 @@ def lib():
         L.ga_apply_shifts.argtypes = [vp, i32, i32, vp, i32, vp, vp]
         L.ga_ritz_vectors.argtypes = [vp, i32, vp, i32, vp, i64]
         L.ga_norm2_resid.argtypes = [vp, vp]
+        L.ga_svd_vectors.argtypes = [vp, i32, vp, vp, i64, vp]
         L.ga_get_stats.argtypes = [vp, ctypes.POINTER(ga_stats)]
         L.ga_reset_stats.argtypes = [vp]
         L.ga_timer_start.argtypes = [vp]
@@ -526,17 +528,82 @@ def hermeigs(A, k, **kw):  # src/interface.jl:158-168
     return symeigs(A, k, **kw)
 
 
+class SVD:
+    """LinearAlgebra.SVD(U, S, Vt) as returned by the reference's svds (src/interface.jl:336);
+    iterates as (U, S, V) like Julia's destructuring."""
+
+    def __init__(self, U, S, Vt, einfo=None):
+        self.U, self.S, self.Vt, self.einfo = U, S, Vt, einfo
+
+    @property
+    def V(self):
+        return None if self.Vt is None else np.conj(self.Vt).T
+
+    def __iter__(self):
+        yield self.U
+        yield self.S
+        yield self.V
+
+
 def svds(A, k, *, which="LM", dtype=None, **kw):
-    """svds(A, k) (src/interface.jl:304-337) via ArpackNormalOp: singular values (largest first
-    for which=:LM) and right/left singular vectors.  The Lanczos iteration on A'A / AA' runs on
-    the device; turning eigenvectors into the other side's singular vectors
-    (eigenvecs_to_singvecs!, src/idonow_ops.jl:295-333) uses the device OP for A*v and a host QR --
-    SURVEY.md section 8(f) rank 1 ("next")."""
+    """svds(A, k; which, kwargs...) (src/interface.jl:304-337) via ArpackNormalOp.
+
+    The Lanczos iteration on A'A (m > n) / AA' (m <= n) runs on the device; so does
+    eigenvecs_to_singvecs! + orth! (src/idonow_ops.jl:279-333, C ABI ga_svd_vectors): the other side's
+    vectors A v_i / A' u_i, their norms, scaling and the orthonormalisation.  Returns SVD(U, S, V')
+    with singular values largest first for which in (LM, LA), smallest first for (SA, SM)."""
+    import warnings
+
     op = _as_op(A, dtype, normal=True)
-    arwhich = {"LM": "LM", "LA": "LM", "SM": "SA", "SA": "SA", "BE": "BE"}[which]  # :240-253
-    einfo = symeigs(op, k, which=arwhich, **kw)
-    vals = np.sqrt(np.maximum(einfo.values, 0.0))                    # :255-260
-    order = np.argsort(-vals, kind="stable") if which in ("LM", "LA") else np.argsort(vals, kind="stable")
-    S = vals[order]
-    Z = None if einfo.vectors is None else einfo.vectors[:, order]
-    return S, Z, einfo
+    if which not in ("LM", "LA", "SM", "SA", "BE"):
+        raise ValueError("which = %s is not valid for SVD of ArpackNormalOp" % which)     # :252
+    arwhich = {"LM": "LM", "LA": "LM", "SM": "SA", "SA": "SA", "BE": "BE"}[which]         # :240-253
+    ritzvec = kw.get("ritzvec", True)
+    einfo = symeigs(op, k, which=arwhich, keep_context=True, **kw)
+    ctx = einfo.ctx
+    try:
+        vals = np.sqrt(np.maximum(dd_to_float(einfo.values) if op.dtype == GA_DD else einfo.values, 0.0))  # :255-260
+        if which in ("LM", "LA"):                                         # src/interface.jl:323-329
+            order = np.argsort(-vals, kind="stable")
+        elif which in ("SA", "SM"):
+            order = np.argsort(vals, kind="stable")
+        else:
+            order = np.arange(len(vals))
+        S = vals[order]
+        m, n = op.shape
+        if not ritzvec or einfo.vectors is None or einfo.vectors.shape[1] == 0:
+            es = _eshape(op.dtype)
+            return SVD(np.zeros((m, 0) + es), S, np.zeros((0, n) + es), einfo)
+        nvec = einfo.vectors.shape[1]
+        order = order[:nvec]
+        Z = einfo.vectors[:, order]
+        other = m if op.At_side == "left" else n
+        Wt = np.zeros((nvec, other) + _eshape(op.dtype), dtype=_np_dtype(op.dtype))
+        norms = np.zeros((nvec, 2))
+        perm = np.ascontiguousarray(order, dtype=np.int32)
+        rc = lib().ga_svd_vectors(ctx.h, nvec, _p(perm), _p(Wt), other, _p(norms))
+        nr = norms.reshape(-1)[:nvec] if op.dtype != GA_DD else norms[:, 0]
+        eps = 4.930380657631324e-32 if op.dtype == GA_DD else np.finfo(np.float64).eps
+        side = "U" if op.At_side == "left" else "V"
+        if rc == GA_ERR_NUMERIC or (rc == 0 and np.any(nr <= eps / 2)):   # check_norm (src/idonow_ops.jl:300-306)
+            raise ArpackException("encountered sigma ~ %g when computing %s subspace" % (float(np.min(nr)), side))
+        ctx._ck(rc)
+        if np.any(nr <= eps ** (2.0 / 3.0)):
+            warnings.warn("%s subspace may be inaccurate due to small singular value (sigma ~ %g)" % (side, float(np.min(nr))))
+        W = np.swapaxes(Wt, 0, 1)
+        U, V = (W, Z) if op.At_side == "left" else (Z, W)
+        if op.dtype == GA_C64:
+            Vt = np.conj(V).T
+        elif op.dtype == GA_DD:
+            Vt = np.swapaxes(V, 0, 1)
+        else:
+            Vt = V.T
+        return SVD(U, S, Vt, einfo)
+    finally:
+        ctx.close()
+        einfo.ctx = None
+
+
+def svd_residuals(A, U, s, V):
+    """svd_residuals (src/interface.jl:388-407): ||A V[:,i] - U[:,i] s[i]|| (host helper, Float64/ComplexF64)."""
+    return np.array([float(np.linalg.norm(A @ V[:, i] - U[:, i] * s[i])) for i in range(len(s))])

@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ga_ctx.cuh"
 
@@ -89,6 +90,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   CK(cudaMalloc(&c->resid, (size_t)c->n_pad * c->esize));
   CK(cudaMemsetAsync(c->V, 0, (size_t)c->n_pad * ncv * c->esize, c->stream));
   CK(cudaMemsetAsync(c->resid, 0, (size_t)c->n_pad * c->esize, c->stream));
+  c->vs.V = c->V; c->vs.w = c->resid; c->vs.ld = c->n_pad; c->vs.rows = c->n;
   CK(cudaMalloc(&c->ctl, sizeof(DevCtl)));
   CK(cudaMemsetAsync(c->ctl, 0, sizeof(DevCtl), c->stream));
   CK(cudaMallocHost(&c->ctl_host, sizeof(DevCtl)));
@@ -111,7 +113,7 @@ void ga_destroy(ga_ctx* c) {
   c->A.free_all();
   c->At.free_all();
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
-  cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev);
+  cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev); cudaFree(c->wbuf);
   cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -466,6 +468,64 @@ int ga_ritz_vectors(ga_ctx* c, int nconv, const void* Qh, int ldq, void* z_host,
   if (rc) return rc;
   GA_CUDA(c, cudaStreamSynchronize(c->stream));
   if (z_host && nconv > 0) rc = ga_download_v(c, 0, nconv, z_host, ldz);  // Z <- V[:,1:nconv] (:1434)
+  c->stats.trvec += now_s() - t0;
+  return rc;
+}
+
+// ------------------------------------------------------------------ svds: eigenvecs_to_singvecs! + orth!
+int ga_svd_vectors(ga_ctx* c, int nvec, const int32_t* perm, void* w_host, int64_t ldw, double* norms_out) {
+  if (!c || !perm || !norms_out || nvec < 1 || nvec > c->ncv) return GA_ERR_ARG;
+  if (c->op_kind != 2) return set_err(c, GA_ERR_NOOP, "ga_svd_vectors needs a normal-operator context");
+  for (int i = 0; i < nvec; ++i)
+    if (perm[i] < 0 || perm[i] >= c->ncv) return GA_ERR_ARG;
+  const i64 other = c->normal_left ? c->normal_m : c->normal_n;   // rows of the other side's vectors
+  if (w_host && ldw < other) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  const double t0 = now_s();
+  const size_t rs = real_size(c);
+  const i64 ld = (other + kRowPad - 1) / kRowPad * kRowPad;
+  if (!c->wbuf || c->wbuf_ld != ld || c->wbuf_cols < nvec) {
+    cudaFree(c->wbuf);
+    c->wbuf = nullptr;
+    GA_CUDA(c, cudaMalloc(&c->wbuf, (size_t)ld * nvec * c->esize));
+    c->wbuf_ld = ld; c->wbuf_cols = nvec;
+  }
+  GA_CUDA(c, cudaMemsetAsync(c->wbuf, 0, (size_t)ld * nvec * c->esize, c->stream));  // padding rows stay zero
+  void* norms_dev = nullptr;
+  GA_CUDA(c, cudaMalloc(&norms_dev, 16 * (size_t)nvec));
+  int rc = reset_status(c);
+  const ga_ctx::VSpace saved = c->vs;
+  for (int i = 0; i < nvec && rc == 0; ++i) {
+    char* wi = (char*)c->wbuf + (size_t)i * ld * c->esize;
+    rc = launch_normal_half(c, (const char*)c->V + (size_t)perm[i] * c->n_pad * c->esize, wi);   // :311 / :322
+    if (rc) break;
+    c->vs.V = c->wbuf; c->vs.w = wi; c->vs.ld = ld; c->vs.rows = other;
+    if ((rc = launch_norm_resid(c, DK_NORM))) break;                       // nrm = norm(U[:,i])  (:313)
+    if (cudaMemcpyAsync((char*)norms_dev + 16 * (size_t)i, c->ctl->rnorm, 16, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { rc = GA_ERR_CUDA; break; }
+    if ((rc = launch_normalize(c, i, false))) break;                      // _scale_from_to(nrm, 1, U[:,i])  (:315)
+    if (i == 0) continue;                                                 // orth!: first column is already unit
+    if ((rc = launch_gs(c, 0, i, -1, DK_GETV0_DOT))) break;               // h = W_i' w
+    if ((rc = launch_gs(c, 1, i, -1, DK_GETV0_UPD))) break;               // w -= W_i h ; s = W_i' w
+    if ((rc = launch_gs(c, 2, i, -1, DK_NORM))) break;                    // w -= W_i s ; ||w||
+    if ((rc = launch_normalize(c, i, false))) break;                      // unit column, R[i,i] > 0
+  }
+  c->vs = saved;
+  if (rc == 0) rc = sync_ctl(c);
+  if (rc == 0 && c->ctl_host->status != ST_OK)
+    rc = set_err(c, GA_ERR_NUMERIC, "svd vectors: a column of A*V vanished or is not finite");
+  if (rc == 0) {
+    std::vector<double> nb(2 * (size_t)nvec);
+    cudaError_t e = cudaMemcpy(nb.data(), norms_dev, 16 * (size_t)nvec, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = set_err(c, GA_ERR_CUDA, cudaGetErrorString(e));
+    for (int i = 0; i < nvec && rc == 0; ++i) memcpy((char*)norms_out + rs * (size_t)i, &nb[2 * (size_t)i], rs);
+  }
+  cudaFree(norms_dev);
+  if (rc == 0 && w_host) {
+    cudaError_t e = cudaMemcpy2DAsync(w_host, (size_t)ldw * c->esize, c->wbuf, (size_t)ld * c->esize,
+                                      (size_t)other * c->esize, nvec, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_err(c, GA_ERR_CUDA, cudaGetErrorString(e));
+  }
   c->stats.trvec += now_s() - t0;
   return rc;
 }

@@ -107,6 +107,11 @@ struct ga_ctx {
   // big arrays (element type T), all n_pad long with zero padding rows
   void* V = nullptr;       // n_pad x ncv, column-major, ld = n_pad
   void* resid = nullptr;   // n_pad   (also holds w = OP v_j before orthogonalisation, like the reference)
+  // The tall-skinny kernels (Gram-Schmidt sweeps, norm, scale) run on the "active vector space":
+  // a basis (ld = padded row count, zero padding rows) and the vector being orthogonalised.  It is
+  // (V, resid) except while ga_svd_vectors orthonormalises the other side's singular vectors.
+  struct VSpace { void* V = nullptr; void* w = nullptr; ga::i64 ld = 0, rows = 0; } vs;
+  void* wbuf = nullptr; ga::i64 wbuf_ld = 0; int wbuf_cols = 0;   // other-side singular vectors (svds)
   void* xfull = nullptr;   // normal operator: scratch vector of length max(m, n)
   ga::i64 xfull_len = 0;
 
@@ -174,11 +179,12 @@ int set_err(ga_ctx* c, int code, const std::string& msg);
 int launch_lcg_fill(ga_ctx* c, const i64 iseed[4]);
 void lcg_advance_seed(i64 iseed[4], i64 nvalues);
 // k_vec.cu
-int launch_normalize(ga_ctx* c, int jcol);                 // V[:,jcol] = resid / rnorm (device rnorm)
+int launch_normalize(ga_ctx* c, int jcol, bool push_halo = true);  // vs.V[:,jcol] = vs.w / rnorm (device rnorm)
 int launch_norm_resid(ga_ctx* c, int decide_kind);         // ||resid|| -> ctl
 int launch_zero_resid(ga_ctx* c);
 // k_spmv.cu
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated);  // y = OP x (device vectors)
+int launch_normal_half(ga_ctx* c, const void* x, void* y);       // y = A x or A^H x (svds post-processing)
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift);
 // k_gs.cu

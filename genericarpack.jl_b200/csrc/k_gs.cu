@@ -220,7 +220,7 @@ __global__ void k_decide(DevCtl* ctl, const double2* gathered, int world, int j,
 template <class T, int MODE, int SEG>
 static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int nstages) {
   typedef GsCfg<T, SEG> C;
-  const i64 ntiles = c->n_pad / C::R;
+  const i64 ntiles = c->vs.ld / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
   const size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
   static bool attr_set = false;
@@ -230,8 +230,8 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
   if (grid > kMaxCtas) grid = kMaxCtas;
-  const T* V = (const T*)c->V;
-  T* r = (T*)c->resid;
+  const T* V = (const T*)c->vs.V;
+  T* r = (T*)c->vs.w;
   const bool fused = c->world == 1 || c->devcomm != nullptr;  // decide inside the sweep kernel
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->prof) {
@@ -242,7 +242,7 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
     c->prof_used += 2;
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
-  k_gs<T, MODE, SEG><<<grid, C::THREADS, smem, c->stream>>>(V, c->n_pad, j, r, r, ntiles, c->ctl, c->partial, nstages,
+  k_gs<T, MODE, SEG><<<grid, C::THREADS, smem, c->stream>>>(V, c->vs.ld, j, r, r, ntiles, c->ctl, c->partial, nstages,
                                                            gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
                                                            c->world > 1 ? c->devcomm : nullptr, c->trace,
                                                            (int)(c->gs_flip++ & 1));

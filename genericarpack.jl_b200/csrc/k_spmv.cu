@@ -329,6 +329,14 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   }
 }
 
+// First half of the normal operator on device vectors: y = A x (At_side = :left, y has m rows) or
+// y = A^H x (:right, y has n rows): what eigenvecs_to_singvecs! applies to each eigenvector
+// (src/idonow_ops.jl:311,322).
+int launch_normal_half(ga_ctx* c, const void* x, void* y) {
+  if (c->op_kind != 2) return set_err(c, GA_ERR_NOOP, "not a normal-operator context (ga_set_normal_csr)");
+  return spmv_launch(c, c->normal_left ? c->A : c->At, x, y, false);
+}
+
 // Upload a host CSR (int64 rowptr, int32 col, T val) and build the row blocks.
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift) {

@@ -43,7 +43,7 @@ __device__ __forceinline__ T scaled_by_inv_norm(T x, TR rnorm, TR temp1, bool sa
 // a sequence flag in each peer's mailbox; the peers' SpMV waits on that flag.  No pack kernel, no
 // NCCL send/recv on the per-step path.
 template <class T>
-__global__ void __launch_bounds__(256) k_normalize(T* __restrict__ vj, const T* __restrict__ resid, i64 n,
+__global__ void __launch_bounds__(256) k_normalize(T* vj, const T* resid, i64 n,  // vj may alias resid (in-place scaling)
                                                    DevCtl* ctl, int jstep, const DevComm* cm,
                                                    const int* __restrict__ send_idx) {
   typedef typename Elem<T>::real_t TR;
@@ -85,25 +85,26 @@ __global__ void __launch_bounds__(256) k_normalize(T* __restrict__ vj, const T* 
   if (threadIdx.x == 0) { ctl->hseq = hseq; ctl->ticket = 0u; }
 }
 
-int launch_normalize(ga_ctx* c, int jcol) {
+int launch_normalize(ga_ctx* c, int jcol, bool push_halo) {
   const int threads = 256;
-  i64 blocks = (c->n + threads - 1) / threads;
+  const i64 n = c->vs.rows, ld = c->vs.ld;
+  i64 blocks = (n + threads - 1) / threads;
   const i64 maxb = (i64)c->sm_count * 8;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
-  const DevComm* cm = c->world > 1 ? c->devcomm : nullptr;
+  const DevComm* cm = (c->world > 1 && push_halo) ? c->devcomm : nullptr;
   switch (c->dtype) {
     case GA_F64:
-      k_normalize<double><<<(int)blocks, threads, 0, c->stream>>>((double*)c->V + (size_t)jcol * c->n_pad,
-                                                                 (const double*)c->resid, c->n, c->ctl, jcol + 1, cm, c->send_idx);
+      k_normalize<double><<<(int)blocks, threads, 0, c->stream>>>((double*)c->vs.V + (size_t)jcol * ld,
+                                                                 (const double*)c->vs.w, n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
     case GA_C64:
-      k_normalize<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)c->V + (size_t)jcol * c->n_pad,
-                                                               (const cdbl*)c->resid, c->n, c->ctl, jcol + 1, cm, c->send_idx);
+      k_normalize<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)c->vs.V + (size_t)jcol * ld,
+                                                               (const cdbl*)c->vs.w, n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
     default:
-      k_normalize<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->V + (size_t)jcol * c->n_pad,
-                                                               (const ddbl*)c->resid, c->n, c->ctl, jcol + 1, cm, c->send_idx);
+      k_normalize<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->vs.V + (size_t)jcol * ld,
+                                                               (const ddbl*)c->vs.w, n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
   }
   GA_CUDA(c, cudaGetLastError());
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(256) k_norm(const T* __restrict__ x, i64 n, De
 
 int launch_norm_resid(ga_ctx* c, int decide_kind) {
   const int threads = 256;
-  i64 blocks = (c->n + threads * 4 - 1) / (threads * 4);
+  const i64 n = c->vs.rows;
+  i64 blocks = (n + threads * 4 - 1) / (threads * 4);
   const i64 maxb = (i64)c->sm_count * 4;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
@@ -152,9 +154,9 @@ int launch_norm_resid(ga_ctx* c, int decide_kind) {
   const int dk = single ? decide_kind : DK_NONE;
   const DevComm* cm = c->world > 1 ? c->devcomm : nullptr;
   switch (c->dtype) {
-    case GA_F64: k_norm<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, cm); break;
-    case GA_C64: k_norm<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, cm); break;
-    default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->resid, c->n, c->ctl, c->partial, dk, c->ncv, cm); break;
+    case GA_F64: k_norm<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
+    case GA_C64: k_norm<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
+    default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;

@@ -132,6 +132,20 @@ int ga_apply_shifts(ga_ctx* ctx, int kev, int np, const void* Q, int ldq, const 
  * reference leaves V), Z <- V[:,1:nconv] copied to z_host (ldz >= n_local) when z_host != NULL. */
 int ga_ritz_vectors(ga_ctx* ctx, int nconv, const void* Qh, int ldq, void* z_host, int64_t ldz);
 
+/* ---- svds post-processing: eigenvecs_to_singvecs! + orth! (src/idonow_ops.jl:279-333) -----------
+ * For an ArpackNormalOp context whose basis columns V[:,perm[i]], i < nvec, hold the wanted
+ * eigenvectors of A^H A (At_side = :left) or A A^H (:right) -- e.g. after ga_symeigs_end / ga_ritz_vectors:
+ *   W[:,i] = A V[:,perm[i]]  (or A^H V[:,perm[i]]),  norms_out[i] = ||W[:,i]||,  W[:,i] /= norms_out[i]
+ *   (_scale_from_to),  then orth!(W).
+ * The reference's orth! is Householder QR (_dgeqr2!) + dorg2r! + a column sign fix that makes R's
+ * diagonal positive, i.e. the unique thin-QR Q factor; here the same Q is formed on the device by
+ * classical Gram-Schmidt with one full reorthogonalisation per column (the fused tall-skinny sweeps
+ * of the Lanczos step, overflow-safe norms), all nvec columns without a host round trip.
+ * w_host: (other dimension) x nvec, ldw >= other dimension (m for :left, n for :right).
+ * norms_out: nvec reals (the caller applies the reference's check_norm thresholds, :300-306).
+ * Returns 0, GA_ERR_NOOP for a non-normal context, GA_ERR_NUMERIC if a column vanished. */
+int ga_svd_vectors(ga_ctx* ctx, int nvec, const int32_t* perm, void* w_host, int64_t ldw, double* norms_out);
+
 /* ---- small device services used by tests and by the Julia shim ---------------------------------
  * ga_norm2: norm2(TR, resid) (src/arpack-blas-nrm2.jl:355-372) of the device resid. */
 int ga_norm2_resid(ga_ctx* ctx, double* out);

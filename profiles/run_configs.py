@@ -92,13 +92,21 @@ def main():
         t0 = time.perf_counter()
         csr5 = syn.tall_sparse(m5, n5, 10)
         tgen = time.perf_counter() - t0
-        S, V, einfo = pkg.svds(pkg.ArpackNormalOp(csr5), 20, ncv=60, keep_context=False)
+        t0 = time.perf_counter()
+        sv = pkg.svds(pkg.ArpackNormalOp(csr5), 20, ncv=60)
+        tsolve = time.perf_counter() - t0
+        U, S, V = sv
+        einfo = sv.einfo
         A5 = syn.to_scipy(csr5)
         resid = float(np.max(np.linalg.norm(A5.T @ (A5 @ V) - V * (S ** 2), axis=0) / (S ** 2)))
+        svd_resid = float(np.max(np.linalg.norm(A5 @ V - U * S, axis=0) / S))
+        u_orth = float(np.max(np.abs(U.T @ U - np.eye(U.shape[1]))))
         res["C5 svds tall sparse %dx%d nnz=%d k=20 ncv=60 (scale %.2f of 50Mx2M)" % (m5, n5, len(csr5[1]), scale)] = {
             "gen_s": round(tgen, 1), "singular_values_top5": [float(s) for s in S[:5]], "restarts": int(einfo.iparam[2]),
             "lanczos_steps": int(einfo.stats["nopx"]), "taitr_s": round(einfo.stats["taitr"], 3),
-            "steps_per_s": round(einfo.stats["nopx"] / max(einfo.stats["taitr"], 1e-9), 1), "max_normal_eq_residual_rel": resid}
+            "steps_per_s": round(einfo.stats["nopx"] / max(einfo.stats["taitr"], 1e-9), 1), "max_normal_eq_residual_rel": resid,
+            "svds_total_s": round(tsolve, 3), "trvec_s": round(einfo.stats["trvec"], 3),
+            "max_svd_residual_rel": svd_resid, "U_orthonormality": u_orth}
     dump()
     if "c2tts" in which:
         m = int(os.environ.get("C2_M", "4000"))

@@ -452,13 +452,86 @@ def test_eigs_double64(pkg, syn, O):
     assert np.allclose(_dd_float(np.asarray(res2.values)), f.values, rtol=1e-12)
 
 
+def _mytestmat(m, n, minval=None, maxdiagval=2.0):
+    """test/utility.jl:259-265"""
+    import scipy.sparse as sp
+
+    minval = 1.0 / m if minval is None else minval
+    v = np.linspace(1.0, minval, m).astype(np.result_type(minval, np.float64))
+    B = sp.coo_matrix((np.linspace(1.0, maxdiagval, n - 1), (np.arange(n - 1), np.arange(n - 1))), shape=(m, n - 1))
+    return sp.hstack([sp.csr_matrix(v.reshape(-1, 1)), B]).tocsr()
+
+
+def _check_svd(A, U, s, V, tol):
+    """check_svd (test/utility.jl:244-253)"""
+    k = len(s)
+    assert np.allclose(U.conj().T @ U, np.eye(k), atol=1e-12)
+    assert np.allclose(V.conj().T @ V, np.eye(k), atol=1e-12)
+    r = [np.linalg.norm(A @ V[:, i] - U[:, i] * s[i]) for i in range(k)]
+    assert max(r) <= np.finfo(np.float64).eps * tol, r
+
+
 def test_svds_normal(pkg, syn):
-    """C5 at reduced size: svds via the normal operator (src/interface.jl:304-337)."""
+    """C5 at reduced size: svds via the normal operator (src/interface.jl:304-337), U and V from the
+    device (ga_svd_vectors) against the CPU oracle's Householder orth! and a dense SVD."""
+    from oracle import oracle_svd as OS
+
     A = syn.to_scipy(syn.tall_sparse(4000, 200, 8))
-    S, V, info = pkg.svds(A, 5, ncv=20)
+    U, S, V = pkg.svds(A, 5, ncv=20)
     s = np.linalg.svd(A.toarray(), compute_uv=False)
     assert np.allclose(S, s[:5], rtol=1e-9)
-    assert np.allclose(V.T @ V, np.eye(5), atol=1e-10)
+    _check_svd(A, U, S, V, tol=200)
+    Uo, So, Vo, _ = OS.svds(A, 5, ncv=20)
+    assert np.allclose(S, So, rtol=1e-10)
+    # same unique factors up to the sign of each eigenvector pair (Lanczos start identical, so signs match too)
+    for i in range(5):
+        sg = np.sign(np.vdot(Vo[:, i], V[:, i]))
+        assert np.allclose(V[:, i] * sg, Vo[:, i], atol=1e-8)
+        assert np.allclose(U[:, i] * sg, Uo[:, i], atol=1e-8)
+
+
+def test_svds_golden_values(pkg):
+    """the reference's own svds known answers (test/interface_simple.jl:56-63,100-105; interface_complex.jl:30-43)"""
+    import scipy.sparse as sp
+
+    A = _mytestmat(10, 8)
+    U, s, V = pkg.svds(A, 2, which="BE")
+    assert np.allclose(s, [0.20022491452411176, 2.424417285164735], rtol=1e-12)
+    _check_svd(A, U, s, V, tol=75)
+    U, s, V = pkg.svds(A.T.tocsr(), 2, which="BE")             # m <= n: the AA' side
+    assert np.allclose(s, [0.20022491452411176, 2.424417285164735], rtol=1e-12)
+    _check_svd(A.T.tocsr(), U, s, V, tol=75)
+    A1 = sp.csr_matrix(np.ones((5, 5)))
+    U, s, V = pkg.svds(A1, 1)
+    assert np.allclose(s, [5.0])
+    _check_svd(A1, U, s, V, tol=10)
+    Ac = _mytestmat(10, 8, -3.0j)
+    U, s, V = pkg.svds(Ac, 2, which="BE")
+    assert np.allclose(s, [0.9640220546797924, 6.0316491543925785], rtol=1e-12)
+    _check_svd(Ac, U, s, V, tol=60)
+    U, s, V = pkg.svds(Ac, 2, which="LM")
+    assert np.allclose(s, [6.0316491543925785, 1.9374903374733126], rtol=1e-12)
+    _check_svd(Ac, U, s, V, tol=60)
+    U, s, V = pkg.svds(A, 2, which="SA", ritzvec=False)
+    assert U.shape[1] == 0 and V.shape[1] == 0 and len(s) == 2
+
+
+def test_svds_arpack_example(pkg):
+    """ARPACK's dsvd example operator as a matrix (test/interface_simple.jl:160-222)"""
+    import scipy.sparse as sp
+
+    m, n = 500, 100
+    h, k = 1.0 / (m + 1), 1.0 / (n + 1)
+    A = np.zeros((m, n))
+    for j in range(n):
+        t = (j + 1) * k
+        sv = (np.arange(m) + 1) * h
+        A[: j + 1, j] = k * sv[: j + 1] * (t - 1)
+        A[j + 1:, j] = k * t * (sv[j + 1:] - 1)
+    U, s, V = pkg.svds(sp.csr_matrix(A), 4, ncv=10)
+    gold = sorted([4.1012320445852e-02, 6.0488061100249e-02, 1.1784357891005e-01, 5.5723400180223e-01], reverse=True)
+    assert np.allclose(s, gold, rtol=1e-10)
+    _check_svd(A, U, s, V, tol=4)
 
 
 def test_maxiter_exception(pkg, syn):

@@ -41,7 +41,7 @@ _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 # every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
-    "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
+    "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_bench_opx", "ga_debug_trace", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
@@ -102,6 +102,7 @@ def lib():
         L.ga_comm_ipc_import.argtypes = [vp, vp]
         L.ga_set_csr_dist.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
         L.ga_set_normal_csr.argtypes = [vp, i64, i64, vp, vp, vp]
+        L.ga_set_normal_csr_dist.argtypes = [vp, i64, vp, vp, vp, i32, vp, vp, vp, vp]
         L.ga_opx.argtypes = [vp, vp, vp]
         L.ga_upload_resid.argtypes = [vp, vp]
         L.ga_download_resid.argtypes = [vp, vp]
@@ -241,7 +242,12 @@ class Context:
         self.op = op
         self.dtype = op.dtype
         self.ncv = int(ncv)
-        self.n = int(op.size()) if world_size == 1 else int(len(op.rowptr) - 1)
+        if world_size == 1:
+            self.n = int(op.size())
+        elif op.normal:       # op holds this rank's rows of the tall orientation T; the plan knows the Lanczos block
+            self.n = int(plan["row_range"][1] - plan["row_range"][0])
+        else:
+            self.n = int(len(op.rowptr) - 1)
         self.n_global = int(n_global) if n_global is not None else self.n
         h = ctypes.c_void_p()
         rc = L.ga_create(ctypes.byref(h), self.dtype, self.n_global, self.n, int(row_offset), self.ncv, device, rank,
@@ -249,7 +255,15 @@ class Context:
         if rc != 0 or not h:
             raise RuntimeError("ga_create failed with code %d (is a CUDA device present? there is no CPU fallback)" % rc)
         self.h = h
-        if op.normal:
+        if op.normal and world_size > 1:
+            if plan is None:
+                raise ValueError("a multi-GPU context needs the halo plan (dist.halo_plan / dist.shard_normal)")
+            self.plan = plan
+            self.mt_local = int(len(op.rowptr) - 1)
+            self._ck(L.ga_set_normal_csr_dist(self.h, self.mt_local, _p(op.rowptr), _p(plan["col_local"]), _p(op.val),
+                                              int(plan["nhalo"]), _p(plan["recv_counts"]), _p(plan["send_counts"]),
+                                              _p(plan["send_idx"]), _p(plan["send_dest_off"])))
+        elif op.normal:
             m, n = op.shape
             self._ck(L.ga_set_normal_csr(self.h, m, n, _p(op.rowptr), _p(op.col), _p(op.val)))
         elif world_size > 1:
@@ -359,6 +373,23 @@ class Context:
         Zt = np.zeros((max(nconv, 1), self.n) + _eshape(self.dtype), dtype=_np_dtype(self.dtype)) if want_z else None
         self._ck(lib().ga_ritz_vectors(self.h, int(nconv), _p(Qf), Qh.shape[0], _p(Zt), self.n))
         return np.swapaxes(Zt[:nconv], 0, 1) if want_z else None
+
+    def svd_vectors(self, order):
+        """eigenvecs_to_singvecs! + orth! on the device (ga_svd_vectors): the other side's singular
+        vectors for the eigenvectors held in basis columns `order`.  Returns (rc, W, norms); W has
+        this rank's rows of the other side (all of them on one GPU)."""
+        nvec = len(order)
+        if getattr(self, "mt_local", None) is not None:
+            rows = self.mt_local
+        else:
+            m, n = self.op.shape
+            rows = m if self.op.At_side == "left" else n
+        Wt = np.zeros((nvec, rows) + _eshape(self.dtype), dtype=_np_dtype(self.dtype))
+        norms = np.zeros((nvec, 2))
+        perm = np.ascontiguousarray(order, dtype=np.int32)
+        rc = lib().ga_svd_vectors(self.h, nvec, _p(perm), _p(Wt), max(rows, 1), _p(norms))
+        nr = norms.reshape(-1)[:nvec].copy() if self.dtype != GA_DD else norms[:, 0].copy()
+        return rc, np.swapaxes(Wt, 0, 1), nr
 
     def norm2_resid(self):
         out = np.zeros(2)
@@ -577,12 +608,7 @@ def svds(A, k, *, which="LM", dtype=None, **kw):
         nvec = einfo.vectors.shape[1]
         order = order[:nvec]
         Z = einfo.vectors[:, order]
-        other = m if op.At_side == "left" else n
-        Wt = np.zeros((nvec, other) + _eshape(op.dtype), dtype=_np_dtype(op.dtype))
-        norms = np.zeros((nvec, 2))
-        perm = np.ascontiguousarray(order, dtype=np.int32)
-        rc = lib().ga_svd_vectors(ctx.h, nvec, _p(perm), _p(Wt), other, _p(norms))
-        nr = norms.reshape(-1)[:nvec] if op.dtype != GA_DD else norms[:, 0]
+        rc, W, nr = ctx.svd_vectors(order)
         eps = 4.930380657631324e-32 if op.dtype == GA_DD else np.finfo(np.float64).eps
         side = "U" if op.At_side == "left" else "V"
         if rc == GA_ERR_NUMERIC or (rc == 0 and np.any(nr <= eps / 2)):   # check_norm (src/idonow_ops.jl:300-306)
@@ -590,7 +616,6 @@ def svds(A, k, *, which="LM", dtype=None, **kw):
         ctx._ck(rc)
         if np.any(nr <= eps ** (2.0 / 3.0)):
             warnings.warn("%s subspace may be inaccurate due to small singular value (sigma ~ %g)" % (side, float(np.min(nr))))
-        W = np.swapaxes(Wt, 0, 1)
         U, V = (W, Z) if op.At_side == "left" else (Z, W)
         if op.dtype == GA_C64:
             Vt = np.conj(V).T

@@ -1,6 +1,7 @@
 // C ABI of the hot path (include/garpack_b200.h): context, operator upload, dgetv0!, dsaitr!,
 // the device tails of dsapps! and simple_dseupd!.  Host logic here is only what the reference
 // routine itself does around its vector operations (loop over steps, restart handling).
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -114,7 +115,7 @@ void ga_destroy(ga_ctx* c) {
   c->At.free_all();
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev); cudaFree(c->wbuf);
-  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace);
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace); cudaFree(c->zinv); cudaFree(c->zrecv);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -214,6 +215,92 @@ int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, co
   GA_CUDA(c, cudaMalloc(&c->xfull, (size_t)extra_pad * c->esize));
   GA_CUDA(c, cudaMemset(c->xfull, 0, (size_t)extra_pad * c->esize));
   c->xfull_len = extra_pad;
+  c->op_kind = 2;
+  return 0;
+}
+
+// Row-sharded normal operator (see the header): T_loc and its adjoint in the [own | halo] column space.
+int ga_set_normal_csr_dist(ga_ctx* c, int64_t mt_local, const int64_t* rowptr, const int32_t* col_local,
+                           const void* val, int32_t nhalo, const int32_t* recv_counts, const int32_t* send_counts,
+                           const int32_t* send_idx, const int32_t* send_dest_off) {
+  if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0 || mt_local < 0) return GA_ERR_ARG;
+  if (c->world < 2) return set_err(c, GA_ERR_ARG, "single-GPU contexts take ga_set_normal_csr");
+  GA_CUDA(c, cudaSetDevice(c->device));
+  c->op_kind = 0;
+  const i64 ncol = c->n_pad + nhalo;                       // local column space [own | halo]
+  int rc = csr_upload(c, c->A, mt_local, ncol, rowptr, col_local, val, 0);
+  if (rc) return rc;
+  // adjoint of T_loc: rows = local column space, columns = local rows of T
+  const i64 nnz = rowptr[mt_local] - rowptr[0];
+  {
+    std::vector<int64_t> tp((size_t)ncol + 1, 0);
+    const int64_t base = rowptr[0];
+    for (i64 k = 0; k < nnz; ++k) {
+      const int32_t cc = col_local[base + k];
+      if (cc < 0 || cc >= ncol) return set_err(c, GA_ERR_ARG, "normal operator: column outside [own | halo]");
+      tp[(size_t)cc + 1]++;
+    }
+    for (i64 j = 0; j < ncol; ++j) tp[(size_t)j + 1] += tp[(size_t)j];
+    std::vector<int32_t> tc((size_t)std::max<i64>(nnz, 1));
+    std::vector<char> tv((size_t)std::max<i64>(nnz, 1) * c->esize);
+    std::vector<int64_t> pos(tp.begin(), tp.end() - 1);
+    for (i64 i = 0; i < mt_local; ++i)
+      for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const i64 d = pos[(size_t)col_local[k]]++;
+        tc[(size_t)d] = (int32_t)i;
+        memcpy(&tv[(size_t)d * c->esize], (const char*)val + (size_t)k * c->esize, c->esize);
+        if (c->dtype == GA_C64) ((double*)&tv[(size_t)d * c->esize])[1] *= -1.0;
+      }
+    rc = csr_upload(c, c->At, ncol, mt_local, tp.data(), tc.data(), tv.data(), 0);
+    if (rc) return rc;
+  }
+  // halo plan (same bookkeeping as ga_set_csr_dist)
+  c->send_counts.assign(send_counts, send_counts + c->world);
+  c->recv_counts.assign(recv_counts, recv_counts + c->world);
+  if (send_dest_off) c->dest_off.assign(send_dest_off, send_dest_off + c->world);
+  else c->dest_off.assign(c->world, 0);
+  int nsend = 0, nrecv = 0;
+  for (int q = 0; q < c->world; ++q) { nsend += send_counts[q]; nrecv += recv_counts[q]; }
+  if (nrecv != nhalo || (nsend > 0 && !send_idx)) return set_err(c, GA_ERR_ARG, "halo plan is inconsistent");
+  c->nhalo = nhalo; c->nsend = nsend;
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->zinv); cudaFree(c->zrecv); cudaFree(c->xfull);
+  c->send_idx = nullptr; c->send_buf = nullptr; c->halo = nullptr; c->zinv = nullptr; c->zrecv = nullptr; c->xfull = nullptr;
+  // One peer-readable allocation with offsets that are the same on every rank:
+  //   [halo: cap | z0: n_pad + cap | z1: n_pad + cap],  cap = (world - 1) * n_pad >= any rank's halo
+  const i64 cap = (i64)(c->world - 1) * c->n_pad;
+  if (nhalo > cap) return set_err(c, GA_ERR_ARG, "halo larger than the rest of the vector");
+  const size_t total = (size_t)(cap + 2 * (c->n_pad + cap)) * c->esize;
+  GA_CUDA(c, cudaMalloc(&c->halo, total));
+  GA_CUDA(c, cudaMemset(c->halo, 0, total));
+  c->zp[0] = (char*)c->halo + (size_t)cap * c->esize;
+  c->zp[1] = (char*)c->zp[0] + (size_t)(c->n_pad + cap) * c->esize;
+  GA_CUDA(c, cudaMalloc(&c->send_idx, sizeof(int) * (size_t)std::max(nsend, 1)));
+  GA_CUDA(c, cudaMalloc(&c->send_buf, c->esize * (size_t)std::max(nsend, 1)));
+  GA_CUDA(c, cudaMalloc(&c->zrecv, c->esize * (size_t)std::max(nsend, 1)));
+  if (nsend > 0) GA_CUDA(c, cudaMemcpy(c->send_idx, send_idx, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+  // inverse of the send lists: own row i sits at position zinv[q][i] of the segment rank q holds for me
+  {
+    std::vector<int> inv((size_t)c->world * c->n_pad, -1);
+    size_t off = 0;
+    for (int q = 0; q < c->world; ++q) {
+      for (int k = 0; k < send_counts[q]; ++k) {
+        const int row = send_idx[off + k];
+        if (row < 0 || row >= c->n) return set_err(c, GA_ERR_ARG, "send_idx outside the local rows");
+        inv[(size_t)q * c->n_pad + row] = k;
+      }
+      off += (size_t)send_counts[q];
+    }
+    GA_CUDA(c, cudaMalloc(&c->zinv, sizeof(int) * inv.size()));
+    GA_CUDA(c, cudaMemcpy(c->zinv, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice));
+  }
+  c->mt_local = mt_local;
+  c->mt_pad = (std::max<i64>(mt_local, 1) + kRowPad - 1) / kRowPad * kRowPad;
+  GA_CUDA(c, cudaMalloc(&c->xfull, (size_t)c->mt_pad * c->esize));
+  GA_CUDA(c, cudaMemset(c->xfull, 0, (size_t)c->mt_pad * c->esize));
+  c->xfull_len = c->mt_pad;
+  c->normal_dist = true; c->normal_left = true;
+  c->normal_m = mt_local; c->normal_n = c->n;   // local view: T_loc is mt_local x (own | halo)
+  c->zpar = 0;
   c->op_kind = 2;
   return 0;
 }

@@ -137,6 +137,11 @@ int comm_ipc_import(ga_ctx* c, const void* all_handles) {
     hc.recv_counts[q] = c->recv_counts.empty() ? 0 : c->recv_counts[q];
   }
   hc.send_off[c->world] = off;
+  if (c->normal_dist) {
+    hc.zp_off[0] = (long long)((const char*)c->zp[0] - (const char*)c->halo);
+    hc.zp_off[1] = (long long)((const char*)c->zp[1] - (const char*)c->halo);
+    hc.zp_halo_elem = c->n_pad;
+  }
   if (!c->devcomm) GA_CUDA(c, cudaMalloc(&c->devcomm, sizeof(DevComm)));
   GA_CUDA(c, cudaMemcpy(c->devcomm, &hc, sizeof(DevComm), cudaMemcpyHostToDevice));
   return 0;
@@ -192,6 +197,30 @@ int comm_halo_exchange(ga_ctx* c, const void* x_local) {
                         (ncclComm_t)c->nccl_comm, c->stream));
     if (c->recv_counts[q] > 0)
       GA_NCCL(c, a.Recv((char*)c->halo + roff * c->esize, (size_t)c->recv_counts[q] * per, ncclFloat64, q,
+                        (ncclComm_t)c->nccl_comm, c->stream));
+    soff += (size_t)c->send_counts[q];
+    roff += (size_t)c->recv_counts[q];
+  }
+  GA_NCCL(c, a.GroupEnd());
+  return 0;
+}
+
+// NCCL path of the sharded normal operator's reduce-scatter: the segment of my partial result that
+// belongs to rank q (my halo columns owned by q) goes to q; q's segment for me lands in zrecv laid
+// out like send_buf (grouped by source rank, send_counts[q] entries each).
+int comm_zp_exchange(ga_ctx* c, const void* zp) {
+  if (c->world <= 1) return 0;
+  if (int rc = comm_ensure(c)) return rc;
+  NcclApi& a = nccl();
+  const size_t per = c->esize / 8;
+  GA_NCCL(c, a.GroupStart());
+  size_t soff = 0, roff = 0;
+  for (int q = 0; q < c->world; ++q) {
+    if (c->recv_counts[q] > 0)
+      GA_NCCL(c, a.Send((const char*)zp + ((size_t)c->n_pad + roff) * c->esize, (size_t)c->recv_counts[q] * per, ncclFloat64, q,
+                        (ncclComm_t)c->nccl_comm, c->stream));
+    if (c->send_counts[q] > 0)
+      GA_NCCL(c, a.Recv((char*)c->zrecv + soff * c->esize, (size_t)c->send_counts[q] * per, ncclFloat64, q,
                         (ncclComm_t)c->nccl_comm, c->stream));
     soff += (size_t)c->send_counts[q];
     roff += (size_t)c->recv_counts[q];

@@ -44,6 +44,7 @@ struct DevCtl {
   unsigned int gbar_count, gbar_gen;  // grid barrier of the persistent step kernel
   unsigned int seq;              // sequence number of the fused cross-GPU slot exchange
   unsigned int hseq;             // sequence number of the fused halo push
+  unsigned int zseq;             // sequence number of the sharded normal operator's partial-result exchange
   unsigned int prof_runs;        // executed (not phase-gated) Gram-Schmidt sweep launches
   unsigned long long prof_units; // n-vector passes those launches moved: (j+1) reads + 1 write when updating
   double rnorm[2], wnorm[2], rnorm0[2], rnorm1[2];
@@ -59,6 +60,7 @@ struct Mailbox {
   double2 slots[2][kMaxWorld][kMaxSlots];   // [parity][source rank][slot]
   unsigned int flags[2][kMaxWorld];         // [parity][source rank] = seq when the slots are complete
   unsigned int hflags[kMaxWorld];           // [source rank] = hseq when that peer's halo entries landed
+  unsigned int zflags[kMaxWorld];           // [source rank] = zseq when that peer's partial A^H(A x) is complete
   // low-latency slot exchange: every 16-byte slot travels as four 8-byte words {32 data bits, seq};
   // an aligned 8-byte store is a single NVLink transaction, so data and flag arrive together and the
   // receiver needs neither a system-scope fence nor a second round trip for a separate flag
@@ -71,6 +73,10 @@ struct DevComm {
   int send_off[kMaxWorld + 1];              // my send list, grouped by destination rank
   int dest_off[kMaxWorld];                  // where my entries start in peer q's halo buffer
   int recv_counts[kMaxWorld];
+  // sharded normal operator: byte offsets of the two partial-result buffers inside every rank's
+  // exported halo allocation (identical on all ranks), and the element offset of the halo part
+  long long zp_off[2];
+  long long zp_halo_elem;                   // = n_pad: partial results are laid out [own rows | halo columns]
 };
 
 struct CsrDev {
@@ -139,6 +145,13 @@ struct ga_ctx {
   void* send_buf = nullptr;      // device, nsend elements of T
   void* halo = nullptr;          // device, nhalo elements of T (x entries owned by peers)
   std::vector<int> dest_off;     // where my entries start in each peer's halo
+  // sharded normal operator OP = T^H T (rows of the tall T partitioned, see ga_set_normal_csr_dist)
+  bool normal_dist = false;
+  ga::i64 mt_local = 0, mt_pad = 0;
+  void* zp[2] = {nullptr, nullptr};   // partial results T_loc^H (T_loc x), inside the halo allocation (peer-readable)
+  int* zinv = nullptr;                // [world][n_pad]: position of own row i in peer q's halo segment, or -1
+  void* zrecv = nullptr;              // NCCL path: the peers' contributions, laid out like send_buf
+  unsigned int zpar = 0;              // parity of the partial-result buffer used by the next OP*x
   // fused peer-memory collectives (cudaIpc): own mailbox, device-side descriptor, mapped peers
   ga::Mailbox* mbox = nullptr;
   ga::DevComm* devcomm = nullptr;   // device copy; nullptr -> NCCL fallback (or single GPU)

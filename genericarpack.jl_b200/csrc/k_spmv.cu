@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) k_spmv_long(const int* __restrict__ longr
 template <class T>
 static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
   typedef SpmvStreamCfg<T> C;
-  const bool split = c->world > 1 && &M == &c->A && c->op_kind == 1;
+  const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
   const int nsplit = split ? (int)c->n_pad : 2147483647;
   const DevComm* cm = (split && wait_halo) ? c->devcomm : nullptr;
   static bool attr_set = false;
@@ -279,7 +279,7 @@ static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void*
 template <class T>
 static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
   if (M.nblk <= 0) return;
-  const bool split = c->world > 1 && &M == &c->A && c->op_kind == 1;
+  const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
   k_spmv<T><<<M.nblk, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
                                                           (const T*)c->halo, split ? (int)c->n_pad : 2147483647,
                                                           (T*)y, c->ctl, gated ? 1 : 0,
@@ -303,6 +303,97 @@ static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sharded normal operator OP = T^H T: after z = T_loc^H (T_loc x) every rank owns a full-length
+// partial result in its [own | halo] layout; the halo segment "owned by rank q" is rank q's share.
+// k_zsignal publishes "my partial result is complete" to the peers (fused path); k_reduce_scatter
+// adds, in rank order, the peers' segments to the own part.  src[q] points at the segment rank q
+// holds for this rank: in q's memory over NVLink (fused) or in the receive buffer (NCCL path).
+__global__ void k_zsignal(DevCtl* ctl, const DevComm* cm, int gated) {
+  if (gated && ctl->status != ST_OK) return;
+  __threadfence_system();
+  const unsigned int zs = ctl->zseq + 1u;
+  __syncthreads();
+  if ((int)threadIdx.x < cm->world && (int)threadIdx.x != cm->rank) st_sys_u32(&cm->peer[threadIdx.x]->zflags[cm->rank], zs);
+  if (threadIdx.x == 0) ctl->zseq = zs;
+}
+
+struct ZSrc { const void* p[kMaxWorld]; };
+
+template <class T>
+__global__ void __launch_bounds__(256) k_reduce_scatter(T* __restrict__ out, const T* __restrict__ own, ZSrc src,
+                                                        const int* __restrict__ inv, i64 n, i64 n_pad, int world,
+                                                        int rank, DevCtl* ctl, int gated, const DevComm* cm) {
+  if (gated && ctl->status != ST_OK) return;
+  if (cm) {  // wait until every peer's partial result is complete (flags written after a system-scope fence)
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+      if (!spin_until(&cm->peer[rank]->zflags[threadIdx.x], ctl->zseq)) ctl->status = ST_COMM;
+    }
+    __syncthreads();
+  }
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    T acc = own[i];
+    for (int q = 0; q < world; ++q) {
+      if (q == rank) continue;
+      const int p = inv[(size_t)q * n_pad + i];
+      if (p >= 0) {
+        const T* sq = reinterpret_cast<const T*>(src.p[q]);
+        T v;
+        if (sizeof(T) == 8) {
+          double d;
+          asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(d) : "l"(sq + p));
+          *reinterpret_cast<double*>(&v) = d;
+        } else {
+          double2 d = ld_sys_d2(reinterpret_cast<const double2*>(sq + p));
+          *reinterpret_cast<double2*>(&v) = d;
+        }
+        Elem<T>::add(acc, v);
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+int comm_zp_exchange(ga_ctx* c, const void* zp);  // ga_comm.cu (NCCL path)
+
+static int launch_normal_dist(ga_ctx* c, const void* x, void* y, bool gated, bool fused) {
+  // (1) the halo of x is in place (pushed by the normalisation kernel, or exchanged by the caller)
+  int rc = spmv_launch(c, c->A, x, c->xfull, gated, fused);               // (2) y_loc = T_loc [x_own | halo]
+  if (rc) return rc;
+  void* zp = c->zp[c->zpar & 1u];
+  rc = spmv_launch(c, c->At, c->xfull, zp, gated);                        // (3) z = T_loc^H y_loc
+  if (rc) return rc;
+  const bool peer = c->devcomm != nullptr;                                // (4) reduce-scatter
+  ZSrc src;
+  const size_t zoff = (size_t)((const char*)zp - (const char*)c->halo);
+  size_t soff = 0;
+  for (int q = 0; q < c->world; ++q) {
+    if (peer) src.p[q] = (const char*)c->hostcomm.peer_halo[q] + zoff + ((size_t)c->n_pad + (size_t)c->dest_off[q]) * c->esize;
+    else src.p[q] = (const char*)c->zrecv + soff * c->esize;
+    soff += (size_t)c->send_counts[q];
+  }
+  if (peer) {
+    k_zsignal<<<1, 32, 0, c->stream>>>(c->ctl, c->devcomm, gated ? 1 : 0);
+    GA_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+  } else if ((rc = comm_zp_exchange(c, zp))) return rc;
+  const int threads = 256;
+  i64 blocks = (c->n + threads - 1) / threads;
+  if (blocks > (i64)c->sm_count * 8) blocks = (i64)c->sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  const DevComm* cm = peer ? c->devcomm : nullptr;
+  switch (c->dtype) {
+    case GA_F64: k_reduce_scatter<double><<<(int)blocks, threads, 0, c->stream>>>((double*)y, (const double*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
+    case GA_C64: k_reduce_scatter<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)y, (const cdbl*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
+    default: k_reduce_scatter<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)y, (const ddbl*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
+  }
+  GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  c->zpar ^= 1u;
+  return 0;
+}
+
 int comm_halo_exchange(ga_ctx* c, const void* x_local);  // ga_comm.cu
 
 // y = OP x for device vectors of the (local) problem size.
@@ -317,6 +408,7 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
     if (rc) return rc;
   }
   if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated, fused);
+  if (c->normal_dist) return launch_normal_dist(c, xin, y, gated, fused);
   // normal operator (single GPU): left: y = A^H (A x); right: y = A (A^H x)
   if (c->normal_left) {
     int rc = spmv_launch(c, c->A, xin, c->xfull, gated);
@@ -334,6 +426,10 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
 // (src/idonow_ops.jl:311,322).
 int launch_normal_half(ga_ctx* c, const void* x, void* y) {
   if (c->op_kind != 2) return set_err(c, GA_ERR_NOOP, "not a normal-operator context (ga_set_normal_csr)");
+  if (c->normal_dist) {  // y_loc = T_loc [x_own | halo]: the halo of x travels first (grouped ncclSend/ncclRecv)
+    int rc = comm_halo_exchange(c, x);
+    if (rc) return rc;
+  }
   return spmv_launch(c, c->normal_left ? c->A : c->At, x, y, false);
 }
 

@@ -72,6 +72,27 @@ def halo_plan(col, n, rank, world, all_gather_object=None):
             "row_range": (r0, r1)}
 
 
+def shard_normal(A, rank, world, all_gather_object=None):
+    """Row sharding of ArpackNormalOp(A) (svds): T = A for m > n (At_side = :left), T = A^H otherwise;
+    rank r owns a uniform block of T's rows and the usual block of the length-min(m, n) Lanczos vectors.
+    A: scipy sparse matrix (every rank may pass the full matrix, or just its rows via `rows_of_T`).
+    Returns (csr_rows, plan, n, (t0, t1)): csr_rows = (rowptr int64, col int32 global, val, (mt_local, n))."""
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix(A)
+    m, n0 = A.shape
+    T = A if m > n0 else A.conj().T.tocsr()
+    T.sort_indices()
+    mt, n = T.shape
+    tblk, tparts = block_partition(mt, world)
+    t0, t1 = tparts[rank]
+    Tl = T[t0:t1]
+    rowptr = np.ascontiguousarray(Tl.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(Tl.indices, dtype=np.int32)
+    plan = halo_plan(col, n, rank, world, all_gather_object)
+    return (rowptr, col, Tl.data, (t1 - t0, n)), plan, n, (t0, t1)
+
+
 def setup_comm(ctx, comm_unique_id, rank, world, fused=True):
     """Rendezvous for one context (torch.distributed must be initialised): broadcast the NCCL unique
     id, then (fused=True) all-gather the cudaIpc handles so that the per-step collectives run inside
@@ -105,3 +126,42 @@ def emulate_sharded_spmv(csr_rows, plan, x_blocks, rank):
     prod = val * xext[plan["col_local"]]
     np.add.at(y, np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr)), prod)
     return y
+
+
+def emulate_sharded_normal(csr_rows, plan, gathered, rank):
+    """numpy emulation of one OP*x = T^H (T x) of the row-sharded normal operator on one rank, step by
+    step as the library performs it (used by the CPU tests).  `gathered[q]` = dict(x=x block of rank q,
+    sendbuf={peer: entries}, zhalo=None) from every rank; returns (y_loc, z) where z is this rank's
+    partial result in the [own | halo] layout.  Call twice: first to get z of every rank, then
+    reduce_scatter_emulated to finish."""
+    rowptr, _, val, _ = csr_rows
+    world = len(gathered)
+    halo = [gathered[q]["sendbuf"][rank] for q in range(world) if plan["recv_counts"][q]]
+    halo = np.concatenate(halo) if halo else np.zeros(0, dtype=val.dtype)
+    xl = gathered[rank]["x"]
+    n_pad = plan["n_pad"]
+    xext = np.concatenate([xl, np.zeros(n_pad - len(xl), dtype=xl.dtype), halo])
+    nrows = len(rowptr) - 1
+    rows = np.repeat(np.arange(nrows), np.diff(rowptr))
+    y = np.zeros(nrows, dtype=np.result_type(val.dtype, xl.dtype))
+    np.add.at(y, rows, val * xext[plan["col_local"]])                       # y_loc = T_loc [x_own | halo]
+    z = np.zeros(n_pad + plan["nhalo"], dtype=y.dtype)
+    np.add.at(z, plan["col_local"], np.conj(val) * y[rows])                 # z = T_loc^H y_loc
+    return y, z
+
+
+def reduce_scatter_emulated(plan, zs, rank, plans):
+    """rank-ordered sum of the peers' halo segments that belong to this rank's rows (what
+    k_reduce_scatter does): zs[q] = rank q's partial result, plans[q] = its plan."""
+    world = len(zs)
+    r0, r1 = plan["row_range"]
+    n_pad = plan["n_pad"]
+    out = zs[rank][: r1 - r0].copy()
+    off = np.concatenate([[0], np.cumsum(plan["send_counts"])])
+    for q in range(world):
+        if q == rank or plan["send_counts"][q] == 0:
+            continue
+        rows = plan["send_idx"][off[q]:off[q + 1]]                          # my rows that rank q references
+        seg0 = n_pad + int(plan["send_dest_off"][q])                        # where they start in q's halo part
+        out[rows] += zs[q][seg0: seg0 + len(rows)]
+    return out

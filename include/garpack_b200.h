@@ -95,6 +95,20 @@ int ga_set_csr_dist(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col_local
                     start in peer q's halo; may be NULL when the fused path is not used */);
 int ga_set_normal_csr(ga_ctx* ctx, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
                       const void* val);
+/* Row-sharded ArpackNormalOp (world_size > 1): OP = T^H T, T = the tall orientation of A (T = A for
+ * m > n, At_side = :left; T = A^H otherwise).  The Lanczos vectors (length min(m, n)) are block-
+ * partitioned as usual; this rank additionally owns mt_local consecutive rows of T.  The columns of
+ * those rows are remapped exactly as for ga_set_csr_dist ([own block | halo]; for a matrix with
+ * scattered columns the halo is nearly all of x, i.e. an all-gather) and the halo-plan arguments mean
+ * the same.  Per OP*x: (1) the halo of x moves (pushed by the normalisation kernel over NVLink peer
+ * memory, or one grouped ncclSend/ncclRecv round); (2) y_loc = T_loc [x_own | halo]; (3) the partial
+ * result z = T_loc^H y_loc is formed in the same [own | halo] layout; (4) reduce-scatter: every rank
+ * adds, in rank order, the halo segments of its peers' z that belong to its rows -- read straight out
+ * of the peers' memory (fused path) or exchanged with ncclSend/ncclRecv -- to its own part.
+ * Fixed order = bit-reproducible, and correct for Double64 (a NCCL sum over hi/lo words is not). */
+int ga_set_normal_csr_dist(ga_ctx* ctx, int64_t mt_local, const int64_t* rowptr, const int32_t* col_local,
+                           const void* val, int32_t nhalo, const int32_t* recv_counts,
+                           const int32_t* send_counts, const int32_t* send_idx, const int32_t* send_dest_off);
 /* y = OP*x on host vectors of the problem size (test / svds post-processing helper). */
 int ga_opx(ga_ctx* ctx, const void* x_host, void* y_host);
 

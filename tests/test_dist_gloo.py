@@ -80,6 +80,64 @@ def test_halo_plan_gloo(world, kind):
     assert q.get(timeout=5) is True
 
 
+def _worker_normal(rank, world, port, wide, q):
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    entry.load_package()
+    syn = importlib.import_module(entry.PKG_NAME + ".synthetic")
+    gd = importlib.import_module(entry.PKG_NAME + ".dist")
+    A = syn.to_scipy(syn.tall_sparse(2300, 170, 6))
+    if wide:
+        A = A.T.tocsr()                      # m <= n: OP = A A^H, T = A^H
+    rows, plan, n, (t0, t1) = gd.shard_normal(A, rank, world)
+    assert n == 170 and rows[3] == (t1 - t0, 170)
+    x = np.sin(np.arange(n) * 0.11) + 0.3
+    r0, r1 = plan["row_range"]
+    xl = x[r0:r1]
+    off = np.concatenate([[0], np.cumsum(plan["send_counts"])])
+    sendbuf = {p: xl[plan["send_idx"][off[p]:off[p + 1]]] for p in range(world)}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {"x": xl, "sendbuf": sendbuf})
+    _, z = gd.emulate_sharded_normal(rows, plan, gathered, rank)
+    zs = [None] * world
+    dist.all_gather_object(zs, z)
+    plans = [None] * world
+    dist.all_gather_object(plans, {k: plan[k] for k in ("send_counts", "send_idx", "send_dest_off", "n_pad", "row_range")})
+    y = gd.reduce_scatter_emulated(plan, zs, rank, plans)
+    ref = (A @ (A.T @ x)) if wide else (A.T @ (A @ x))
+    ok = np.allclose(y, ref[r0:r1], rtol=1e-12, atol=1e-12)
+    res = [None] * world
+    dist.all_gather_object(res, bool(ok))
+    if rank == 0:
+        q.put(all(res))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,wide", [(2, False), (3, False), (2, True)])
+def test_sharded_normal_operator_gloo(world, wide):
+    """plan + data flow of ga_set_normal_csr_dist: halo of x, T_loc, T_loc^H, rank-ordered reduce-scatter"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world * 5 + (1 if wide else 0)
+    procs = [ctx.Process(target=_worker_normal, args=(r, world, port, wide, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=5) is True
+
+
 def test_block_partition():
     sys.path.insert(0, ROOT)
     import importlib

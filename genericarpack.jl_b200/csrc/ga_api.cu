@@ -689,6 +689,14 @@ int ga_bench_opx(ga_ctx* c, int reps, double* ms) {
   return 0;
 }
 
+int ga_profile_gs_times(ga_ctx* c, float* ms_out, int64_t n) {
+  if (!c || !ms_out || n < 0) return GA_ERR_ARG;
+  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < n && 2 * (size_t)i + 1 < c->prof_used; ++i)
+    GA_CUDA(c, cudaEventElapsedTime(&ms_out[i], c->prof_ev[2 * (size_t)i], c->prof_ev[2 * (size_t)i + 1]));
+  return 0;
+}
+
 int ga_profile_gs_launches(ga_ctx* c, int64_t* n) {
   if (!c || !n) return GA_ERR_ARG;
   *n = (int64_t)(c->prof_used / 2);

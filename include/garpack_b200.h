@@ -186,6 +186,8 @@ int ga_profile_read(ga_ctx* ctx, double* gs_ms, int64_t* gs_runs, int64_t* gs_un
 /* number of Gram-Schmidt kernel launches bracketed since ga_profile(ctx, 1) (the persistent step kernel
  * runs all sweeps of a Lanczos step in one launch, so this is <= gs_runs). */
 int ga_profile_gs_launches(ga_ctx* ctx, int64_t* n);
+/* per-launch milliseconds of the first min(n, launches) bracketed Gram-Schmidt launches (tuning aid) */
+int ga_profile_gs_times(ga_ctx* ctx, float* ms_out, int64_t n);
 
 /* ---- whole solve: symeigs (src/interface.jl:215-290) = dsaupd! + simple_dseupd! -----------------
  * Host control (dsaup2 loop, dsgets, dsconv, dseigt/dstqrb, dsapps bulge chase, dseupd's small

@@ -143,7 +143,7 @@ int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void*
   int rc = csr_upload(c, c->A, c->n, c->n_global, rowptr, col, val, 0);
   if (rc) return rc;
   c->op_kind = 1;
-  return 0;
+  return spmv_autotune(c, c->A, c->V, c->resid);
 }
 
 // Row-sharded operator: this rank's rows with columns already remapped by the caller:
@@ -174,8 +174,9 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
   GA_CUDA(c, cudaMalloc(&c->send_buf, c->esize * (size_t)(nsend > 0 ? nsend : 1)));
   GA_CUDA(c, cudaMalloc(&c->halo, c->esize * (size_t)(nhalo > 0 ? nhalo : 1)));
   if (nsend > 0) GA_CUDA(c, cudaMemcpy(c->send_idx, send_idx, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+  GA_CUDA(c, cudaMemset(c->halo, 0, c->esize * (size_t)(nhalo > 0 ? nhalo : 1)));
   c->op_kind = 1;
-  return 0;
+  return spmv_autotune(c, c->A, c->V, c->resid);
 }
 
 int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col, const void* val) {
@@ -216,7 +217,10 @@ int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, co
   GA_CUDA(c, cudaMemset(c->xfull, 0, (size_t)extra_pad * c->esize));
   c->xfull_len = extra_pad;
   c->op_kind = 2;
-  return 0;
+  // A: m x n (x has n entries, y has m); At: n x m.  V's first column / resid / xfull serve as operands.
+  const bool a_first = left;   // left: x (problem size n) -> A -> xfull (m) -> At -> resid
+  if ((rc = spmv_autotune(c, c->A, a_first ? c->V : c->xfull, a_first ? c->xfull : c->resid))) return rc;
+  return spmv_autotune(c, c->At, a_first ? c->xfull : c->V, a_first ? c->resid : c->xfull);
 }
 
 // Row-sharded normal operator (see the header): T_loc and its adjoint in the [own | halo] column space.
@@ -302,7 +306,8 @@ int ga_set_normal_csr_dist(ga_ctx* c, int64_t mt_local, const int64_t* rowptr, c
   c->normal_m = mt_local; c->normal_n = c->n;   // local view: T_loc is mt_local x (own | halo)
   c->zpar = 0;
   c->op_kind = 2;
-  return 0;
+  if ((rc = spmv_autotune(c, c->A, c->V, c->xfull))) return rc;
+  return spmv_autotune(c, c->At, c->xfull, c->zp[0]);
 }
 
 int ga_opx(ga_ctx* c, const void* x_host, void* y_host) {

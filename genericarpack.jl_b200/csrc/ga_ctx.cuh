@@ -92,6 +92,7 @@ struct CsrDev {
   int ndesc = 0;
   int* longrow = nullptr;   // nlong row indices
   int nlong = 0;
+  int tune_groups = 4, tune_stages = 6;  // consumer groups / pipeline stages picked by the upload-time autotune
   void free_all() {
     cudaFree(rowptr); cudaFree(col); cudaFree(val); cudaFree(rowblk); cudaFree(desc); cudaFree(longrow);
     rowptr = col = rowblk = longrow = nullptr; val = nullptr; desc = nullptr; nblk = 0; nnz = 0; ndesc = 0; nlong = 0;
@@ -197,6 +198,7 @@ int launch_norm_resid(ga_ctx* c, int decide_kind);         // ||resid|| -> ctl
 int launch_zero_resid(ga_ctx* c);
 // k_spmv.cu
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated);  // y = OP x (device vectors)
+int spmv_autotune(ga_ctx* c, CsrDev& M, const void* x, void* y);  // time the streamed SpMV's configurations once
 int launch_normal_half(ga_ctx* c, const void* x, void* y);       // y = A x or A^H x (svds post-processing)
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift);

@@ -93,10 +93,10 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
 
 // ---------------------------------------------------------------------------------------------
 // Streamed SpMV: persistent CTAs, TMA-staged row blocks.
-template <class T> struct SpmvStreamCfg {
+template <class T, int GROUPS_ = 4> struct SpmvStreamCfg {
   static constexpr int CAP = (sizeof(T) == 8) ? 2048 : 1024;  // non-zeros per row block (one pipeline stage)
   static constexpr int MAXROWS = 512;    // rows per row block
-  static constexpr int GROUPS = 4, GT = 128;
+  static constexpr int GROUPS = GROUPS_, GT = 128;
   static constexpr int THREADS = GROUPS * GT + 32;      // consumer groups + producer warp
   static constexpr int COL_BYTES = (CAP + 8) * 4;       // +8: 16-byte alignment slack of the segment
   static constexpr int VAL_BYTES = (CAP + 8) * (int)sizeof(T);
@@ -113,12 +113,12 @@ template <class T> struct SpmvStreamCfg {
   static constexpr int smem_bytes(int nst) { return nst * STAGE_BYTES + 2 * MAX_STAGES * 8 + 16; }
 };
 
-template <class T>
-__global__ void __launch_bounds__(SpmvStreamCfg<T>::THREADS, 1)
+template <class T, int NG>
+__global__ void __launch_bounds__(SpmvStreamCfg<T, NG>::THREADS, 1)
 k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ rowptr, const int* __restrict__ col,
               const T* __restrict__ val, const T* __restrict__ x, const T* __restrict__ xh, int nsplit,
               T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm, int NST) {
-  typedef SpmvStreamCfg<T> C;
+  typedef SpmvStreamCfg<T, NG> C;
   constexpr int GT = C::GT, GROUPS = C::GROUPS;
   if (gated && ctl->status != ST_OK) return;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -241,31 +241,51 @@ __global__ void __launch_bounds__(256) k_spmv_long(const int* __restrict__ longr
   if (tid == 0) y[r] = red[0];
 }
 
+// tuning overrides (GA_SPMV_STAGES, GA_SPMV_GROUPS); 0 = use the per-matrix autotuned values
+static int g_spmv_force_stages = -1, g_spmv_force_groups = -1;
+static void spmv_read_env() {
+  if (g_spmv_force_stages >= 0) return;
+  g_spmv_force_stages = 0; g_spmv_force_groups = 0;
+  if (const char* e = getenv("GA_SPMV_STAGES")) { const int v = atoi(e); if (v >= 4 && v <= 8) g_spmv_force_stages = v; }
+  if (const char* e = getenv("GA_SPMV_GROUPS")) { const int v = atoi(e); if (v == 4 || v == 6) g_spmv_force_groups = v; }
+}
+
+template <class T, int NG>
+static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, int nsplit,
+                                const DevComm* cm, int nst) {
+  typedef SpmvStreamCfg<T, NG> C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GA_CUDA(c, cudaFuncSetAttribute(k_spmv_stream<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::smem_bytes(C::MAX_STAGES)));
+    attr_set = true;
+  }
+  if (nst < NG) nst = NG;
+  const int grid = M.ndesc < c->sm_count ? M.ndesc : c->sm_count;
+  k_spmv_stream<T, NG><<<grid, C::THREADS, C::smem_bytes(nst), c->stream>>>(M.desc, M.ndesc, M.rowptr, M.col,
+                                                                           (const T*)M.val, (const T*)x,
+                                                                           (const T*)c->halo, nsplit, (T*)y, c->ctl,
+                                                                           gated ? 1 : 0, cm, nst);
+  GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
 template <class T>
 static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
   typedef SpmvStreamCfg<T> C;
   const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
   const int nsplit = split ? (int)c->n_pad : 2147483647;
   const DevComm* cm = (split && wait_halo) ? c->devcomm : nullptr;
-  static bool attr_set = false;
-  static int nst = C::STAGES;
-  if (!attr_set) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_spmv_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::smem_bytes(C::MAX_STAGES)));
-    if (const char* e = getenv("GA_SPMV_STAGES")) {  // tuning knob
-      const int v = atoi(e);
-      if (v >= C::GROUPS && v <= C::MAX_STAGES) nst = v;
-    }
-    attr_set = true;
-  }
+  spmv_read_env();
+  int nst = M.tune_stages, ngroups = M.tune_groups;
+  if (g_spmv_force_stages > 0) nst = g_spmv_force_stages;
+  if (g_spmv_force_groups > 0) ngroups = g_spmv_force_groups;
+  if (nst > C::MAX_STAGES) nst = C::MAX_STAGES;
   if (M.ndesc > 0) {
-    const int grid = M.ndesc < c->sm_count ? M.ndesc : c->sm_count;
-    k_spmv_stream<T><<<grid, C::THREADS, C::smem_bytes(nst), c->stream>>>(M.desc, M.ndesc, M.rowptr, M.col,
-                                                                         (const T*)M.val, (const T*)x,
-                                                                         (const T*)c->halo, nsplit, (T*)y, c->ctl,
-                                                                         gated ? 1 : 0, cm, nst);
-    GA_CUDA(c, cudaGetLastError());
-    c->launches += 1;
+    int rc = ngroups == 6 ? spmv_stream_launch_g<T, 6>(c, M, x, y, gated, nsplit, cm, nst)
+                          : spmv_stream_launch_g<T, 4>(c, M, x, y, gated, nsplit, cm, nst);
+    if (rc) return rc;
   }
   if (M.nlong > 0) {
     k_spmv_long<T><<<M.nlong, 256, 0, c->stream>>>(M.longrow, M.rowptr, M.col, (const T*)M.val, (const T*)x,
@@ -419,6 +439,39 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
     if (rc) return rc;
     return spmv_launch(c, c->A, c->xfull, y, gated);
   }
+}
+
+// Upload-time autotune of the streamed SpMV: the best (consumer groups, pipeline stages) pair depends
+// on the matrix -- stencils want the deepest pipeline (6 groups, 8 stages: 5.99 TB/s on the n = 16M
+// Laplacian vs 5.16 with 4 x 6), matrices with scattered columns want fewer stages so that more of
+// the SM's unified memory stays L1 for the x gathers (profiles/r01/spmv_stage_sweep.jsonl).  Every
+// configuration computes the same bits, so the choice affects speed only.
+int spmv_autotune(ga_ctx* c, CsrDev& M, const void* x, void* y) {
+  spmv_read_env();
+  if (!c->use_spmv_stream || M.ndesc < 4 * c->sm_count) return 0;   // tiny matrices: launch-bound either way
+  static const int cand[][2] = {{4, 6}, {4, 5}, {6, 8}, {4, 8}, {6, 6}};
+  cudaEvent_t e0, e1;
+  GA_CUDA(c, cudaEventCreate(&e0));
+  GA_CUDA(c, cudaEventCreate(&e1));
+  float best = 1e30f;
+  int bg = M.tune_groups, bs = M.tune_stages;
+  for (const auto& cd : cand) {
+    M.tune_groups = cd[0]; M.tune_stages = cd[1];
+    int rc = spmv_launch(c, M, x, y, false);           // warm-up (also sets the kernel attributes)
+    if (rc) return rc;
+    GA_CUDA(c, cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < 3 && rc == 0; ++r) rc = spmv_launch(c, M, x, y, false);
+    if (rc) return rc;
+    GA_CUDA(c, cudaEventRecord(e1, c->stream));
+    GA_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GA_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) { best = ms; bg = cd[0]; bs = cd[1]; }
+  }
+  M.tune_groups = bg; M.tune_stages = bs;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  c->launches = 0;
+  return 0;
 }
 
 // First half of the normal operator on device vectors: y = A x (At_side = :left, y has m rows) or

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -124,6 +124,8 @@ def lib():
         L.ga_profile_gs_times.argtypes = [vp, vp, i64]
         L.ga_bench_opx.argtypes = [vp, i32, vp]
         L.ga_debug_trace.argtypes = [vp, vp]
+        L.ga_debug_spmv_check.argtypes = [vp, vp]
+        L.ga_tune_spmv.argtypes = [vp, i32, i32]
         L.ga_symeigs.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
         L.ga_symeigs_begin.argtypes = [vp, i32, i32, vp, i32, vp]
         L.ga_symeigs_iterate.argtypes = [vp, i32]
@@ -435,6 +437,17 @@ class Context:
             return None
         out = np.zeros(64, dtype=np.uint64)
         self._ck(lib().ga_debug_trace(self.h, _p(out)))
+        return out
+
+    def tune_spmv(self, groups, stages):
+        self._ck(lib().ga_tune_spmv(self.h, int(groups), int(stages)))
+
+    def debug_spmv_check(self, read=False):
+        if not read:
+            self._ck(lib().ga_debug_spmv_check(self.h, None))
+            return None
+        out = np.zeros(128, dtype=np.uint32)
+        self._ck(lib().ga_debug_spmv_check(self.h, _p(out)))
         return out
 
     def bench_opx(self, reps=20):

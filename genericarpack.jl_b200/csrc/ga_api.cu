@@ -115,7 +115,7 @@ void ga_destroy(ga_ctx* c) {
   c->At.free_all();
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev); cudaFree(c->wbuf);
-  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace); cudaFree(c->zinv); cudaFree(c->zrecv);
+  cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace); cudaFree(c->spmv_chk); cudaFree(c->zinv); cudaFree(c->zrecv);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -720,6 +720,35 @@ int ga_debug_trace(ga_ctx* c, uint64_t* out16) {  // 64 samples
   if (out16) {
     GA_CUDA(c, cudaStreamSynchronize(c->stream));
     GA_CUDA(c, cudaMemcpy(out16, c->trace, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// Override the upload-time autotune of the streamed SpMV for this context's operator: groups in {4, 6},
+// groups <= stages <= 8; groups == 0 selects the first (non-streamed) row-segment kernel.
+int ga_tune_spmv(ga_ctx* c, int groups, int stages) {
+  if (!c) return GA_ERR_ARG;
+  if (groups == 0) { c->use_spmv_stream = false; return 0; }
+  if ((groups != 4 && groups != 6) || stages < groups || stages > 8) return set_err(c, GA_ERR_ARG, "ga_tune_spmv: groups in {0,4,6}, groups <= stages <= 8");
+  c->use_spmv_stream = true;
+  c->A.tune_groups = c->At.tune_groups = groups;
+  c->A.tune_stages = c->At.tune_stages = stages;
+  return 0;
+}
+
+// debug: enable (out == NULL) or read back (out = 128 x uint32) the streamed SpMV's stage self-check:
+// out[0] = number of row blocks whose staged rowptr slice did not belong to the block, then 15 records
+// of 8 words from out[8] on (CTA, ring iteration, block-in-CTA, expected k0, found, expected k1, found, 16*stages+groups)
+int ga_debug_spmv_check(ga_ctx* c, uint32_t* out128) {
+  if (!c) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  if (!c->spmv_chk) {
+    GA_CUDA(c, cudaMalloc(&c->spmv_chk, 128 * sizeof(unsigned int)));
+    GA_CUDA(c, cudaMemset(c->spmv_chk, 0, 128 * sizeof(unsigned int)));
+  }
+  if (out128) {
+    GA_CUDA(c, cudaStreamSynchronize(c->stream));
+    GA_CUDA(c, cudaMemcpy(out128, c->spmv_chk, 128 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
   }
   return 0;
 }

@@ -174,6 +174,7 @@ struct ga_ctx {
   bool use_step_kernel = true;
   bool use_spmv_stream = true;          // TMA-staged persistent SpMV (GA_SPMV_V1=1 selects the first kernel)
   unsigned int gs_flip = 0;             // consecutive sweeps traverse the row tiles in opposite directions (L2 reuse)
+  unsigned int* spmv_chk = nullptr;     // device, 128 words: stale-stage self-check of the streamed SpMV (debug)
   unsigned long long* trace = nullptr;  // device, 16 globaltimer samples of the last traced sweep (debug)
   std::string err;
 };
@@ -185,7 +186,7 @@ int set_err(ga_ctx* c, int code, const std::string& msg);
   do {                                                                                           \
     cudaError_t e_ = (call);                                                                     \
     if (e_ != cudaSuccess)                                                                       \
-      return ga::set_err((ctx), GA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+      return ga::set_err((ctx), GA_ERR_CUDA, std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " + #call + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
 // ---- kernel launchers (each in its own .cu) -------------------------------------------------

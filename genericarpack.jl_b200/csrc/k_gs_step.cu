@@ -15,6 +15,8 @@
 // Same arithmetic, same fixed summation order as k_gs.cu, bit-identical results.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "ga_gs_cfg.cuh"
 
 namespace ga {
@@ -53,7 +55,7 @@ __device__ __forceinline__ void grid_barrier(DevCtl* ctl) {
 template <class T, int SEG>
 __global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
 k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ctl, double2* partial, int nstages,
-          int ncv, const DevComm* cm, unsigned long long* trace) {
+          int ncv, const DevComm* cm, unsigned long long* trace, int xprefetch) {
   typedef GsCfg<T, SEG> C;
 #define GA_TRACE(slot, cond)                                                        \
   if (trace != nullptr && (cond)) {                                                 \
@@ -140,7 +142,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       }
       // prefetch for the next phase: V does not change between the phases of a step
       npre = 0;
-      if (ph < 3) {
+      if (ph < 3 && xprefetch) {
         for (i64 t = blockIdx.x; t < ntiles && npre < nstages; t += gridDim.x, ++itp, ++npre) {
           const int s = itp % nstages;
           const uint32_t phb = (uint32_t)(itp / nstages) & 1u;
@@ -332,6 +334,8 @@ static int launch_step_seg(ga_ctx* c, int j, int nstages) {
   int ncv = c->ncv;
   const DevComm* cm = c->world > 1 ? c->devcomm : nullptr;
   unsigned long long* trace = c->trace;
+  static int xprefetch = -1;   // GA_GS_XPREFETCH=0 disables the cross-phase V prefetch (debug / A-B switch)
+  if (xprefetch < 0) { const char* e = getenv("GA_GS_XPREFETCH"); xprefetch = (e && e[0] == '0') ? 0 : 1; }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->prof) {
     if (c->prof_used + 2 > c->prof_ev.size()) {
@@ -342,7 +346,7 @@ static int launch_step_seg(ga_ctx* c, int j, int nstages) {
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
   void* args[] = {(void*)&V, (void*)&ldv, (void*)&j, (void*)&wr, (void*)&ntiles, (void*)&ctl, (void*)&partial,
-                  (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace};
+                  (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace, (void*)&xprefetch};
   GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));

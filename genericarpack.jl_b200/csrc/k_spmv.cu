@@ -105,25 +105,47 @@ template <class T, int GROUPS_ = 4> struct SpmvStreamCfg {
   // 6 stages (160 KB / 136 KB): measured on B200, 4 stages lose 20 % on the Laplacian (pipeline too
   // shallow) while 8 stages (214 KB) leave ~14 KB of L1 and halve the rate of gather-heavy matrices
   // (the L1 lines double as miss buffers for the x gathers); see profiles/RESULTS.md
-  // The stage count must be >= GROUPS: a consumer group only observes every GROUPS-th phase of the
-  // ring, and mbarrier parity waits are only unambiguous when the awaited phase is at most one
-  // ahead of the last one the group has seen complete.
+  //
+  // Ring protocol.  The stages form ONE ring shared by all consumer groups, so unless GROUPS divides
+  // the stage count a group observes only some of the phases of a stage's `full` barrier, and a
+  // parity wait alone is ambiguous: if the previous fill of the stage is still in flight when the
+  // group arrives, the awaited parity equals that of the phase before it and the wait falls
+  // through.  That happens on B200 (bulk copies do NOT complete in issue order: with (groups,
+  // stages) = (4, 5) / (6, 8) the complex stencil gave wrong products once per ~10^6 row blocks, or
+  // read a never-filled stage), so the producer also publishes the ring iteration held by a stage
+  // (`seq[s]`, written before it arms the barrier) and a consumer re-waits until the stage holds ITS
+  // iteration (wait_stage below).  Any stage count >= GROUPS is then correct.
   static constexpr int MAX_STAGES = 8;
   static constexpr int STAGES = 6;
-  static constexpr int smem_bytes(int nst) { return nst * STAGE_BYTES + 2 * MAX_STAGES * 8 + 16; }
+  static constexpr int BAR_BYTES = 2 * MAX_STAGES * 8 + MAX_STAGES * 4 + 16;   // full[], empty[], seq[]
+  static constexpr int smem_bytes(int nst) { return nst * STAGE_BYTES + BAR_BYTES; }
 };
+
+// Block until stage `s` holds ring iteration `it` (phase parity `ph` of its `full` barrier).  While an
+// OLDER fill of the stage is still in flight the parity wait falls through and `seq` names that older
+// iteration: poll (the window is the tail of one bulk copy) until the barrier has moved on; from then
+// on the parity wait blocks properly.  No second blocking wait on the opposite parity: the barrier may
+// advance two phases between the two instructions, which would park this group forever.
+__device__ __forceinline__ void wait_stage(uint64_t* full_s, const volatile int* seq_s, uint32_t ph, int it) {
+  for (;;) {
+    mbar_wait(full_s, ph);
+    if (*seq_s == it) return;       // armed for `it` by the producer, and complete
+    __nanosleep(32);
+  }
+}
 
 template <class T, int NG>
 __global__ void __launch_bounds__(SpmvStreamCfg<T, NG>::THREADS, 1)
 k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ rowptr, const int* __restrict__ col,
               const T* __restrict__ val, const T* __restrict__ x, const T* __restrict__ xh, int nsplit,
-              T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm, int NST) {
+              T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm, int NST, unsigned int* chk) {
   typedef SpmvStreamCfg<T, NG> C;
   constexpr int GT = C::GT, GROUPS = C::GROUPS;
   if (gated && ctl->status != ST_OK) return;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NST * C::STAGE_BYTES);
   uint64_t* empty = full + C::MAX_STAGES;
+  volatile int* seq = reinterpret_cast<volatile int*>(empty + C::MAX_STAGES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // contiguous chunk of row blocks per CTA: consecutive blocks share most of their x window, so the
   // four consumer groups of a CTA (working on adjacent blocks) hit the same L1 lines
@@ -131,7 +153,7 @@ k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ 
   const int b_begin = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
   const int b_end = b_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
   if (tid == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GT / 32); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GT / 32); seq[s] = -1; }
     fence_mbar_init();
   }
   __syncthreads();
@@ -152,6 +174,7 @@ k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ 
         const int k0a = d.z & ~3, k1a = (d.w + 3) & ~3;
         const int r0a = d.x & ~3, nrp = (d.y - r0a + 1 + 3) & ~3;
         const uint32_t nk = (uint32_t)(k1a - k0a);
+        seq[s] = it;   // published by the release of the arrive below
         mbar_arrive_expect_tx(&full[s], nk * (4u + (uint32_t)sizeof(T)) + (uint32_t)nrp * 4u);
         if (nk > 0) {
           bulk_g2s(st, col + k0a, nk * 4u, &full[s]);
@@ -186,7 +209,19 @@ k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ 
     const int* cs = reinterpret_cast<const int*>(st) + sh;
     T* vs = reinterpret_cast<T*>(st + C::COL_BYTES) + sh;
     const int* rp = reinterpret_cast<const int*>(st + C::COL_BYTES + C::VAL_BYTES) + (d.x - (d.x & ~3));
-    mbar_wait(&full[s], ph);
+    wait_stage(&full[s], &seq[s], ph, it);
+    if (chk != nullptr && (gt & 31) == 0) {
+      // debug self-check (ga_debug_spmv_check): the staged rowptr slice must be the one of THIS row block
+      const int f0 = rp[0], f1 = rp[d.y - d.x];
+      if (f0 != d.z || f1 != d.w) {
+        const unsigned int i = atomicAdd(&chk[0], 1u);
+        if (i < 15u) {
+          unsigned int* o = chk + 8 + 8 * i;
+          o[0] = blockIdx.x; o[1] = (unsigned)it; o[2] = (unsigned)(b - b_begin); o[3] = (unsigned)d.z; o[4] = (unsigned)f0;
+          o[5] = (unsigned)d.w; o[6] = (unsigned)f1; o[7] = (unsigned)(NST * 16 + GROUPS);
+        }
+      }
+    }
     // products in place: vs[k] <- val[k] * x[col[k]], 8 independent gathers in flight per thread
     for (int k = gt; k < cnt; k += 8 * GT) {
       int cc[8];
@@ -265,7 +300,7 @@ static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void*
   k_spmv_stream<T, NG><<<grid, C::THREADS, C::smem_bytes(nst), c->stream>>>(M.desc, M.ndesc, M.rowptr, M.col,
                                                                            (const T*)M.val, (const T*)x,
                                                                            (const T*)c->halo, nsplit, (T*)y, c->ctl,
-                                                                           gated ? 1 : 0, cm, nst);
+                                                                           gated ? 1 : 0, cm, nst, c->spmv_chk);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   return 0;

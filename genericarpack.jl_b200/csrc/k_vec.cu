@@ -60,8 +60,17 @@ __global__ void __launch_bounds__(256) k_normalize(T* vj, const T* resid, i64 n,
   const i64 stride = (i64)gridDim.x * blockDim.x;
   const bool safe = rnorm >= Real<TR>::floatmin();
   const TR temp1 = Real<TR>::from(1.0) / rnorm;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    vj[i] = scaled_by_inv_norm<T, TR>(resid[i], rnorm, temp1, safe);
+  // vj may alias resid, so the compiler cannot batch the loads on its own: stage four elements in
+  // registers before the stores (four independent loads in flight per thread)
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const T a0 = resid[i], a1 = resid[i + stride], a2 = resid[i + 2 * stride], a3 = resid[i + 3 * stride];
+    vj[i] = scaled_by_inv_norm<T, TR>(a0, rnorm, temp1, safe);
+    vj[i + stride] = scaled_by_inv_norm<T, TR>(a1, rnorm, temp1, safe);
+    vj[i + 2 * stride] = scaled_by_inv_norm<T, TR>(a2, rnorm, temp1, safe);
+    vj[i + 3 * stride] = scaled_by_inv_norm<T, TR>(a3, rnorm, temp1, safe);
+  }
+  for (; i < n; i += stride) vj[i] = scaled_by_inv_norm<T, TR>(resid[i], rnorm, temp1, safe);
   if (!cm) return;
   const int nsend = cm->send_off[cm->world];
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nsend; i += stride) {

@@ -182,6 +182,14 @@ int ga_bench_opx(ga_ctx* ctx, int reps, double* ms);
 /* debug: out16 == NULL enables an in-kernel globaltimer timeline of the Gram-Schmidt sweep; a later
  * call with out16 != NULL reads the 64 samples (ns) of the most recent sweep launch. */
 int ga_debug_trace(ga_ctx* ctx, uint64_t* out16);
+/* Override the per-matrix autotune of the streamed SpMV (tuning aid): groups in {4, 6} consumer groups,
+ * groups <= stages <= 8 pipeline stages; groups == 0 selects the first, non-streamed kernel.  Every
+ * configuration computes the same bits. */
+int ga_tune_spmv(ga_ctx* ctx, int groups, int stages);
+/* debug: out128 == NULL arms a self-check inside the streamed SpMV (every consumer group verifies that the
+ * rowptr slice staged by TMA belongs to its row block); a later call with out128 != NULL reads the counter
+ * (out128[0]) and up to 15 records of 8 words from out128[8] on. */
+int ga_debug_spmv_check(ga_ctx* ctx, uint32_t* out128);
 int ga_profile_read(ga_ctx* ctx, double* gs_ms, int64_t* gs_runs, int64_t* gs_units, int64_t* launches);
 /* number of Gram-Schmidt kernel launches bracketed since ga_profile(ctx, 1) (the persistent step kernel
  * runs all sweeps of a Lanczos step in one launch, so this is <= gs_runs). */

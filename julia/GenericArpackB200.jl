@@ -9,9 +9,10 @@
 module GenericArpackB200
 
 using GenericArpack, LinearAlgebra, SparseArrays
-import GenericArpack: ArpackOp, AbstractArpackState, ArpackState, AitrState, Getv0State, Saup2State,
+import GenericArpack: ArpackOp, ArpackNormalSVDOp, AbstractArpackState, ArpackState, AitrState, Getv0State, Saup2State,
                       dgetv0!, dsaitr!, dsapps!, dorm2r!, norm2, opx!, arpack_mode, bmat,
-                      is_arpack_mode_valid_for_op, symeigs
+                      is_arpack_mode_valid_for_op, symeigs, eigenvecs_to_singvecs!, _uv_size,
+                      _adjust_nev_which_for_svd, _adjust_eigenvalues_to_singular_values!
 
 const lib = "libgarpack_b200.so"
 const GA_F64, GA_C64, GA_DD = Cint(0), Cint(1), Cint(2)
@@ -135,6 +136,48 @@ function symeigs(::Type{TV}, ::Type{TF}, op::B200ArpackOp{TV}, nev::Integer; ncv
   state = B200ArpackState{TF}(ctx=op.ctx)
   V = DeviceMatrix{TV}(op.ctx, op.n, ncv); resid = DeviceVector{TV}(op.ctx, op.n); workd = DeviceVector{TV}(op.ctx, 3op.n)
   return GenericArpack._symeigs_with_arrays(TV, TF, op, nev, V, resid, workd; ncv, state, kwargs...)  # body of :245-289 with the allocations hoisted
+end
+
+# ---- svds: ArpackNormalOp on the device (src/idonow_ops.jl:216-333).  `svds(B200NormalOp(A, ncv), k)` runs the
+# reference's own svds (src/interface.jl:312-337): symeigs on A'A / AA' through the methods above, then
+# eigenvecs_to_singvecs!, which here is ONE library call (A*v_i, norms, scaling and orth! on the device).
+mutable struct B200NormalOp{T} <: ArpackNormalSVDOp
+  ctx::Ptr{Cvoid}; m::Int; n::Int; ncv::Int
+end
+function B200NormalOp(A::SparseMatrixCSC{T}, ncv::Int; device::Int=0) where T
+  m, n = size(A)
+  At = SparseMatrixCSC(transpose(A)); rowptr = Int64.(At.colptr .- 1); col = Int32.(At.rowval .- 1)   # CSR of A
+  ctxref = Ref{Ptr{Cvoid}}(C_NULL); sz = min(m, n)
+  rc = ccall((:ga_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Cint, Int64, Int64, Int64, Cint, Cint, Cint, Cint),
+             ctxref, ga_dtype(T), sz, sz, 0, ncv, device, 0, 1)
+  rc == 0 || error("ga_create failed ($rc)")
+  check(ccall((:ga_set_normal_csr, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}),
+              ctxref[], m, n, rowptr, col, At.nzval), ctxref[])
+  op = B200NormalOp{T}(ctxref[], m, n, ncv)
+  finalizer(o -> ccall((:ga_destroy, lib), Cvoid, (Ptr{Cvoid},), o.ctx), op)
+  return op
+end
+Base.size(op::B200NormalOp) = min(op.m, op.n)
+arpack_mode(::B200NormalOp) = 1
+bmat(::B200NormalOp) = Val(:I)
+_uv_size(op::B200NormalOp) = (op.m, op.n)
+# _adjust_nev_which_for_svd / _adjust_eigenvalues_to_singular_values! are inherited from ArpackNormalSVDOp (:240-260)
+
+# eigenvecs_to_singvecs!(U, V, OP, Z) (src/idonow_ops.jl:295-333): Z holds the (re-sorted) eigenvectors; the
+# device still holds them as basis columns, `perm` says which column is Z[:,i].  The reference's check_norm
+# thresholds are applied to the norms the library returns.
+function eigenvecs_to_singvecs!(U::AbstractMatrix{T}, V::AbstractMatrix{T}, op::B200NormalOp{T}, Z::AbstractMatrix{T};
+                                perm::Vector{Int32}=Int32.(size(Z, 2)-1:-1:0)) where T
+  k = size(Z, 2); left = op.m > op.n
+  W = left ? U : V; copyto!(left ? V : U, Z)
+  norms = Vector{real(T)}(undef, k)
+  rc = ccall((:ga_svd_vectors, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+             op.ctx, k, perm, W, size(W, 1), norms)
+  rc == -104 && throw(GenericArpack.ArpackException("encountered σ ≈ 0 when computing $(left ? "U" : "V") subspace"))
+  check(rc, op.ctx)
+  any(norms .<= eps(real(T))/2) && throw(GenericArpack.ArpackException("encountered σ ≈ $(minimum(norms))"))
+  any(norms .<= GenericArpack._eps23(real(T))) && @warn "subspace may be inaccurate due to small singular value"
+  return nothing
 end
 
 end # module

@@ -139,6 +139,34 @@ def test_opx_stream_vs_first_kernel_bitwise(pkg, O, dtype, monkeypatch):
     assert np.allclose(got, yref, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("dtype", ["f64", "c64"])
+def test_opx_stream_every_ring_config_bitwise(pkg, syn, dtype):
+    """Every (consumer groups, stages) pair of the streamed SpMV computes the same bits as the first
+    kernel, repeatedly, on a matrix large enough for the persistent ring to wrap many times (>= 4 x 148
+    row blocks, the size from which the upload-time autotune picks among these configurations).  The
+    shared ring is only correct because consumers re-check which iteration a stage holds (bulk copies
+    complete out of issue order on B200); the in-kernel self-check must stay silent."""
+    m = 640
+    csr = syn.hermitian_stencil(m) if dtype == "c64" else syn.laplacian2d(m)
+    n = m * m
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(n) + (1j * rng.standard_normal(n) if dtype == "c64" else 0.0)
+    ctx = pkg.Context(pkg.ArpackSimpleOp(csr, dtype=dtype), 2)
+    ctx.tune_spmv(0, 0)
+    y0 = np.array(ctx.opx(x))
+    assert np.allclose(y0, syn.to_scipy(csr) @ x, rtol=1e-13, atol=1e-13)
+    ctx.debug_spmv_check()
+    for g, st in [(4, 4), (4, 5), (4, 6), (4, 7), (4, 8), (6, 6), (6, 7), (6, 8)]:
+        ctx.tune_spmv(g, st)
+        for rep in range(6):
+            y = np.array(ctx.opx(x))
+            assert np.array_equal(y.view(np.uint64), y0.view(np.uint64)), (g, st, rep)
+    assert int(ctx.debug_spmv_check(read=True)[0]) == 0
+    with pytest.raises(pkg.ArpackException):
+        ctx.tune_spmv(6, 5)
+    ctx.close()
+
+
 def test_normal_opx(pkg, syn, O):
     A = syn.to_scipy(syn.tall_sparse(5000, 300, 6))
     op = pkg.ArpackNormalOp(A)
@@ -579,6 +607,35 @@ def test_full_size_properties(pkg, syn):
     w = np.linalg.eigvalsh(T)
     assert w.min() > 0 and w.max() < 8
     ctx.close()
+
+
+def test_full_size_complex_c4(pkg, syn):
+    """BASELINE config C4 at full size (complex Hermitian stencil, n = 4M, nev = 6, ncv = 30): the whole
+    solve, checked through properties only -- true Ritz residuals ||A z - lambda z|| <= 1e-10 |lambda|
+    against SciPy's SpMV, orthonormal Ritz vectors, and a solve with the first SpMV kernel giving the
+    same restart count and eigenvalues (the streamed kernel's configurations are bit-identical)."""
+    m = 2000
+    csr = syn.hermitian_stencil(m)
+    A = syn.to_scipy(csr)
+    res = []
+    for first_kernel in (False, True):
+        ctx = pkg.Context(pkg.ArpackSimpleOp(csr, dtype="c64"), 30)
+        if first_kernel:
+            ctx.tune_spmv(0, 0)
+        assert ctx.symeigs_begin(6, "LM", 0.0, 300, None) == 0
+        ctx.symeigs_iterate(-1)
+        rc, vals, bounds, Z, iparam = ctx.symeigs_end(6, True)
+        assert rc == 0 and len(vals) == 6
+        res.append((vals.copy(), int(iparam[2]), ctx.stats()["nopx"]))
+        if not first_kernel:
+            for i in range(6):
+                r = A @ Z[:, i] - vals[i] * Z[:, i]
+                assert np.linalg.norm(r) <= 1e-10 * abs(vals[i])
+            G = Z.conj().T @ Z
+            assert np.allclose(G, np.eye(6), atol=1e-12)
+        ctx.close()
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2]
+    assert np.array_equal(res[0][0], res[1][0])
 
 
 def test_large_ncv_fallback(pkg, syn, O):

@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=4000, help="grid side (n = m*m); 4000 = BASELINE config C2")
+    ap.add_argument("--m", "--grid", dest="m", type=int, default=4000, help="grid side (n = m*m); 4000 = BASELINE config C2")
     ap.add_argument("--nev", type=int, default=10)
     ap.add_argument("--ncv", type=int, default=40)
     ap.add_argument("--tts", action="store_true", help="also run the full solve (time to solution)")

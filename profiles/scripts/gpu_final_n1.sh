@@ -13,7 +13,7 @@ echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gs_step|k_spmv_stream|k_vq" -s 270 -c 6 -o gpurun_out/final_prof $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 timeout 400 python profiles/run_configs.py c1 c3 c4 c5 > gpurun_out/final_configs.log 2>&1; echo "configs rc=$?"; cp gpurun_out/configs.json gpurun_out/final_configs.json
-timeout 400 python bench.py --m 8000 --no-cpu --no-e2e --steps 5 > gpurun_out/final_bench_64M_n1.json 2> gpurun_out/final_bench_64M_n1.err; echo "64M rc=$?"
+timeout 400 python bench.py --grid 8000 --no-cpu --no-e2e --steps 5 > gpurun_out/final_bench_64M_n1.json 2> gpurun_out/final_bench_64M_n1.err; echo "64M rc=$?"
 python - <<'PY'
 import json
 for f in ["final_bench_n1","final_bench_ref","final_bench_64M_n1"]:

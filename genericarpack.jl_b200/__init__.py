@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 __all__ = [
-    "ArpackException", "ArpackSimpleOp", "ArpackNormalOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
+    "ArpackException", "ArpackSimpleOp", "ArpackNormalOp", "ArpackSymmetricGeneralizedOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
     "Context", "comm_unique_id", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD",
 ]
 
@@ -33,7 +33,7 @@ _SO = os.path.join(_HERE, "libgarpack_b200.so")
 _LIB = None
 
 GA_F64, GA_C64, GA_DD = 0, 1, 2
-GA_ERR_CUDA, GA_ERR_ARG, GA_ERR_NOOP, GA_ERR_COMM, GA_ERR_NUMERIC = -100, -101, -102, -103, -104
+GA_ERR_CUDA, GA_ERR_ARG, GA_ERR_NOOP, GA_ERR_COMM, GA_ERR_NUMERIC, GA_ERR_SOLVE = -100, -101, -102, -103, -104, -105
 _DTYPES = {"f64": GA_F64, "float64": GA_F64, "c64": GA_C64, "complex128": GA_C64, "dd": GA_DD, "double64": GA_DD,
            GA_F64: GA_F64, GA_C64: GA_C64, GA_DD: GA_DD}
 _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -104,6 +104,10 @@ def lib():
         L.ga_set_normal_csr.argtypes = [vp, i64, i64, vp, vp, vp]
         L.ga_set_normal_csr_dist.argtypes = [vp, i64, vp, vp, vp, i32, vp, vp, vp, vp]
         L.ga_opx.argtypes = [vp, vp, vp]
+        L.ga_set_generalized_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.ga_set_solve_callback.argtypes = [vp, vp, vp]
+        L.ga_bx.argtypes = [vp, vp, vp]
+        L.ga_get_solve_stats.argtypes = [vp, vp, vp, vp]
         L.ga_upload_resid.argtypes = [vp, vp]
         L.ga_download_resid.argtypes = [vp, vp]
         L.ga_upload_v.argtypes = [vp, i32, i32, vp, i64]
@@ -233,6 +237,31 @@ class ArpackNormalOp(B200ArpackOp):  # src/idonow_ops.jl:216-277
         return "right" if m <= n else "left"
 
 
+class ArpackSymmetricGeneralizedOp(B200ArpackOp):
+    """ArpackSymmetricGeneralizedOp(A, S, B) (src/idonow_ops.jl:462-492): A x = lambda B x in mode 2 with
+    bmat = :G.  A and B are full (both triangles) sparse matrices, B Hermitian positive definite.  The
+    reference's factorisation object S is replaced by a preconditioned conjugate-gradient solve with B on
+    the device (relative residual ``cg_tol``, default 8 eps; at most ``cg_maxit`` iterations)."""
+
+    arpack_mode = 2
+    bmat = "G"
+
+    def __init__(self, A, B, dtype=None, cg_tol=None, cg_maxit=0):
+        import scipy.sparse as sp
+
+        if dtype is None:
+            cplx = any(np.iscomplexobj(M[2] if isinstance(M, tuple) else sp.csr_matrix(M).data) for M in (A, B))
+            dtype = GA_C64 if cplx else GA_F64
+        super().__init__(A, dtype=dtype)
+        self.Bop = B200ArpackOp(B, dtype=dtype)
+        if self.Bop.shape != self.shape or self.shape[0] != self.shape[1]:
+            raise ValueError("A and B must be square matrices of the same size")
+        self.cg_tol, self.cg_maxit = cg_tol, int(cg_maxit)
+
+    def is_arpack_mode_valid_for_op(self, mode):
+        return mode == 2
+
+
 # ------------------------------------------------------------------ low-level context
 class Context:
     """One device problem instance = the arrays symeigs allocates (src/interface.jl:245-251) on
@@ -258,7 +287,13 @@ class Context:
         if rc != 0 or not h:
             raise RuntimeError("ga_create failed with code %d (is a CUDA device present? there is no CPU fallback)" % rc)
         self.h = h
-        if op.normal and world_size > 1:
+        if isinstance(op, ArpackSymmetricGeneralizedOp):
+            if world_size != 1:
+                raise ValueError("the generalised problem runs on one GPU")
+            tol = None if op.cg_tol is None else np.array([float(op.cg_tol), 0.0])
+            self._ck(L.ga_set_generalized_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val), _p(op.Bop.rowptr),
+                                              _p(op.Bop.col), _p(op.Bop.val), _p(tol), op.cg_maxit))
+        elif op.normal and world_size > 1:
             if plan is None:
                 raise ValueError("a multi-GPU context needs the halo plan (dist.halo_plan / dist.shard_normal)")
             self.plan = plan
@@ -343,6 +378,19 @@ class Context:
         y = np.zeros_like(x)
         self._ck(lib().ga_opx(self.h, _p(x), _p(y)))
         return y
+
+    def bx(self, x):
+        """bx!(y, op, x) of the generalised problem: y = B x."""
+        x = to_elem(x, self.dtype)
+        y = np.zeros_like(x)
+        self._ck(lib().ga_bx(self.h, _p(x), _p(y)))
+        return y
+
+    def solve_stats(self):
+        """(solves with B, CG iterations in total, largest final relative residual)."""
+        a, b, r = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0.0)
+        lib().ga_get_solve_stats(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(r))
+        return a.value, b.value, r.value
 
     # --- hot path
     def getv0(self, initv=False, j=1):
@@ -525,18 +573,29 @@ class ArpackEigen:
         return self.ctx.download_resid()
 
 
-def _as_op(A, dtype=None, normal=False):
+def _as_op(A, dtype=None, normal=False, B=None):
     if isinstance(A, B200ArpackOp):
         return A
+    if B is not None:
+        return ArpackSymmetricGeneralizedOp(A, B, dtype=dtype)
     return (ArpackNormalOp if normal else ArpackSimpleOp)(A, dtype=dtype)
 
 
-def symeigs(A, nev, *, which="LM", maxiter=None, ncv=None, v0=None, stats=None, tol=0.0, ritzvec=True,
+def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, tol=0.0, ritzvec=True,
             failonmaxiter=True, dtype=None, device=0, keep_context=False):
     """symeigs(TV, TF, op, nev; which, maxiter, ncv, v0, stats, tol, ritzvec, failonmaxiter)
-    (src/interface.jl:215-290) on the B200.  ``A``: scipy sparse matrix (full storage) or a
-    B200ArpackOp.  Returns an ArpackEigen; values ascending like the reference."""
-    op = _as_op(A, dtype)
+    (src/interface.jl:215-290) on the B200.  ``symeigs(A, nev)``: scipy sparse matrix (full storage) or a
+    B200ArpackOp; ``symeigs(A, B, nev)``: the generalised problem A x = lambda B x through
+    ArpackSymmetricGeneralizedOp (src/interface.jl:143-163).  Returns an ArpackEigen; values ascending like
+    the reference."""
+    if len(args) == 1:
+        B, nev = None, args[0]
+    elif len(args) == 2:
+        B, nev = args
+    else:
+        raise TypeError("symeigs(A, nev) or symeigs(A, B, nev)")
+    nev = int(nev)
+    op = _as_op(A, dtype, B=B)
     n = op.size()
     if maxiter is None:
         maxiter = max(300, int(math.ceil(math.sqrt(n))))            # :217
@@ -568,14 +627,15 @@ def symeigs(A, nev, *, which="LM", maxiter=None, ncv=None, v0=None, stats=None, 
             ctx.close()
 
 
-def eigs(A, k, **kw):
-    """eigs(Symmetric(A) / Hermitian(A), k; kwargs...) (src/interface.jl:133-139)."""
-    return symeigs(A, k, **kw)
+def eigs(A, *args, **kw):
+    """eigs(Symmetric(A) / Hermitian(A), k; kwargs...) (src/interface.jl:133-139) and
+    eigs(Symmetric(A), Symmetric(B), k; kwargs...) (:143-147)."""
+    return symeigs(A, *args, **kw)
 
 
-def hermeigs(A, k, **kw):  # src/interface.jl:158-168
+def hermeigs(A, *args, **kw):  # src/interface.jl:158-168
     kw.setdefault("dtype", "c64")
-    return symeigs(A, k, **kw)
+    return symeigs(A, *args, **kw)
 
 
 class SVD:

@@ -113,6 +113,7 @@ void ga_destroy(ga_ctx* c) {
   comm_destroy(c);
   c->A.free_all();
   c->At.free_all();
+  general_free(c);
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev); cudaFree(c->wbuf);
   cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace); cudaFree(c->spmv_chk); cudaFree(c->zinv); cudaFree(c->zrecv);
@@ -310,6 +311,60 @@ int ga_set_normal_csr_dist(ga_ctx* c, int64_t mt_local, const int64_t* rowptr, c
   return spmv_autotune(c, c->At, c->xfull, c->zp[0]);
 }
 
+// ArpackSymmetricGeneralizedOp(A, S, B): mode 2, bmat = :G (see the header and k_general.cu)
+int ga_set_generalized_csr(ga_ctx* c, const int64_t* a_rowptr, const int32_t* a_col, const void* a_val,
+                           const int64_t* b_rowptr, const int32_t* b_col, const void* b_val, const double* cg_tol,
+                           int cg_maxit) {
+  if (!c || !a_rowptr || !a_col || !a_val || !b_rowptr || !b_col || !b_val || cg_maxit < 0) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  c->op_kind = 0;
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "generalised problem: single GPU only");
+  c->cg_tol[0] = cg_tol ? cg_tol[0] : 0.0;
+  c->cg_tol[1] = 0.0;
+  c->cg_maxit = cg_maxit;
+  c->solve_count = c->solve_iters = 0;
+  c->solve_max_relres = 0.0;
+  int rc = general_upload(c, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val);
+  if (rc) return rc;
+  c->op_kind = 3;
+  return 0;
+}
+
+int ga_set_solve_callback(ga_ctx* c, ga_solve_fn fn, void* user) {
+  if (!c) return GA_ERR_ARG;
+  c->solve_cb = fn;
+  c->solve_user = user;
+  return 0;
+}
+
+int ga_get_solve_stats(const ga_ctx* c, int64_t* solves, int64_t* iterations, double* max_relres) {
+  if (!c) return GA_ERR_ARG;
+  if (solves) *solves = c->solve_count;
+  if (iterations) *iterations = c->solve_iters;
+  if (max_relres) *max_relres = c->solve_max_relres;
+  return 0;
+}
+
+int ga_bx(ga_ctx* c, const void* x_host, void* y_host) {
+  if (!c || !x_host || !y_host) return GA_ERR_ARG;
+  if (c->op_kind != 3) return set_err(c, GA_ERR_NOOP, "ga_bx: not a generalised-problem context (ga_set_generalized_csr)");
+  GA_CUDA(c, cudaSetDevice(c->device));
+  void *dx = nullptr, *dy = nullptr;
+  GA_CUDA(c, cudaMalloc(&dx, (size_t)c->n_pad * c->esize));
+  GA_CUDA(c, cudaMalloc(&dy, (size_t)c->n_pad * c->esize));
+  GA_CUDA(c, cudaMemsetAsync(dx, 0, (size_t)c->n_pad * c->esize, c->stream));
+  GA_CUDA(c, cudaMemsetAsync(dy, 0, (size_t)c->n_pad * c->esize, c->stream));
+  GA_CUDA(c, cudaMemcpyAsync(dx, x_host, (size_t)c->n * c->esize, cudaMemcpyHostToDevice, c->stream));
+  int rc = general_bx(c, dx, dy);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(y_host, dy, (size_t)c->n * c->esize, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_err(c, GA_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
 int ga_opx(ga_ctx* c, const void* x_host, void* y_host) {
   if (!c || !x_host || !y_host) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
@@ -378,6 +433,7 @@ static bool real_gt_717(const ga_ctx* c, const double a[2], const double b[2]) {
 int ga_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm) {
   if (!c || !iseed || !rnorm || j < 1 || j > c->ncv) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
+  if (c->op_kind == 3) return general_getv0(c, iseed, initv, j, rnorm);   // bmat = :G
   const double t0 = now_s();
   int rc = reset_status(c);
   if (rc) return rc;
@@ -455,6 +511,7 @@ int ga_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, int64_
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
   if (np == 0) return 0;
   GA_CUDA(c, cudaSetDevice(c->device));
+  if (c->op_kind == 3) return general_lanczos(c, k, np, H, ldh, rnorm, iseed);   // mode 2, bmat = :G
   const double t0 = now_s();
   const size_t rs = real_size(c);
   // control block: status/phase cleared, counters cleared, rnorm from the caller
@@ -541,6 +598,7 @@ int ga_apply_shifts(ga_ctx* c, int kev, int np, const void* Q, int ldq, const do
   if (rc) return rc;
   if ((rc = sync_ctl(c))) return rc;
   pair_to_host_real(c, c->ctl_host->rnorm, rnorm_out);
+  if (c->op_kind == 3 && (rc = general_resid_bnorm(c, rnorm_out))) return rc;   // bmat = :G: the B-norm (src/dsaup2.jl:1383-1411)
   c->stats.tapps += now_s() - t0;
   return 0;
 }

@@ -18,7 +18,8 @@ constexpr int kMaxWorld = 8;  // one NVSwitch node
 
 // Step phases written by the on-device decision logic (dsaitr's flags, src/dsaitr.jl:1324-1447)
 enum : int { PH_DONE = 0, PH_ORTH1 = 1, PH_ORTH2 = 2 };
-enum : int { ST_OK = 0, ST_BREAKDOWN = 1, ST_NUMERIC = 2, ST_COMM = 3 };
+enum : int { ST_OK = 0, ST_BREAKDOWN = 1, ST_NUMERIC = 2, ST_COMM = 3,
+              ST_CG_DONE = 100 /* the B-solve of the generalised problem converged: later launches of the batch are no-ops */ };
 
 // What the last CTA of a reduction kernel does with the reduced slots.
 enum : int {
@@ -29,7 +30,8 @@ enum : int {
   DK_ORTH2 = 4,   // second DGKS correction done                       (:1424-1446)
   DK_GETV0_DOT = 5,  // getv0 restart: h <- dots, rnorm0 <- norm       (src/dgetv0.jl:630,662)
   DK_GETV0_UPD = 6,  // getv0 restart: rnorm <- norm, h <- dots        (:665,700)
-  DK_NORM = 7     // rnorm <- norm                                    (src/dsaup2.jl:1414)
+  DK_NORM = 7,    // rnorm <- norm                                    (src/dsaup2.jl:1414)
+  DK_TAKE = 8     // h <- dots, nothing else (bmat = :G: the host runs the step's scalar logic)
 };
 
 // Small control block in device memory.  Reals are stored as (hi, lo); lo = 0 for F64/C64.
@@ -51,6 +53,9 @@ struct DevCtl {
   double2 red[kMaxSlots];    // reduced slots of the last reduction kernel
   double2 hbuf[kMaxNcv];     // coefficient vector h / s (element type T, padded to 16 B)
   double2 H[2 * kMaxNcv];    // H(:,1) sub-diagonal [0..ncv), H(:,2) diagonal [ncv..2ncv), real type
+  // conjugate-gradient B-solve of the generalised problem (k_general.cu); reals as (hi, lo)
+  double cg_rz[2], cg_pq[2], cg_bb[2], cg_rr[2], cg_beta[2], cg_tol2[2];
+  int cg_iters, cg_pad;
 };
 
 // Peer-memory mailbox (one per GPU, IPC-mapped into every peer): the fused compute+collective
@@ -130,8 +135,19 @@ struct ga_ctx {
   void* zdev = nullptr; ga::i64 zcols = 0;
 
   // operator
-  int op_kind = 0;  // 0 none, 1 simple CSR, 2 normal (A^H A / A A^H)
+  int op_kind = 0;  // 0 none, 1 simple CSR, 2 normal (A^H A / A A^H), 3 generalised A x = lambda B x (mode 2, bmat = :G)
   ga::CsrDev A, At;  // At: explicit adjoint CSR for the normal operator
+  // generalised problem (ArpackSymmetricGeneralizedOp, src/idonow_ops.jl:462-492): B, the A*v / B*r work vector
+  // of the B-inner products, and the work vectors + Jacobi preconditioner of the CG solve with B
+  ga::CsrDev Bm;
+  void* gz = nullptr;                  // n_pad: A v_j (mode 2: WORKD(IVJ)) or B r (WORKD(IPJ))
+  void* cg_r = nullptr; void* cg_p = nullptr; void* cg_q = nullptr;   // n_pad each
+  void* b_dinv = nullptr;              // n_pad reals: 1 / diag(B)
+  double cg_tol[2] = {0.0, 0.0};       // relative residual target of the solve (<= 0: 8 eps)
+  int cg_maxit = 0;                    // 0: 1000
+  ga_solve_fn solve_cb = nullptr; void* solve_user = nullptr;   // optional user solve (device pointers)
+  long long solve_count = 0, solve_iters = 0; double solve_max_relres = 0.0;
+  const void* gs_dotvec = nullptr;     // when set, the MODE 0 sweep forms V' * (this vector) instead of V' * resid
   ga::i64 normal_m = 0, normal_n = 0; bool normal_left = true;
 
   // collectives (NCCL, loaded at run time)
@@ -208,6 +224,17 @@ int launch_gs(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind);
 int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind);
 // k_gs_step.cu
 int launch_gs_step(ga_ctx* c, int j);
+// k_spmv.cu: y = M x for any uploaded CSR matrix (device vectors)
+int launch_spmv_mat(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated);
+// k_general.cu: generalised problem A x = lambda B x (mode 2, bmat = :G), host-driven scalar logic
+int general_upload(ga_ctx* c, const int64_t* arp, const int32_t* acol, const void* aval, const int64_t* brp,
+                   const int32_t* bcol, const void* bval);
+void general_free(ga_ctx* c);
+int general_opx(ga_ctx* c, const void* x, void* y, void* ax_out);   // y = inv(B) A x; ax_out (may be null) <- A x
+int general_bx(ga_ctx* c, const void* x, void* y);                  // y = B x
+int general_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm);
+int general_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, int64_t iseed[4]);
+int general_resid_bnorm(ga_ctx* c, double* rnorm_out);              // sqrt|resid' B resid| (src/dsaup2.jl:1383-1411)
 // k_update.cu
 int launch_vq(ga_ctx* c, int kplusp, int nout, bool do_resid, const void* sigma, const void* beta, int kev);
 

@@ -115,7 +115,8 @@ __device__ void gs_decide(DevCtl* ctl, const double2* red, int j, int ncv, int k
     }
     if (r_isnan(nrm)) ctl->status = ST_NUMERIC;
   }
-  take_dots = (kind == DK_DOT || kind == DK_CGS || kind == DK_ORTH1 || kind == DK_GETV0_DOT || kind == DK_GETV0_UPD);
+  take_dots = (kind == DK_DOT || kind == DK_CGS || kind == DK_ORTH1 || kind == DK_GETV0_DOT || kind == DK_GETV0_UPD ||
+               kind == DK_TAKE);
   if (take_dots)
     for (int c = threadIdx.x; c < j; c += blockDim.x) hb[c] = slot_to_elem<T>(red[c]);
 }

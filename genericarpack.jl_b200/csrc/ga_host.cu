@@ -162,7 +162,7 @@ struct Solve : SolveBase {
     if (aupd_info == 2) aupd_info = 3;                         // src/dsaupd.jl:1092-1094
     if (iparam_out) {
       for (int i = 0; i < 11; ++i) iparam_out[i] = 0;
-      iparam_out[0] = ishift; iparam_out[3] = 1; iparam_out[6] = 1;
+      iparam_out[0] = ishift; iparam_out[3] = 1; iparam_out[6] = c->op_kind == 3 ? 2 : 1;   // mode
       iparam_out[2] = mxiter;                                  // :1081
       iparam_out[4] = finished ? np : 0;                       // :1082 (nconv)
       iparam_out[8] = c->stats.nopx; iparam_out[9] = c->stats.nbx; iparam_out[10] = c->stats.nrorth;

@@ -232,6 +232,8 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
   if (grid > kMaxCtas) grid = kMaxCtas;
   const T* V = (const T*)c->vs.V;
   T* r = (T*)c->vs.w;
+  // bmat = :G: the dots of a MODE 0 sweep are taken with B r / A v_j (c->gs_dotvec) instead of r itself
+  const T* wv = (MODE == 0 && c->gs_dotvec != nullptr) ? (const T*)c->gs_dotvec : r;
   const bool fused = c->world == 1 || c->devcomm != nullptr;  // decide inside the sweep kernel
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->prof) {
@@ -242,7 +244,7 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
     c->prof_used += 2;
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
-  k_gs<T, MODE, SEG><<<grid, C::THREADS, smem, c->stream>>>(V, c->vs.ld, j, r, r, ntiles, c->ctl, c->partial, nstages,
+  k_gs<T, MODE, SEG><<<grid, C::THREADS, smem, c->stream>>>(V, c->vs.ld, j, wv, r, ntiles, c->ctl, c->partial, nstages,
                                                            gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
                                                            c->world > 1 ? c->devcomm : nullptr, c->trace,
                                                            (int)(c->gs_flip++ & 1));

@@ -358,6 +358,8 @@ static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool 
   return 0;
 }
 
+int launch_spmv_mat(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) { return spmv_launch(c, M, x, y, gated); }
+
 // ---------------------------------------------------------------------------------------------
 // Sharded normal operator OP = T^H T: after z = T_loc^H (T_loc x) every rank owns a full-length
 // partial result in its [own | halo] layout; the halo segment "owned by rank q" is rank q's share.
@@ -463,6 +465,7 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
     if (rc) return rc;
   }
   if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated, fused);
+  if (c->op_kind == 3) return general_opx(c, xin, y, nullptr);
   if (c->normal_dist) return launch_normal_dist(c, xin, y, gated, fused);
   // normal operator (single GPU): left: y = A^H (A x); right: y = A (A^H x)
   if (c->normal_left) {

@@ -38,6 +38,7 @@ enum {
   GA_ERR_NOOP = -102,      /* no operator uploaded */
   GA_ERR_COMM = -103,      /* collective layer failure */
   GA_ERR_NUMERIC = -104,   /* non-finite value met on the device */
+  GA_ERR_SOLVE = -105,     /* generalised problem: the solve with B failed (B not positive definite / no convergence) */
   GA_ERR_TRIDIAG = -8      /* dsaupd's code for a failed tridiagonal eigen-solve */
 };
 
@@ -109,6 +110,27 @@ int ga_set_normal_csr(ga_ctx* ctx, int64_t m, int64_t n, const int64_t* rowptr, 
 int ga_set_normal_csr_dist(ga_ctx* ctx, int64_t mt_local, const int64_t* rowptr, const int32_t* col_local,
                            const void* val, int32_t nhalo, const int32_t* recv_counts,
                            const int32_t* send_counts, const int32_t* send_idx, const int32_t* send_dest_off);
+/* Generalised symmetric problem A x = lambda B x in ARPACK's "regular inverse" mode 2 with bmat = :G:
+ * the reference's ArpackSymmetricGeneralizedOp(A, S, B) (src/idonow_ops.jl:462-492), reached by
+ * eigs(Symmetric(A), Symmetric(B), k) (src/interface.jl:143-163).  A and B are n x n full (both triangles)
+ * CSR matrices, B Hermitian positive definite.  OP = inv(B) A; the Krylov basis is B-orthonormal and every
+ * norm of dgetv0!/dsaitr!/dsaup2! becomes sqrt(|x' B x|) (src/dsaitr.jl:1195-1204,1298-1300,1405-1407,
+ * src/dgetv0.jl:625-627,696-698, src/dsaup2.jl:1383-1411).  The reference's S is any factorisation object the
+ * caller brings; here the solve with B is a Jacobi-preconditioned conjugate-gradient iteration on the device
+ * (relative residual cg_tol, NULL -> 8 eps of the real type; at most cg_maxit iterations, 0 -> 1000), or the
+ * caller's own solver on device pointers via ga_set_solve_callback.  Single GPU.  After this call
+ * ga_getv0 / ga_lanczos / ga_apply_shifts / ga_symeigs* run mode 2; ga_opx applies inv(B) A. */
+int ga_set_generalized_csr(ga_ctx* ctx, const int64_t* a_rowptr, const int32_t* a_col, const void* a_val,
+                           const int64_t* b_rowptr, const int32_t* b_col, const void* b_val,
+                           const double* cg_tol, int cg_maxit);
+/* The S of ArpackSymmetricGeneralizedOp(A, S, B) as a callback: x_dev <- inv(B) rhs_dev, both device vectors of
+ * n elements, work enqueued on `cuda_stream` (a cudaStream_t); return 0 on success.  NULL restores the built-in CG. */
+typedef int (*ga_solve_fn)(void* user, const void* rhs_dev, void* x_dev, int64_t n, void* cuda_stream);
+int ga_set_solve_callback(ga_ctx* ctx, ga_solve_fn fn, void* user);
+/* y = B x on host vectors (bx!, src/idonow_ops.jl:490-492). */
+int ga_bx(ga_ctx* ctx, const void* x_host, void* y_host);
+/* solves with B so far, CG iterations they took, and the largest final relative residual */
+int ga_get_solve_stats(const ga_ctx* ctx, int64_t* solves, int64_t* iterations, double* max_relres);
 /* y = OP*x on host vectors of the problem size (test / svds post-processing helper). */
 int ga_opx(ga_ctx* ctx, const void* x_host, void* y_host);
 

@@ -42,6 +42,7 @@ using cplx = std::complex<double>;
 
 // ------------------------------------------------------------------ scalar helpers
 static inline double abs(double x) { return std::fabs(x); }
+static inline double abs(std::complex<double> x) { return std::abs(x); }
 static inline double sqrt(double x) { return std::sqrt(x); }
 static inline bool isnan(double x) { return std::isnan(x); }
 static inline double copysign(double x, double y) { return std::copysign(x, y); }
@@ -626,10 +627,15 @@ static int dseigt(TR rnorm, int n, const TR* H, int ldh, TR* eig, TR* bounds, TR
 
 // ------------------------------------------------------------------ operators
 template <class T>
-struct Op {  // src/idonow_ops.jl:50-88 : size, opx!
+struct Op {  // src/idonow_ops.jl:50-88 : size, arpack_mode, bmat, opx!, genopx!, bx!
   i64 n = 0;
+  int mode = 1;          // arpack_mode(op)
+  bool bmat_g = false;   // bmat(op) == Val(:G)
   virtual ~Op() {}
   virtual void opx(T* y, const T* x) = 0;
+  // mode 2 (src/idonow_ops.jl:471-487): y = inv(B) A x AND x <- A x (ARPACK remark 5)
+  virtual void genopx(T* y, T* x) { opx(y, x); }
+  virtual void bx(T* y, const T* x) { for (i64 i = 0; i < n; ++i) y[i] = x[i]; }
 };
 template <class T>
 struct CsrOp : Op<T> {  // ArpackSimpleOp over a (full, both triangles) CSR matrix
@@ -673,6 +679,90 @@ struct NormalOp : Op<T> {
     else { Ahx(extra.data(), x); Ax(y, extra.data()); }
   }
 };
+
+// ArpackSymmetricGeneralizedOp(A, S, B) (src/idonow_ops.jl:462-492): mode 2, bmat = :G.  A and B are
+// full (both triangles) CSR matrices, B Hermitian positive definite.  The reference's S is whatever
+// factorisation the caller passes (factorize(B): LDLt / Cholesky / LU, outside /root/reference); it is
+// restated here as a banded Cholesky B = L L^H (band = the bandwidth of B's pattern).
+template <class T>
+struct GeneralizedOp : Op<T> {
+  using TR = typename vt<T>::real_t;
+  const i64* arp; const int* acol; const T* aval;
+  const i64* brp; const int* bcol; const T* bval;
+  i64 kd = 0;            // half bandwidth of B
+  std::vector<T> L;      // L(i, j) for i - kd <= j <= i at L[i * (kd + 1) + (i - j)]
+  bool spd = true;
+  GeneralizedOp(i64 n_, const i64* arp_, const int* acol_, const T* aval_, const i64* brp_, const int* bcol_,
+                const T* bval_) : arp(arp_), acol(acol_), aval(aval_), brp(brp_), bcol(bcol_), bval(bval_) {
+    this->n = n_; this->mode = 2; this->bmat_g = true;
+    const i64 n = n_;
+    for (i64 i = 0; i < n; ++i)
+      for (i64 k = brp[i]; k < brp[i + 1]; ++k) kd = std::max<i64>(kd, i - (i64)bcol[k]);
+    const i64 w = kd + 1;
+    L.assign((size_t)n * w, T(0.0));
+    for (i64 i = 0; i < n; ++i)
+      for (i64 k = brp[i]; k < brp[i + 1]; ++k)
+        if (bcol[k] <= i) L[(size_t)i * w + (i - bcol[k])] = bval[k];      // lower triangle of B
+    for (i64 j = 0; j < n; ++j) {                                           // column-by-column Cholesky
+      const i64 iend = std::min(n - 1, j + kd);
+      for (i64 i = j; i <= iend; ++i) {
+        T sum = L[(size_t)i * w + (i - j)];
+        for (i64 k = std::max<i64>(0, i - kd); k < j; ++k) {
+          if (j - k > kd) continue;
+          sum -= L[(size_t)i * w + (i - k)] * vt<T>::conj(L[(size_t)j * w + (j - k)]);
+        }
+        if (i == j) {
+          const TR d = vt<T>::re(sum);
+          if (!(d > TR(0.0))) { spd = false; L[(size_t)j * w] = T(1.0); }
+          else L[(size_t)j * w] = T(sqrt(d));
+        } else {
+          L[(size_t)i * w + (i - j)] = sum / L[(size_t)j * w];
+        }
+      }
+    }
+  }
+  static void spmv(i64 n, const i64* rp, const int* col, const T* val, T* y, const T* x) {
+#pragma omp parallel for schedule(static) if (n > 20000)
+    for (i64 i = 0; i < n; ++i) {
+      T s = T(0.0);
+      for (i64 k = rp[i]; k < rp[i + 1]; ++k) s += val[k] * x[col[k]];
+      y[i] = s;
+    }
+  }
+  void solve(T* y) const {  // y <- inv(B) y
+    const i64 n = this->n, w = kd + 1;
+    for (i64 i = 0; i < n; ++i) {                                           // L z = y
+      T sum = y[i];
+      for (i64 k = std::max<i64>(0, i - kd); k < i; ++k) sum -= L[(size_t)i * w + (i - k)] * y[k];
+      y[i] = sum / L[(size_t)i * w];
+    }
+    for (i64 i = n - 1; i >= 0; --i) {                                      // L^H x = z
+      T sum = y[i];
+      const i64 kend = std::min(n - 1, i + kd);
+      for (i64 k = i + 1; k <= kend; ++k) sum -= vt<T>::conj(L[(size_t)k * w + (k - i)]) * y[k];
+      y[i] = sum / L[(size_t)i * w];
+    }
+  }
+  void genopx(T* y, T* x) override {                                        // :471-487
+    spmv(this->n, arp, acol, aval, y, x);
+    for (i64 i = 0; i < this->n; ++i) x[i] = y[i];
+    solve(y);
+  }
+  void opx(T* y, const T* x) override {                                     // :488 (opx! = genopx!; x kept here)
+    spmv(this->n, arp, acol, aval, y, x);
+    solve(y);
+  }
+  void bx(T* y, const T* x) override { spmv(this->n, brp, bcol, bval, y, x); }  // :490-492
+};
+
+// dot(a, b) = sum conj(a_i) b_i (LinearAlgebra.dot -> BLAS ddot / zdotc, plain accumulation; the B-norms of
+// bmat = :G are sqrt(abs(dot(r, B r))), src/dsaitr.jl:1195-1204)
+template <class T>
+static typename vt<T>::real_t bnorm_from_dot(const T* a, const T* b, i64 n) {
+  T s = T(0.0);
+  for (i64 i = 0; i < n; ++i) s += vt<T>::conj(a[i]) * b[i];
+  return sqrt(typename vt<T>::real_t(abs(s)));
+}
 
 // ------------------------------------------------------------------ tall-skinny BLAS2
 // The reference calls LinearAlgebra.mul! -> OpenBLAS dgemv/zgemv (Float64/ComplexF64) or
@@ -755,26 +845,45 @@ struct Problem {
   }
 };
 
-// ------------------------------------------------------------------ dgetv0  (bmat = :I)
+// ------------------------------------------------------------------ dgetv0  (bmat = :I and :G)
 // src/dgetv0.jl:504-753, idonow flow.  j is the 1-based column being generated.
 template <class T>
 static int dgetv0(Problem<T>& P, int itry, bool initv, int j) {
   using TR = typename vt<T>::real_t;
   (void)itry;
   const i64 n = P.n;
+  const bool G = P.op->bmat_g;
   double t0 = now_s();
   T* resid = P.resid.data(); T* workd = P.workd.data(); const T* V = P.V.data();
   int ierr = 0, iter = 0;
   if (!initv) dlarnv_idist_2<T>(P.iseed, n, resid);                 // :551-553
-  vcopy(workd, resid, n);                                           // :612
-  TR rnorm0 = norm2(resid, n);                                      // :630
+  TR rnorm0;
+  if (G) {
+    P.stats.nopx++;                                                 // :566-576: force the vector into the range of OP
+    vcopy(workd, resid, n);
+    P.op->genopx(workd + n, workd);
+    P.stats.nbx++;                                                  // :596-606
+    vcopy(resid, workd + n, n);
+    P.op->bx(workd, workd + n);
+    rnorm0 = bnorm_from_dot<T>(resid, workd, n);                    // :625-627
+  } else {
+    vcopy(workd, resid, n);                                         // :612
+    rnorm0 = norm2(resid, n);                                       // :630
+  }
   P.rnorm = rnorm0;
   if (j == 1) { P.stats.tgetv0 += now_s() - t0; return 0; }         // :633-637
   while (true) {
     gemv_adj<T>(n, j - 1, V, n, workd, workd + n);                  // :662
     gemv_sub<T>(n, j - 1, V, n, workd + n, resid);                  // :665
-    vcopy(workd, resid, n);                                         // :681
-    P.rnorm = norm2(resid, n);                                      // :700
+    if (G) {
+      P.stats.nbx++;                                                // :669-679
+      vcopy(workd + n, resid, n);
+      P.op->bx(workd, workd + n);
+      P.rnorm = bnorm_from_dot<T>(resid, workd, n);                 // :696-698
+    } else {
+      vcopy(workd, resid, n);                                       // :681
+      P.rnorm = norm2(resid, n);                                    // :700
+    }
     if (P.rnorm > TR(0.717) * rnorm0) break;                        // :711
     iter += 1;
     if (iter <= 5) { rnorm0 = P.rnorm; }                            // :716-720
@@ -789,7 +898,7 @@ static int dgetv0(Problem<T>& P, int itry, bool initv, int j) {
   return ierr;
 }
 
-// ------------------------------------------------------------------ dsaitr  (mode 1, bmat = :I)
+// ------------------------------------------------------------------ dsaitr  (mode 1 bmat = :I; mode 2 bmat = :G)
 // src/dsaitr.jl:962-1535, idonow flow.  H is ldh x 2.  Returns info (0 or invariant-subspace size).
 template <class T>
 static int dsaitr(Problem<T>& P, int k, int np, typename vt<T>::real_t* H, int ldh) {
@@ -802,6 +911,7 @@ static int dsaitr(Problem<T>& P, int k, int np, typename vt<T>::real_t* H, int l
   T* wr = P.workd.data() + n;      // irj
   T* wv = P.workd.data() + 2 * n;  // ivj
   int info = 0;
+  const bool G = P.op->bmat_g;     // only with mode 2 (dsaupd rejects the other combinations)
   for (int j = k + 1; j <= k + np; ++j) {  // 1-based j as in the reference
     bool rstart = false;
     if (P.rnorm <= TR(0.0)) {                                        // :1061-1087, :1497-1525
@@ -833,18 +943,32 @@ static int dsaitr(Problem<T>& P, int k, int np, typename vt<T>::real_t* H, int l
     P.stats.nopx++;                                                  // :1113
     vcopy(wv, vj, n);                                                // :1115
     double t2 = now_s();
-    P.op->opx(wr, wv);                                               // :1126
+    if (G) P.op->genopx(wr, wv);                                     // :1128 (mode 2: wv <- A v_j)
+    else P.op->opx(wr, wv);                                          // :1126
     P.stats.tmvopx += now_s() - t2;
     vcopy(resid, wr, n);                                             // :1142
-    vcopy(wp, resid, n);                                             // :1173
-    TR wnorm = norm2(resid, n);                                      // :1208
-    gemv_adj<T>(n, j, V, n, wp, wr);                                 // :1227
+    TR wnorm;
+    if (G) {
+      wnorm = bnorm_from_dot<T>(resid, wv, n);                       // :1195-1200: inv(B)-norm of A v_j
+      gemv_adj<T>(n, j, V, n, wv, wr);                               // :1232
+    } else {
+      vcopy(wp, resid, n);                                           // :1173
+      wnorm = norm2(resid, n);                                       // :1208
+      gemv_adj<T>(n, j, V, n, wp, wr);                               // :1227
+    }
     gemv_sub<T>(n, j, V, n, wr, resid);                              // :1240
     H[(j - 1) + ldh] = vt<T>::re(wr[j - 1]);                         // :1243
     if (j == 1 || rstart) H[j - 1] = TR(0.0); else H[j - 1] = P.rnorm;  // :1259-1263
     double t4 = now_s();
-    vcopy(wp, resid, n);                                             // :1284
-    P.rnorm = norm2(resid, n);                                       // :1304
+    if (G) {
+      P.stats.nbx++;                                                 // :1272-1282
+      vcopy(wr, resid, n);
+      P.op->bx(wp, wr);
+      P.rnorm = bnorm_from_dot<T>(resid, wp, n);                     // :1298-1300
+    } else {
+      vcopy(wp, resid, n);                                           // :1284
+      P.rnorm = norm2(resid, n);                                     // :1304
+    }
     if (!(P.rnorm > TR(0.717) * wnorm)) {                            // :1324
       int iter = 0;
       P.stats.nrorth++;                                              // :1335 (net of :1439)
@@ -853,8 +977,16 @@ static int dsaitr(Problem<T>& P, int k, int np, typename vt<T>::real_t* H, int l
         gemv_sub<T>(n, j, V, n, wr, resid);                          // :1363
         if (j == 1 || rstart) H[j - 1] = TR(0.0);                    // :1364-1366
         H[(j - 1) + ldh] = H[(j - 1) + ldh] + vt<T>::re(wr[j - 1]);  // :1367
-        vcopy(wp, resid, n);                                         // :1386
-        TR rnorm1 = norm2(resid, n);                                 // :1410
+        TR rnorm1;
+        if (G) {
+          P.stats.nbx++;                                             // :1373-1384
+          vcopy(wr, resid, n);
+          P.op->bx(wp, wr);
+          rnorm1 = bnorm_from_dot<T>(resid, wp, n);                  // :1405-1407
+        } else {
+          vcopy(wp, resid, n);                                       // :1386
+          rnorm1 = norm2(resid, n);                                  // :1410
+        }
         if (rnorm1 > TR(0.717) * P.rnorm) { P.rnorm = rnorm1; break; }  // :1424-1426
         P.stats.nitref++;                                            // :1430
         P.rnorm = rnorm1;
@@ -1044,8 +1176,15 @@ static int dsaup2(Problem<T>& P, Which which, int& nev, int& np, typename vt<T>:
       if (nevbef < nev) dsgets<TR>(ishift, which, nev, np, ritz, bounds, workl);
     }
     dsapps<T>(P, nev, np, ritz, H, ldh, Q, ldq);                         // :1374
-    vcopy(P.workd.data(), P.resid.data(), n);                            // :1397
-    P.rnorm = norm2(P.resid.data(), n);                                  // :1414
+    if (P.op->bmat_g) {
+      P.stats.nbx++;                                                     // :1383-1394
+      vcopy(P.workd.data() + n, P.resid.data(), n);
+      P.op->bx(P.workd.data(), P.workd.data() + n);
+      P.rnorm = bnorm_from_dot<T>(P.resid.data(), P.workd.data(), n);    // :1409-1411
+    } else {
+      vcopy(P.workd.data(), P.resid.data(), n);                          // :1397
+      P.rnorm = norm2(P.resid.data(), n);                                // :1414
+    }
   }
 done:
   if (ok) { mxiter = iter; nev = nconv; }                                // :1455-1458
@@ -1074,7 +1213,8 @@ static int dsaupd(Problem<T>& P, Which which, int nev, typename vt<T>::real_t to
   if (mode < 1 || mode > 5) ierr = -10;
   else if (ishift < 0 || ishift > 1) ierr = -12;
   else if (nev == 1 && which == BE) ierr = -13;
-  if (mode != 1) ierr = ierr ? ierr : -10;  // oracle restates mode 1 only
+  else if (mode == 1 && P.op->bmat_g) ierr = -11;                        // :990-991
+  if (mode > 2 || (mode == 2) != P.op->bmat_g) ierr = ierr ? ierr : -10; // oracle restates modes 1 (:I) and 2 (:G)
   if (ierr != 0) return ierr;
   if (tol <= TR(0.0)) tol = rt<TR>::eps() / TR(2.0);                     // :1009-1011
   const int ldh = ncv, ldq = ncv;
@@ -1289,10 +1429,10 @@ static EigsResult<T> symeigs(Problem<T>& P, int nev, Which which, int maxiter, t
                              const T* v0, bool ritzvec) {
   using TR = typename vt<T>::real_t;
   EigsResult<T> R;
-  P.iparam[0] = 1; P.iparam[3] = 1; P.iparam[2] = maxiter; P.iparam[6] = 1;  // :253-256
+  P.iparam[0] = 1; P.iparam[3] = 1; P.iparam[2] = maxiter; P.iparam[6] = P.op->mode;  // :253-256
   bool initv = false;
   if (v0) { vcopy(P.resid.data(), v0, P.n); initv = true; }              // :259-262
-  R.info = dsaupd<T>(P, which, nev, tol, 1, initv);                      // :265
+  R.info = dsaupd<T>(P, which, nev, tol, P.op->mode, initv);             // :265
   R.niter = (int)P.iparam[2];
   R.nconv = (int)P.iparam[4];
   if (R.info != 0 && R.info != 1) return R;                              // :269-273 (caller raises)

@@ -37,6 +37,9 @@ def lib():
         vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double
         L.oracle_create.restype = vp
         L.oracle_create.argtypes = [i32, i64, i32, vp, vp, vp, i64, i64]
+        L.oracle_create_general.restype = vp
+        L.oracle_create_general.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp, vp]
+        L.oracle_bx.argtypes = [vp, vp, vp]
         L.oracle_destroy.argtypes = [vp]
         L.oracle_size.restype = i64
         L.oracle_size.argtypes = [vp]
@@ -200,15 +203,17 @@ def dd_op(op, a, b=(0.0, 0.0)):
 class Oracle:
     """One problem instance: operator + the work arrays symeigs would allocate
     (src/interface.jl:245-251).  A is a scipy.sparse matrix (any format); it is stored as
-    full CSR with int64 rowptr / int32 col.  normal=True builds ArpackNormalOp."""
+    full CSR with int64 rowptr / int32 col.  normal=True builds ArpackNormalOp; B != None builds
+    ArpackSymmetricGeneralizedOp(A, factorize(B), B) (mode 2, bmat = :G; B positive definite); b_val
+    optionally gives B's stored entries in the element layout (Double64 (hi, lo) pairs that are not doubles)."""
 
-    def __init__(self, A, ncv, dtype=None, normal=False):
+    def __init__(self, A, ncv, dtype=None, normal=False, B=None, b_val=None):
         import scipy.sparse as sp
 
         A = sp.csr_matrix(A)
         A.sort_indices()
         if dtype is None:
-            dtype = C64 if np.iscomplexobj(A.data) else F64
+            dtype = C64 if (np.iscomplexobj(A.data) or (B is not None and np.iscomplexobj(sp.csr_matrix(B).data))) else F64
         self.dtype = dtype
         self.ncv = ncv
         self.rowptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
@@ -216,7 +221,17 @@ class Oracle:
         self.val = to_dtype(A.data, dtype)
         m, n = A.shape
         L = lib()
-        if normal:
+        if B is not None:
+            assert m == n and not normal
+            B = sp.csr_matrix(B)
+            B.sort_indices()
+            assert B.shape == (n, n)
+            self.b_rowptr = np.ascontiguousarray(B.indptr, dtype=np.int64)
+            self.b_col = np.ascontiguousarray(B.indices, dtype=np.int32)
+            self.b_val = to_dtype(B.data if b_val is None else b_val, dtype)
+            self.h = L.oracle_create_general(dtype, n, ncv, _p(self.rowptr), _p(self.col), _p(self.val),
+                                             _p(self.b_rowptr), _p(self.b_col), _p(self.b_val))
+        elif normal:
             self.h = L.oracle_create(dtype, 0, ncv, _p(self.rowptr), _p(self.col), _p(self.val), m, n)
         else:
             assert m == n
@@ -294,6 +309,12 @@ class Oracle:
         x = to_dtype(x, self.dtype)
         y = np.zeros_like(x)
         lib().oracle_opx(self.h, _p(y), _p(x))
+        return y
+
+    def bx(self, x):
+        x = to_dtype(x, self.dtype)
+        y = np.zeros_like(x)
+        lib().oracle_bx(self.h, _p(y), _p(x))
         return y
 
     def dgetv0(self, itry=1, initv=False, j=1):

@@ -58,7 +58,33 @@ void* oracle_create(int dtype, long long n, int ncv, const long long* rowptr, co
   }
   return nullptr;
 }
+// ArpackSymmetricGeneralizedOp(A, factorize(B), B): mode 2, bmat = :G; A, B n x n full CSR, B positive definite.
+// Returns NULL if B is not positive definite.
+void* oracle_create_general(int dtype, long long n, int ncv, const long long* arp, const int* acol, const void* aval,
+                            const long long* brp, const int* bcol, const void* bval) {
+  try {
+    switch (dtype) {
+#define MK(CODE, TT)                                                                                         \
+  case CODE: {                                                                                               \
+    auto* op = new GeneralizedOp<TT>(n, arp, acol, (const TT*)aval, brp, bcol, (const TT*)bval);             \
+    if (!op->spd) { delete op; return nullptr; }                                                             \
+    auto* h = new Handle<TT>();                                                                              \
+    h->dtype = CODE;                                                                                         \
+    h->op = op;                                                                                              \
+    h->P = new Problem<TT>(n, ncv, h->op);                                                                   \
+    return h;                                                                                                \
+  }
+      MK(0, double)
+      MK(1, cplx)
+      MK(2, dd)
+#undef MK
+    }
+  } catch (...) {
+  }
+  return nullptr;
+}
 void oracle_destroy(void* h) { delete (HandleBase*)h; }
+void oracle_bx(void* h, void* y, const void* x) { DISPATCH(h, H_->op->bx((T*)y, (const T*)x)); }
 
 long long oracle_size(void* h) { long long r = 0; DISPATCH(h, r = H_->P->n); return r; }
 // what: 0 V, 1 resid, 2 workd, 3 workl
@@ -131,9 +157,9 @@ int oracle_dsaupd(void* h, int which, int nev, const double* tol, int maxiter, i
     DISPATCH(h, {
       using TR = typename vt<T>::real_t;
       Problem<T>& P = *H_->P;
-      P.iparam[0] = 1; P.iparam[3] = 1; P.iparam[2] = maxiter; P.iparam[6] = 1;
+      P.iparam[0] = 1; P.iparam[3] = 1; P.iparam[2] = maxiter; P.iparam[6] = P.op->mode;
       TR t = make_real<TR>(tol);
-      r = dsaupd<T>(P, (Which)which, nev, t, 1, initv != 0);
+      r = dsaupd<T>(P, (Which)which, nev, t, P.op->mode, initv != 0);
     });
   } catch (const std::exception& e) {
     fprintf(stderr, "oracle_dsaupd: %s\n", e.what());

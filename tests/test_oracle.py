@@ -325,3 +325,98 @@ def test_vs_scipy_arpack(O, syn):
     assert np.allclose(np.sort(w), r["values"], rtol=1e-12)
     assert np.allclose(r["values"], syn.laplacian2d_eigs(m, 10), rtol=1e-12)
     assert abs(r["stats"]["nopx"] - cnt[0]) <= 0.15 * cnt[0]
+
+
+# ---------------------------------------------------------------- generalised problem: mode 2, bmat = :G
+DSDRV3_GOLDEN = [121003.49732902342, 121616.60247324049, 122057.49457079473, 122323.22366457577]
+
+
+def _dsdrv3(n):
+    """arpack_dsdrv3 (test/utility.jl:268-272): 1-D FEM Laplacian, stiffness A and mass matrix B."""
+    A = (sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
+    B = (sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]) * (1.0 / (6 * (n + 1)))).tocsr()
+    return A, B
+
+
+def test_generalized_dsdrv3_golden(O):
+    """test/interface_high.jl:45,72,102: eigs(Symmetric(A), Symmetric(B), 4) on dsdrv3, n = 100, gives
+    [121003.49732902342, 121616.60247324049, 122057.49457079473, 122323.22366457577]."""
+    A, B = _dsdrv3(100)
+    o = O.Oracle(A, 20, B=B)
+    r = o.symeigs(4)
+    assert r["info"] == 0 and r["ierr"] == 0 and r["nconv"] == 4
+    assert np.allclose(r["values"], DSDRV3_GOLDEN, rtol=1e-13, atol=0)
+    assert int(o.iparam[6]) == 2                                     # mode
+    st = r["stats"]
+    assert st["nbx"] > st["nopx"] > 0                                # every B-norm costs one B*x
+    Z = r["vectors"]
+    assert np.allclose(Z.T @ (B @ Z), np.eye(4), atol=1e-12)         # B-orthonormal Ritz vectors
+    for i in range(4):
+        assert np.linalg.norm(A @ Z[:, i] - r["values"][i] * (B @ Z[:, i])) <= 1e-9 * np.linalg.norm(A @ Z[:, i])
+
+
+@pytest.mark.parametrize("which,maxiter", [("LM", 300), ("SA", 400)])
+def test_generalized_vs_dense(O, which, maxiter):
+    """test/dsaupd_idonow.jl:17-110: n = 100, ncv = 10, nev = 4, mode 2 / bmat :G against eigvals(B \\ A)."""
+    import scipy.linalg as sl
+
+    A, B = _dsdrv3(100)
+    w = sl.eigh(A.toarray(), B.toarray(), eigvals_only=True)
+    r = O.Oracle(A, 10, B=B).symeigs(4, which=which, maxiter=maxiter)
+    ref = np.sort(w)[-4:] if which == "LM" else np.sort(w)[:4]
+    assert r["info"] == 0
+    assert np.allclose(np.sort(r["values"]), ref, rtol=1e-10, atol=0)
+
+
+def test_generalized_double64(O):
+    """dsdrv3 in Double64 (test/interface_high.jl:69-73) against the analytic pencil eigenvalues
+    6 (n+1)^2 (2 - 2 cos t) / (4 + 2 cos t), t = k pi / (n+1), to 1e-26 relative."""
+    import mpmath as mp
+
+    mp.mp.prec = 250
+    n = 100
+    A, B = _dsdrv3(n)
+    # B's entries 1/(6(n+1)) are not doubles: build the Double64 matrix from exact (hi, lo) pairs
+    def dd(x):
+        hi = float(x)
+        return hi, float(x - mp.mpf(hi))
+    h = mp.mpf(1) / (6 * (n + 1))
+    Bd = B.copy().astype(np.float64)
+    vals = np.zeros((B.nnz, 2))
+    for k in range(B.nnz):
+        vals[k] = dd(4 * h) if abs(B.data[k]) > 2.5 * float(h) else dd(h)
+    o = O.Oracle(A, 20, dtype=O.DD, B=Bd, b_val=vals)
+    r = o.symeigs(4)
+    assert r["info"] == 0 and r["ierr"] == 0
+    d = r["values"]
+    exact = [6 * (n + 1) ** 2 * (2 - 2 * mp.cos(k * mp.pi / (n + 1))) / (4 + 2 * mp.cos(k * mp.pi / (n + 1)))
+             for k in range(n - 3, n + 1)]
+    got = [mp.mpf(float(v[0])) + mp.mpf(float(v[1])) for v in d]
+    assert max(abs(g - e) / e for g, e in zip(got, exact)) < mp.mpf(10) ** -26
+
+
+def test_generalized_complex_hermitian(O):
+    """Hermitian A, Hermitian positive definite B (hermeigs(A, B, k), src/interface.jl:158-163) against
+    scipy.linalg.eigh(A, B)."""
+    import scipy.linalg as sl
+
+    rng = np.random.default_rng(3)
+    n = 60
+    ph = np.exp(1j * rng.uniform(0, 2 * np.pi, n - 1))
+    A = sp.diags([np.conj(ph), rng.uniform(1, 3, n), ph], [-1, 0, 1]).tocsr()
+    pb = 0.3 * np.exp(1j * rng.uniform(0, 2 * np.pi, n - 1))
+    B = sp.diags([np.conj(pb), rng.uniform(1.5, 2.5, n), pb], [-1, 0, 1]).tocsr()
+    w = sl.eigh(A.toarray(), B.toarray(), eigvals_only=True)
+    r = O.Oracle(A, 16, B=B).symeigs(4)
+    assert r["info"] == 0
+    ref = w[np.argsort(-np.abs(w))[:4]]
+    assert np.allclose(np.sort(r["values"]), np.sort(ref), rtol=1e-10, atol=0)
+    Z = r["vectors"]
+    assert np.allclose(Z.conj().T @ (B @ Z), np.eye(4), atol=1e-11)
+
+
+def test_generalized_rejects_indefinite_b(O):
+    A, B = _dsdrv3(20)
+    Bbad = B.tolil(); Bbad[3, 3] = -1.0
+    with pytest.raises(RuntimeError):
+        O.Oracle(A, 8, B=Bbad.tocsr())

@@ -30,15 +30,21 @@ def O():
     return entry.load_oracle()
 
 
-# the literal 15 x 15 matrix of /root/reference/test/interface_simple.jl:7 (CSC, 1-based)
-KAT15_COLPTR = [1, 9, 16, 22, 27, 33, 38, 47, 51, 58, 62, 71, 78, 85, 89, 95]
-KAT15_ROWVAL = [2, 3, 4, 7, 8, 9, 11, 15, 1, 3, 5, 7, 11, 12, 14, 1, 2, 4, 5, 6, 9, 1, 3, 4, 6, 13, 2, 3, 6, 7, 12, 15, 3, 4, 5, 10, 13, 1, 2, 5, 8, 9, 10, 11, 12, 13, 1, 7, 9, 11, 1, 3, 7, 8, 13, 14, 15, 6, 7, 11, 15, 1, 2, 7, 8, 10, 12, 13, 14, 15, 2, 5, 7, 11, 12, 13, 14, 4, 6, 7, 9, 11, 12, 15, 2, 9, 11, 12, 1, 5, 9, 10, 11, 13]
-KAT15_NZVAL = [1.0619322548149914, 0.8766879002200858, -0.9064189303728223, 0.21600317366983124, -1.283210593569618, 0.94558609230275, 1.9155428985937315, 0.9974159980590636, 1.0619322548149914, 0.07774792930492884, 0.2649798493656264, 0.6491820935668625, -0.6188565210918642, 0.33167352440104847, 0.06581708949429992, 0.8766879002200858, 0.07774792930492884, -0.831030685702723, -0.9593728263464558, -1.0783982816827704, 1.5537090724942313, -0.9064189303728223, -0.831030685702723, -2.73568483736268, -0.2601662488800133, -2.0138536457007397, 0.2649798493656264, -0.9593728263464558, 1.2063734934686803, -0.23345707234182503, -0.598980265258237, -3.235531538166721, -1.0783982816827704, -0.2601662488800133, 1.2063734934686803, -1.2968161204379096, -0.5037853135483386, 0.21600317366983124, 0.6491820935668625, -0.23345707234182503, -1.635181006451923, 1.2505504541996117, -1.8979584955867908, 0.8078340897940672, 0.3488529638883331, -0.8853907377562747, -1.283210593569618, -1.635181006451923, -1.0402874079575923, -0.023802716431538706, 0.94558609230275, 1.5537090724942313, 1.2505504541996117, -1.0402874079575923, -0.4150736664751938, -0.7608617919970803, -0.1985227463733881, -1.2968161204379096, -1.8979584955867908, 0.4120271156295672, -0.033303822949929375, 1.9155428985937315, -0.6188565210918642, 0.8078340897940672, -0.023802716431538706, 0.4120271156295672, -1.7060217210513384, 0.6923442199350044, 0.5061616454994609, 0.5200080839628756, 0.33167352440104847, -0.598980265258237, 0.3488529638883331, -1.7060217210513384, -0.4259291978517505, -0.7347260397652922, -0.45812838793146876, -2.0138536457007397, -0.5037853135483386, -0.8853907377562747, -0.4150736664751938, 0.6923442199350044, -0.7347260397652922, -0.28756151077851555, 0.06581708949429992, -0.7608617919970803, 0.5061616454994609, -0.45812838793146876, 0.9974159980590636, -3.235531538166721, -0.1985227463733881, -0.033303822949929375, 0.5200080839628756, -0.28756151077851555]
+# Golden vectors literal in the reference's own tests, committed as a fixture (tests/golden/reference_kats.json,
+# regenerated / audited from /root/reference/test/*.jl by tests/golden/make_golden.py).
+import json  # noqa: E402
 
-# golden start vector of /root/reference/test/dgetv0_simple.jl:6-15 (seed (1,3,5,7), n = 10)
-GOLDEN_V0 = [0.3957424639187579, 0.0008649603975001696, -0.9227205789982591, -0.9165671495278005,
-             0.1175963848841306, -0.2996262520371218, 0.9038269570258635, -0.25045104802183715,
-             0.33224741301423677, -0.29023922021963955]
+with open(os.path.join(ROOT, "tests", "golden", "reference_kats.json")) as _f:
+    GOLD = json.load(_f)
+
+# the literal 15 x 15 matrix of test/interface_simple.jl:7 (CSC, 1-based)
+KAT15_COLPTR = GOLD["kat15"]["colptr"]
+KAT15_ROWVAL = GOLD["kat15"]["rowval"]
+KAT15_NZVAL = GOLD["kat15"]["nzval"]
+# golden start vector of test/dgetv0_simple.jl:6-15 (seed (1,3,5,7), n = 10)
+GOLDEN_V0 = GOLD["dgetv0_start_vector"]["values"]
+# dsdrv3 generalised problem, n = 100 (test/interface_high.jl:45,72,102)
+DSDRV3_GOLDEN = GOLD["dsdrv3_generalized_n100"]["values"]
 
 
 def kat15():
@@ -46,3 +52,13 @@ def kat15():
     import scipy.sparse as sp
 
     return sp.csc_matrix((KAT15_NZVAL, np.array(KAT15_ROWVAL) - 1, np.array(KAT15_COLPTR) - 1), shape=(15, 15)).tocsr()
+
+
+def dsdrv3(n):
+    """arpack_dsdrv3 (test/utility.jl:268-272): 1-D FEM Laplacian, stiffness A and mass matrix B."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    A = (sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
+    B = (sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]) * (1.0 / (6 * (n + 1)))).tocsr()
+    return A, B

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from conftest import GOLDEN_V0, kat15
+from conftest import GOLD, GOLDEN_V0, kat15
 
 pytestmark = pytest.mark.gpu
 
@@ -524,10 +524,10 @@ def test_svds_golden_values(pkg):
 
     A = _mytestmat(10, 8)
     U, s, V = pkg.svds(A, 2, which="BE")
-    assert np.allclose(s, [0.20022491452411176, 2.424417285164735], rtol=1e-12)
+    assert np.allclose(s, GOLD["svds_mytestmat_10_8_BE"]["values"], rtol=1e-12)
     _check_svd(A, U, s, V, tol=75)
     U, s, V = pkg.svds(A.T.tocsr(), 2, which="BE")             # m <= n: the AA' side
-    assert np.allclose(s, [0.20022491452411176, 2.424417285164735], rtol=1e-12)
+    assert np.allclose(s, GOLD["svds_mytestmat_10_8_BE"]["values"], rtol=1e-12)
     _check_svd(A.T.tocsr(), U, s, V, tol=75)
     A1 = sp.csr_matrix(np.ones((5, 5)))
     U, s, V = pkg.svds(A1, 1)
@@ -535,10 +535,10 @@ def test_svds_golden_values(pkg):
     _check_svd(A1, U, s, V, tol=10)
     Ac = _mytestmat(10, 8, -3.0j)
     U, s, V = pkg.svds(Ac, 2, which="BE")
-    assert np.allclose(s, [0.9640220546797924, 6.0316491543925785], rtol=1e-12)
+    assert np.allclose(s, GOLD["complex_svds_BE"]["values"], rtol=1e-12)
     _check_svd(Ac, U, s, V, tol=60)
     U, s, V = pkg.svds(Ac, 2, which="LM")
-    assert np.allclose(s, [6.0316491543925785, 1.9374903374733126], rtol=1e-12)
+    assert np.allclose(s, GOLD["complex_svds_LM"]["values"], rtol=1e-12)
     _check_svd(Ac, U, s, V, tol=60)
     U, s, V = pkg.svds(A, 2, which="SA", ritzvec=False)
     assert U.shape[1] == 0 and V.shape[1] == 0 and len(s) == 2
@@ -557,7 +557,7 @@ def test_svds_arpack_example(pkg):
         A[: j + 1, j] = k * sv[: j + 1] * (t - 1)
         A[j + 1:, j] = k * t * (sv[j + 1:] - 1)
     U, s, V = pkg.svds(sp.csr_matrix(A), 4, ncv=10)
-    gold = sorted([4.1012320445852e-02, 6.0488061100249e-02, 1.1784357891005e-01, 5.5723400180223e-01], reverse=True)
+    gold = sorted(GOLD["svds_arpack_example_500x100"]["values"], reverse=True)
     assert np.allclose(s, gold, rtol=1e-10)
     _check_svd(A, U, s, V, tol=4)
 

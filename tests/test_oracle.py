@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from conftest import GOLDEN_V0, kat15
+from conftest import DSDRV3_GOLDEN, GOLD, GOLDEN_V0, dsdrv3 as _dsdrv3, kat15
 
 
 # ---------------------------------------------------------------- LCG / start vector (bit-exact)
@@ -18,6 +18,15 @@ def test_golden_start_vector(O):
     assert np.array_equal(o.resid, np.array(GOLDEN_V0))
     assert tuple(o.iseed) != (1, 3, 5, 7)
     assert o.rnorm == pytest.approx(np.linalg.norm(GOLDEN_V0), rel=1e-15)
+
+
+def test_golden_dlarnv_stream_fixture(O):
+    """tests/golden/reference_kats.json:dlarnv_stream (closed form pinned by the golden start vector): last three
+    values (bit patterns) and the seed left behind for n = 1, 10, 127, 128, 129, 4097."""
+    for case in GOLD["dlarnv_stream"]["cases"]:
+        x, seed = O.dlarnv(case["n"])
+        assert [float.hex(float(v)) for v in x[-3:]] == case["last3_hex"], case["n"]
+        assert list(seed) == case["seed_after"], case["n"]
 
 
 def test_lcg_table_rows(O):
@@ -328,16 +337,6 @@ def test_vs_scipy_arpack(O, syn):
 
 
 # ---------------------------------------------------------------- generalised problem: mode 2, bmat = :G
-DSDRV3_GOLDEN = [121003.49732902342, 121616.60247324049, 122057.49457079473, 122323.22366457577]
-
-
-def _dsdrv3(n):
-    """arpack_dsdrv3 (test/utility.jl:268-272): 1-D FEM Laplacian, stiffness A and mass matrix B."""
-    A = (sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]) * (n + 1)).tocsr()
-    B = (sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]) * (1.0 / (6 * (n + 1)))).tocsr()
-    return A, B
-
-
 def test_generalized_dsdrv3_golden(O):
     """test/interface_high.jl:45,72,102: eigs(Symmetric(A), Symmetric(B), 4) on dsdrv3, n = 100, gives
     [121003.49732902342, 121616.60247324049, 122057.49457079473, 122323.22366457577]."""

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+from conftest import GOLD
 from oracle import oracle_svd as OS
 
 EPS = np.finfo(np.float64).eps
@@ -49,7 +50,7 @@ def test_orth_is_positive_diagonal_qr():
 def test_golden_mytestmat_be():
     A = mytestmat(10, 8)
     U, s, V, _ = OS.svds(A, 2, which="BE")
-    assert np.allclose(s, [0.20022491452411176, 2.424417285164735], rtol=1e-12)     # test/interface_simple.jl:104
+    assert np.allclose(s, GOLD["svds_mytestmat_10_8_BE"]["values"], rtol=1e-12)     # test/interface_simple.jl:104
     check_svd(A, U, s, V, tol=75)
 
 
@@ -63,7 +64,7 @@ def test_golden_all_ones():
 def test_golden_arpack_svd_example():
     A = arpack_svd_example()
     U, s, V, _ = OS.svds(sp.csr_matrix(A), 4, ncv=10)
-    gold = sorted([4.1012320445852e-02, 6.0488061100249e-02, 1.1784357891005e-01, 5.5723400180223e-01], reverse=True)
+    gold = sorted(GOLD["svds_arpack_example_500x100"]["values"], reverse=True)
     assert np.allclose(s, gold, rtol=1e-10)                                           # :218-220
     check_svd(A, U, s, V, tol=3)
 
@@ -71,7 +72,7 @@ def test_golden_arpack_svd_example():
 def test_wide_matrix_right_side():
     A = mytestmat(10, 8).T.tocsr()          # m <= n: OP = A A', eigenvectors are U
     U, s, V, _ = OS.svds(A, 2, which="BE")
-    assert np.allclose(s, [0.20022491452411176, 2.424417285164735], rtol=1e-12)
+    assert np.allclose(s, GOLD["svds_mytestmat_10_8_BE"]["values"], rtol=1e-12)
     check_svd(A, U, s, V, tol=75)
 
 

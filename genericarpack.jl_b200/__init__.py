@@ -42,7 +42,7 @@ _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
-    "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid",
+    "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid", "ga_bnorm_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
@@ -117,6 +117,7 @@ def lib():
         L.ga_apply_shifts.argtypes = [vp, i32, i32, vp, i32, vp, vp]
         L.ga_ritz_vectors.argtypes = [vp, i32, vp, i32, vp, i64]
         L.ga_norm2_resid.argtypes = [vp, vp]
+        L.ga_bnorm_resid.argtypes = [vp, vp]
         L.ga_svd_vectors.argtypes = [vp, i32, vp, vp, i64, vp]
         L.ga_get_stats.argtypes = [vp, ctypes.POINTER(ga_stats)]
         L.ga_reset_stats.argtypes = [vp]
@@ -447,6 +448,12 @@ class Context:
         self._ck(lib().ga_norm2_resid(self.h, _p(out)))
         return self._real_out(out)
 
+    def bnorm_resid(self):
+        """The norm dsaup2! recomputes after a restart: 2-norm (bmat = :I) or sqrt|r' B r| (bmat = :G)."""
+        out = np.zeros(2)
+        self._ck(lib().ga_bnorm_resid(self.h, _p(out)))
+        return self._real_out(out)
+
     def stats(self):
         s = ga_stats()
         lib().ga_get_stats(self.h, ctypes.byref(s))
@@ -526,7 +533,7 @@ class Context:
     def symeigs_begin(self, nev, which="LM", tol=0.0, maxiter=300, v0=None):
         t = self._real(tol)
         v = None if v0 is None else to_elem(v0, self.dtype)
-        return lib().ga_symeigs_begin(self.h, _WHICH[which], int(nev), _p(t), int(maxiter), _p(v))
+        return lib().ga_symeigs_begin(self.h, _WHICH.get(str(which).lstrip(":"), -1), int(nev), _p(t), int(maxiter), _p(v))
 
     def symeigs_iterate(self, max_restarts=-1):
         return lib().ga_symeigs_iterate(self.h, int(max_restarts))

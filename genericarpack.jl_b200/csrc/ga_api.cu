@@ -691,6 +691,13 @@ int ga_norm2_resid(ga_ctx* c, double* out) {
   return 0;
 }
 
+int ga_bnorm_resid(ga_ctx* c, double* out) {
+  if (!c || !out) return GA_ERR_ARG;
+  if (c->op_kind != 3) return ga_norm2_resid(c, out);        // bmat = :I: the B-norm is the 2-norm
+  GA_CUDA(c, cudaSetDevice(c->device));
+  return general_resid_bnorm(c, out);
+}
+
 int ga_timer_start(ga_ctx* c) {
   if (!c) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));

@@ -253,12 +253,16 @@ int ga_symeigs_begin(ga_ctx* c, int which, int nev, const double* tol, int maxit
   if (!c) return GA_ERR_ARG;
   solve_free(c);
   // argument checks of dsaupd! (src/dsaupd.jl:963-1002)
-  if (c->n_global <= 0) return -1;
-  if (nev <= 0) return -2;
-  if (c->ncv <= nev || (i64)c->ncv > c->n_global) return -3;
-  if (maxiter < 0) return -4;
-  if (which < GA_LM || which > GA_BE) return -5;
-  if (nev == 1 && which == GA_BE) return -13;
+  // (like the reference, a later failing check overrides an earlier one; -6/-7/-10/-11/-12 cannot be
+  // reached through this ABI: bmat and mode come from the uploaded operator, workl is internal, ishift = 1)
+  int ierr = 0;
+  if (c->n_global <= 0) ierr = -1;
+  else if (nev <= 0) ierr = -2;
+  else if (c->ncv <= nev || (i64)c->ncv > c->n_global) ierr = -3;
+  if (maxiter < 0) ierr = -4;                      // < 0, not <= 0: mxiter = 0 still runs one iteration (:971-976)
+  if (which < GA_LM || which > GA_BE) ierr = -5;
+  if (nev == 1 && which == GA_BE) ierr = -13;
+  if (ierr != 0) return ierr;
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
   const double t0 = hnow();
   int rc;

@@ -185,6 +185,9 @@ int ga_svd_vectors(ga_ctx* ctx, int nvec, const int32_t* perm, void* w_host, int
 /* ---- small device services used by tests and by the Julia shim ---------------------------------
  * ga_norm2: norm2(TR, resid) (src/arpack-blas-nrm2.jl:355-372) of the device resid. */
 int ga_norm2_resid(ga_ctx* ctx, double* out);
+/* The norm dsaup2! recomputes after a restart (src/dsaup2.jl:1378-1414): norm2(resid) for bmat = :I,
+ * sqrt(|resid' B resid|) for bmat = :G (the reference's ido = 2 exchange + dot + sqrt(abs(.))). */
+int ga_bnorm_resid(ga_ctx* ctx, double* out);
 int ga_get_stats(const ga_ctx* ctx, ga_stats* out);
 int ga_reset_stats(ga_ctx* ctx);
 

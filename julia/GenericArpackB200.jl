@@ -180,4 +180,58 @@ function eigenvecs_to_singvecs!(U::AbstractMatrix{T}, V::AbstractMatrix{T}, op::
   return nothing
 end
 
+# ---- generalised problem A x = lambda B x, mode 2 / bmat = :G: the device counterpart of
+# ArpackSymmetricGeneralizedOp(A, S, B) (src/idonow_ops.jl:462-492), reached by eigs(Symmetric(A), Symmetric(B), k)
+# (src/interface.jl:143-163).  The factorisation object S of the reference becomes the library's device CG with B
+# (or the caller's own device solver through ga_set_solve_callback).
+mutable struct B200GeneralizedOp{T} <: ArpackOp
+  ctx::Ptr{Cvoid}; n::Int; ncv::Int
+end
+function B200GeneralizedOp(A::SparseMatrixCSC{T}, B::SparseMatrixCSC{T}, ncv::Int; device::Int=0,
+                           cg_tol::Union{Nothing,Float64}=nothing, cg_maxit::Int=0) where T
+  n = size(A, 1)
+  At = SparseMatrixCSC(transpose(A)); Bt = SparseMatrixCSC(transpose(B))        # CSR of A and of B
+  ctxref = Ref{Ptr{Cvoid}}(C_NULL)
+  rc = ccall((:ga_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Cint, Int64, Int64, Int64, Cint, Cint, Cint, Cint),
+             ctxref, ga_dtype(T), n, n, 0, ncv, device, 0, 1)
+  rc == 0 || error("ga_create failed ($rc)")
+  tol = cg_tol === nothing ? C_NULL : Ref(cg_tol)
+  rc = ccall((:ga_set_generalized_csr, lib), Cint,
+             (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Float64}, Cint),
+             ctxref[], Int64.(At.colptr .- 1), Int32.(At.rowval .- 1), At.nzval,
+             Int64.(Bt.colptr .- 1), Int32.(Bt.rowval .- 1), Bt.nzval, tol, cg_maxit)
+  rc == -105 && throw(ArgumentError("B is not positive definite"))               # GA_ERR_SOLVE
+  check(rc, ctxref[])
+  op = B200GeneralizedOp{T}(ctxref[], n, ncv)
+  finalizer(o -> ccall((:ga_destroy, lib), Cvoid, (Ptr{Cvoid},), o.ctx), op)
+  return op
+end
+Base.size(op::B200GeneralizedOp) = op.n
+arpack_mode(::B200GeneralizedOp) = 2
+bmat(::B200GeneralizedOp) = Val(:G)
+is_arpack_mode_valid_for_op(mode::Int, ::B200GeneralizedOp) = mode == 2
+GenericArpack.bx!(y, op::B200GeneralizedOp, x) =
+  (check(ccall((:ga_bx, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), op.ctx, x, y), op.ctx); y)
+opx!(y, op::B200GeneralizedOp, x) = (check(ccall((:ga_opx, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), op.ctx, x, y), op.ctx); y)
+# The B-norm branches (src/dsaitr.jl:1195-1204,1298-1300,1405-1407; src/dgetv0.jl:625-627,696-698) live inside the
+# library once ga_set_generalized_csr has been called, so the :G methods are the :I methods above with another Val:
+for f in (:dgetv0!, :dsaitr!)
+  @eval $f(ido::Ref{Int}, ::Val{:G}, args...; kw...) = $f(ido, Val(:I), args...; kw...)
+end
+# dsaup2!'s own :G touches outside the overridden routines (SURVEY.md 8b): the ido = 2 exchange that forms B*resid in
+# workd (src/dsaup2.jl:1383-1390, `_i_do_now_bx!`) and rnorm = sqrt(abs(dot(resid, workd))) (:1410-1411) collapse into one
+# library call, ga_bnorm_resid; simple_dseupd!'s bnorm2 = norm2(workd[1:n]) (src/dseupd.jl:1178-1180) only feeds the
+# mode 3-5 Ritz-vector purification and is not used for mode 2.
+GenericArpack._i_do_now_bx!(idonow, ipntr, workd::DeviceVector, n) = nothing
+function LinearAlgebra.dot(r::DeviceVector{T}, ::DeviceVector{T}) where T
+  out = Ref{real(T)}(zero(real(T)))
+  check(ccall((:ga_bnorm_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), r.ctx, out), r.ctx)
+  return out[] * out[]                                         # the caller applies sqrt(abs(.))
+end
+symeigs(::Type{TV}, ::Type{TF}, op::B200GeneralizedOp{TV}, nev::Integer; ncv::Int=op.ncv, kwargs...) where {TV,TF} = begin
+  state = B200ArpackState{TF}(ctx=op.ctx)
+  V = DeviceMatrix{TV}(op.ctx, op.n, ncv); resid = DeviceVector{TV}(op.ctx, op.n); workd = DeviceVector{TV}(op.ctx, 3op.n)
+  GenericArpack._symeigs_with_arrays(TV, TF, op, nev, V, resid, workd; ncv, state, kwargs...)
+end
+
 end # module

@@ -42,6 +42,7 @@ def test_generalized_lockstep_with_oracle(pkg, O):
     o.dgetv0(1, False, 1)
     assert rc == 0
     assert abs(rn - o.rnorm) <= 1e-12 * o.rnorm
+    assert abs(ctx.bnorm_resid() - rn) <= 1e-14 * rn          # sqrt|r' B r| recomputed (src/dsaup2.jl:1378-1411)
     r_gpu = np.asarray(ctx.download_resid())
     assert np.max(np.abs(r_gpu - o.resid)) <= 1e-12 * np.max(np.abs(o.resid))
     H = np.zeros((ncv, 2))

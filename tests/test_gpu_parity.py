@@ -649,3 +649,31 @@ def test_large_ncv_fallback(pkg, syn, O):
     assert np.allclose(Z.T @ Z, np.eye(20), atol=1e-12)
     with pytest.raises(Exception):
         pkg.eigs(A, 20, ncv=65)          # beyond GA_MAX_NCV: refused, never silently degraded
+
+
+def test_dsaupd_error_codes(pkg):
+    """test/dsaupd_errors.jl: the info codes of dsaupd!'s argument checks (src/dsaupd.jl:963-1002) and the zero
+    start vector (-9, src/dsaup2.jl:1071-1076), through the C ABI; the interface level wraps them in
+    ArpackException (src/interface.jl:269-273)."""
+    n = 10
+    A = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), n - 1)
+    assert ctx.symeigs_begin(6, v0=np.zeros(n)) == 0
+    assert ctx.symeigs_iterate(-1) == 99
+    assert ctx.symeigs_end(6)[0] == -9                      # "initial vector is zero"
+    assert ctx.symeigs_begin(0) == -2                       # "nev must be positive"
+    assert ctx.symeigs_begin(n - 1) == -3                   # ncv must be greater than nev
+    assert ctx.symeigs_begin(2, maxiter=-1) == -4
+    assert ctx.symeigs_begin(2, maxiter=0) == 0             # mxiter = 0 is allowed (one iteration)
+    assert ctx.symeigs_begin(2, which="SS") == -5
+    assert ctx.symeigs_begin(1, which="BE") == -13
+    assert ctx.symeigs_begin(0, which="SS") == -5           # a later check overrides an earlier one
+    ctx.close()
+    with pytest.raises(pkg.ArpackException):
+        pkg.eigs(A, 2, which="SS")
+    with pytest.raises(pkg.ArpackException):
+        pkg.eigs(A, 6, ncv=9, v0=np.zeros(n))
+    with pytest.raises(ValueError):                         # src/interface.jl:231-232
+        pkg.eigs(A, 4, ncv=11)
+    with pytest.raises(ValueError):
+        pkg.eigs(A, 4, ncv=4)

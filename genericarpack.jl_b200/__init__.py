@@ -25,17 +25,18 @@ import numpy as np
 
 __all__ = [
     "ArpackException", "ArpackSimpleOp", "ArpackNormalOp", "ArpackSymmetricGeneralizedOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
-    "Context", "comm_unique_id", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD",
+    "Context", "comm_unique_id", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD", "GA_F32",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libgarpack_b200.so")
 _LIB = None
 
-GA_F64, GA_C64, GA_DD = 0, 1, 2
+GA_F64, GA_C64, GA_DD, GA_F32 = 0, 1, 2, 3
 GA_ERR_CUDA, GA_ERR_ARG, GA_ERR_NOOP, GA_ERR_COMM, GA_ERR_NUMERIC, GA_ERR_SOLVE = -100, -101, -102, -103, -104, -105
 _DTYPES = {"f64": GA_F64, "float64": GA_F64, "c64": GA_C64, "complex128": GA_C64, "dd": GA_DD, "double64": GA_DD,
-           GA_F64: GA_F64, GA_C64: GA_C64, GA_DD: GA_DD}
+           "f32": GA_F32, "float32": GA_F32,   # Float32 vectors, Float64 factorisation: symeigs(Float32, Float64, ...)
+           GA_F64: GA_F64, GA_C64: GA_C64, GA_DD: GA_DD, GA_F32: GA_F32}
 _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 
 # every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
@@ -144,7 +145,7 @@ def _p(a):
 
 
 def _np_dtype(dt):
-    return np.complex128 if dt == GA_C64 else np.float64
+    return np.complex128 if dt == GA_C64 else (np.float32 if dt == GA_F32 else np.float64)
 
 
 def _eshape(dt):
@@ -210,7 +211,7 @@ class B200ArpackOp:
             self.col = np.ascontiguousarray(A.indices, dtype=np.int32)
             data = A.data
         if dtype is None:
-            dtype = GA_C64 if np.iscomplexobj(data) else GA_F64
+            dtype = GA_C64 if np.iscomplexobj(data) else (GA_F32 if np.asarray(data).dtype == np.float32 else GA_F64)
         self.dtype = _DTYPES[dtype]
         self.val = to_elem(data, self.dtype)
 
@@ -580,6 +581,18 @@ class ArpackEigen:
         return self.ctx.download_resid()
 
 
+def _type_arg(x):
+    """element type given like the reference's leading TV / TF arguments, or None if x is not a type"""
+    if isinstance(x, str):
+        return _DTYPES.get(x.lower())
+    if isinstance(x, (type, np.dtype)):
+        try:
+            return {np.dtype(np.float32): GA_F32, np.dtype(np.float64): GA_F64, np.dtype(np.complex128): GA_C64}.get(np.dtype(x))
+        except TypeError:
+            return None
+    return None
+
+
 def _as_op(A, dtype=None, normal=False, B=None):
     if isinstance(A, B200ArpackOp):
         return A
@@ -594,7 +607,25 @@ def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, t
     (src/interface.jl:215-290) on the B200.  ``symeigs(A, nev)``: scipy sparse matrix (full storage) or a
     B200ArpackOp; ``symeigs(A, B, nev)``: the generalised problem A x = lambda B x through
     ArpackSymmetricGeneralizedOp (src/interface.jl:143-163).  Returns an ArpackEigen; values ascending like
-    the reference."""
+    the reference.  Like the reference the element types may lead the argument list: ``symeigs(np.float32, A, nev)``
+    (= eigs(Float32, A, k)) and ``symeigs(np.float32, np.float64, A, nev)`` (= eigs(Float32, Float64, A, k), the mixed
+    precision of src/interface.jl:26-34; the factorisation type of Float32 vectors is always Float64 here)."""
+    lead = []
+    allargs = (A,) + tuple(args)
+    while allargs and _type_arg(allargs[0]) is not None and len(lead) < 2:
+        lead.append(_type_arg(allargs[0]))
+        allargs = allargs[1:]
+    if lead:
+        if not allargs:
+            raise TypeError("symeigs(TV, [TF,] A, nev)")
+        tv = lead[0]
+        ok_tf = {GA_F64: (GA_F64,), GA_C64: (GA_F64,), GA_DD: (GA_DD,), GA_F32: (GA_F64, GA_F32)}[tv]
+        if len(lead) == 2 and lead[1] not in ok_tf:
+            raise ValueError("unsupported factorisation type TF for these vectors")
+        if dtype is not None and _DTYPES[dtype] != tv:
+            raise ValueError("conflicting element types")
+        dtype = tv
+        A, args = allargs[0], allargs[1:]
     if len(args) == 1:
         B, nev = None, args[0]
     elif len(args) == 2:
@@ -695,7 +726,7 @@ def svds(A, k, *, which="LM", dtype=None, **kw):
         order = order[:nvec]
         Z = einfo.vectors[:, order]
         rc, W, nr = ctx.svd_vectors(order)
-        eps = 4.930380657631324e-32 if op.dtype == GA_DD else np.finfo(np.float64).eps
+        eps = 4.930380657631324e-32 if op.dtype == GA_DD else (np.finfo(np.float32).eps if op.dtype == GA_F32 else np.finfo(np.float64).eps)
         side = "U" if op.At_side == "left" else "V"
         if rc == GA_ERR_NUMERIC or (rc == 0 and np.any(nr <= eps / 2)):   # check_norm (src/idonow_ops.jl:300-306)
             raise ArpackException("encountered sigma ~ %g when computing %s subspace" % (float(np.min(nr)), side))

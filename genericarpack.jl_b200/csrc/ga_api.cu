@@ -25,6 +25,8 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static size_t real_size(const ga_ctx* c) { return c->dtype == GA_DD ? 16 : 8; }
+// rows are padded to whole Gram-Schmidt tiles: 2 KiB column segments = 256 rows of 8 bytes, 512 rows of Float32
+static i64 row_pad(const ga_ctx* c) { return c->dtype == GA_F32 ? 2 * kRowPad : kRowPad; }
 
 int sync_ctl(ga_ctx* c) {
   GA_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, c->stream));
@@ -49,14 +51,14 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
               int rank, int world_size) {
   if (!out) return GA_ERR_ARG;
   *out = nullptr;
-  if (dtype < 0 || dtype > 2 || n_global <= 0 || n_local <= 0 || ncv <= 0 || ncv > kMaxNcv || world_size < 1 ||
+  if (dtype < 0 || dtype > 3 || (dtype == GA_F32 && world_size != 1) || n_global <= 0 || n_local <= 0 || ncv <= 0 || ncv > kMaxNcv || world_size < 1 ||
       rank < 0 || rank >= world_size || row_offset < 0 || row_offset + n_local > n_global)
     return GA_ERR_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GA_ERR_CUDA;  // no silent CPU fallback
   ga_ctx* c = new ga_ctx();
   c->dtype = dtype;
-  c->esize = dtype == GA_F64 ? 8 : 16;
+  c->esize = dtype == GA_F64 ? 8 : (dtype == GA_F32 ? 4 : 16);
   c->n_global = n_global; c->n = n_local; c->row0 = row_offset;
   c->ncv = ncv; c->ncv_pad = kMaxNcv;
   c->device = device; c->rank = rank; c->world = world_size;
@@ -67,7 +69,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
     if (expect > blk) expect = blk;
     if (row_offset != (i64)rank * blk || n_local != expect) { delete c; return GA_ERR_ARG; }
   }
-  c->n_pad = (blk + kRowPad - 1) / kRowPad * kRowPad;
+  c->n_pad = (blk + row_pad(c) - 1) / row_pad(c) * row_pad(c);
 #define CK(call)                                            \
   do {                                                      \
     cudaError_t e_ = (call);                                \
@@ -211,7 +213,7 @@ int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, co
   if (rc) return rc;
   c->normal_m = m; c->normal_n = n; c->normal_left = left;
   const i64 extra = left ? m : n;
-  const i64 extra_pad = (extra + kRowPad - 1) / kRowPad * kRowPad;
+  const i64 extra_pad = (extra + row_pad(c) - 1) / row_pad(c) * row_pad(c);
   cudaFree(c->xfull);
   c->xfull = nullptr;
   GA_CUDA(c, cudaMalloc(&c->xfull, (size_t)extra_pad * c->esize));
@@ -319,6 +321,7 @@ int ga_set_generalized_csr(ga_ctx* c, const int64_t* a_rowptr, const int32_t* a_
   GA_CUDA(c, cudaSetDevice(c->device));
   c->op_kind = 0;
   if (c->world != 1) return set_err(c, GA_ERR_ARG, "generalised problem: single GPU only");
+  if (c->dtype == GA_F32) return set_err(c, GA_ERR_ARG, "generalised problem: Float32 vectors are not supported (mode 1 / normal operator only)");
   c->cg_tol[0] = cg_tol ? cg_tol[0] : 0.0;
   c->cg_tol[1] = 0.0;
   c->cg_maxit = cg_maxit;
@@ -440,10 +443,8 @@ int ga_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm) {
   int ierr = 0;
   if (!initv) {                                                // src/dgetv0.jl:542-553
     i64 seed[4] = {iseed[0], iseed[1], iseed[2], iseed[3]};
-    rc = launch_lcg_fill(c, seed);
+    rc = launch_lcg_fill_advance(c, seed);
     if (rc) return rc;
-    const i64 per = c->dtype == GA_C64 ? 2 : 1;
-    lcg_advance_seed(seed, per * c->n_global);
     for (int i = 0; i < 4; ++i) iseed[i] = seed[i];
   }
   if (j == 1) {                                                // :630-637
@@ -633,7 +634,7 @@ int ga_svd_vectors(ga_ctx* c, int nvec, const int32_t* perm, void* w_host, int64
   GA_CUDA(c, cudaSetDevice(c->device));
   const double t0 = now_s();
   const size_t rs = real_size(c);
-  const i64 ld = (other + kRowPad - 1) / kRowPad * kRowPad;
+  const i64 ld = (other + row_pad(c) - 1) / row_pad(c) * row_pad(c);
   if (!c->wbuf || c->wbuf_ld != ld || c->wbuf_cols < nvec) {
     cudaFree(c->wbuf);
     c->wbuf = nullptr;

@@ -209,6 +209,7 @@ int set_err(ga_ctx* c, int code, const std::string& msg);
 // k_lcg.cu
 int launch_lcg_fill(ga_ctx* c, const i64 iseed[4]);
 void lcg_advance_seed(i64 iseed[4], i64 nvalues);
+int launch_lcg_fill_advance(ga_ctx* c, i64 iseed[4]);   // fill + the seed the sequential generator leaves behind
 // k_vec.cu
 int launch_normalize(ga_ctx* c, int jcol, bool push_halo = true);  // vs.V[:,jcol] = vs.w / rnorm (device rnorm)
 int launch_norm_resid(ga_ctx* c, int decide_kind);         // ||resid|| -> ctl

@@ -19,6 +19,7 @@ template <> __device__ __forceinline__ ddbl real_from_dd<ddbl>(ddbl v) { return 
 // reduced dot slot -> element of T
 template <class T> __device__ __forceinline__ T slot_to_elem(double2 s);
 template <> __device__ __forceinline__ double slot_to_elem<double>(double2 s) { return s.x + s.y; }
+template <> __device__ __forceinline__ float slot_to_elem<float>(double2 s) { return (float)(s.x + s.y); }
 template <> __device__ __forceinline__ cdbl slot_to_elem<cdbl>(double2 s) { cdbl z; z.re = s.x; z.im = s.y; return z; }
 template <> __device__ __forceinline__ ddbl slot_to_elem<ddbl>(double2 s) { return ddbl(s.x, s.y); }
 

@@ -22,7 +22,9 @@ template <class T, int SEG> struct GsCfg {
   // the kernel at 96 registers/thread):
   //   F64 : 128 row lanes x 4 column groups, 2 rows/thread at 2 KiB (1 at 1 KiB), 16 accumulators
   //   16 B: 64 row lanes x 8 column groups, 2 rows/thread at 2 KiB (1 at 1 KiB), 8 accumulators
-  static constexpr int ROWL = (sizeof(T) == 8) ? 128 : 64;
+  //   F32 : 128 row lanes x 4 column groups, 4 adjacent rows/thread at 2 KiB (one LDS.128; 2 at 1 KiB),
+  //         16 binary64 accumulators
+  static constexpr int ROWL = (sizeof(T) <= 8) ? 128 : 64;
   static constexpr int RPT = R / ROWL;
   static constexpr int TG = 512 / ROWL;
   static constexpr int NC = kMaxNcv / TG;             // columns per thread (register accumulators)

@@ -271,7 +271,11 @@ int ga_symeigs_begin(ga_ctx* c, int which, int nev, const double* tol, int maxit
     c->solve = s;
     rc = s->start(v0_host);
   } else {
-    auto* s = new Solve<double>(c, which, nev, tol ? tol[0] : 0.0, maxiter);
+    double t = tol ? tol[0] : 0.0;
+    // Float32 vectors with a Float64 factorisation: the lowest precision sets the default tolerance
+    // (src/interface.jl:33-34, docs of `tol`): eps(Float32)/2
+    if (c->dtype == GA_F32 && !(t > 0.0)) t = 5.9604644775390625e-08;
+    auto* s = new Solve<double>(c, which, nev, t, maxiter);
     c->solve = s;
     rc = s->start(v0_host);
   }

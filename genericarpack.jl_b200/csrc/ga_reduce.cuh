@@ -43,6 +43,7 @@ struct NormAcc {
       fast_two_sum(sh, sl, med.hi, med.lo);
     }
   }
+  __device__ __forceinline__ void add(float x) { add((double)x); }
   __device__ __forceinline__ void add(cdbl x) { add(x.re); add(x.im); }
   __device__ __forceinline__ void add(ddbl x) {
     double ax = fabs(x.hi);

@@ -4,8 +4,12 @@
 //   C64  cdbl {re, im}     eigs(ComplexF64, Hermitian(A), ...)   (memory layout of Julia ComplexF64)
 //   DD   ddbl {hi, lo}     eigs(Double64, ...)                   (memory layout of DoubleFloats.Double64:
 //                                                                  two adjacent Float64, hi first)
+//   F32  float             eigs(Float32, Float64, ...): Float32 vectors, Float64 factorisation (mixed
+//                           precision, src/interface.jl:26-34); element arithmetic in binary32 like the
+//                           reference's sgemv / SparseArrays products, dot-product and norm accumulators
+//                           in binary64 (every float product is exact in a double)
 // The reference is generic over the element type T and its real type TR
-// (/root/reference/src/dsaitr.jl:962-981); here T in {double, cdbl, ddbl}, TR = Elem<T>::real_t.
+// (/root/reference/src/dsaitr.jl:962-981); here T in {double, cdbl, ddbl, float}, TR = Elem<T>::real_t.
 //
 // Double-double arithmetic uses FMA-based TwoProd and branch-free TwoSum (the same error-free
 // transformations the reference vendors in src/arpack-blas-nrm2.jl:51-145).  All functions are
@@ -180,6 +184,7 @@ GA_HD double mul_rn(double a, double b) {
 
 template <> struct Elem<double> {
   typedef double real_t;
+  typedef double acc_t;
   static constexpr int dtype = 0;
   static constexpr bool is_complex = false;
   static GA_HD double zero() { return 0.0; }
@@ -194,6 +199,7 @@ template <> struct Elem<double> {
 };
 template <> struct Elem<cdbl> {
   typedef double real_t;
+  typedef cdbl acc_t;
   static constexpr int dtype = 1;
   static constexpr bool is_complex = true;
   static GA_HD cdbl zero() { cdbl z; z.re = 0.0; z.im = 0.0; return z; }
@@ -219,6 +225,7 @@ template <> struct Elem<cdbl> {
 };
 template <> struct Elem<ddbl> {
   typedef ddbl real_t;
+  typedef ddbl acc_t;
   static constexpr int dtype = 2;
   static constexpr bool is_complex = false;
   static GA_HD ddbl zero() { return ddbl(0.0, 0.0); }
@@ -230,6 +237,29 @@ template <> struct Elem<ddbl> {
   static GA_HD void add_mul_real(ddbl& y, ddbl v, ddbl q) { y = dd_add(y, dd_mul(v, q)); }
   static GA_HD ddbl mul_real(ddbl v, ddbl a) { return dd_mul(v, a); }
   static GA_HD ddbl mul(ddbl a, ddbl b) { return dd_mul(a, b); }
+};
+
+GA_HD float fmul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+template <> struct Elem<float> {
+  typedef double real_t;                 // TF = Float64: H, Q, norms, tolerances
+  typedef double acc_t;                  // dot-product accumulators
+  static constexpr int dtype = 3;
+  static constexpr bool is_complex = false;
+  static GA_HD float zero() { return 0.0f; }
+  static GA_HD double re(float x) { return (double)x; }
+  static GA_HD float from_real(double r) { return (float)r; }
+  static GA_HD void add(float& a, float b) { a += b; }
+  static GA_HD void acc_conj_mul(double& acc, float v, float w) { acc = fma((double)v, (double)w, acc); }
+  static GA_HD void sub_mul(float& r, float v, float h) { r = fmaf(-v, h, r); }
+  static GA_HD void add_mul_real(float& y, float v, double q) { y = fmaf(v, (float)q, y); }
+  static GA_HD float mul_real(float v, double a) { return (float)((double)v * a); }   // Float32 * Float64, rounded on store
+  static GA_HD float mul(float a, float b) { return fmul_rn(a, b); }
 };
 
 }  // namespace ga

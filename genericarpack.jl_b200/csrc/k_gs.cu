@@ -63,9 +63,9 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
   __syncthreads();
   GA_TRACE(1, blockIdx.x == 0 && threadIdx.x == 0)
 
-  T acc[NC];
+  typename Elem<T>::acc_t acc[NC];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) acc[i] = Elem<T>::zero();
+  for (int i = 0; i < NC; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
   NormAcc nacc;
   nacc.init();
 
@@ -91,7 +91,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
     // rows of the tile owned by this thread: adjacent for 8-byte elements (one LDS.128 fetches
     // both), ROWL apart for 16-byte elements (adjacent rows would be a 32-byte lane stride =
     // 2-way bank conflicts on every shared-memory access; measured 50 % conflict wavefronts)
-#define ROWIDX(q) ((sizeof(T) == 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
+#define ROWIDX(q) ((sizeof(T) <= 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
     int it = 0;
     for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it % nstages;
@@ -287,6 +287,7 @@ int launch_gs(ga_ctx* c, int mode, int j, int gate_phase, int decide_kind) {
   switch (c->dtype) {
     case GA_F64: rc = launch_gs_mode<double>(c, mode, j, gate_phase, decide_kind); break;
     case GA_C64: rc = launch_gs_mode<cdbl>(c, mode, j, gate_phase, decide_kind); break;
+    case GA_F32: rc = launch_gs_mode<float>(c, mode, j, gate_phase, decide_kind); break;
     default: rc = launch_gs_mode<ddbl>(c, mode, j, gate_phase, decide_kind); break;
   }
   if (rc) return rc;
@@ -302,6 +303,7 @@ int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind) {
   switch (c->dtype) {
     case GA_F64: k_decide<double><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
     case GA_C64: k_decide<cdbl><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
+    case GA_F32: k_decide<float><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
     default: k_decide<ddbl><<<1, 128, 0, c->stream>>>(c->ctl, c->gather, c->world, j, c->ncv, gate_phase, decide_kind); break;
   }
   GA_CUDA(c, cudaGetLastError());

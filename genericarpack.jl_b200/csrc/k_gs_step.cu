@@ -88,7 +88,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
   __syncthreads();
 
   const int slice = warp % SLICES, g = warp / SLICES, rl = slice * 32 + lane;
-#define ROWIDX(q) ((sizeof(T) == 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
+#define ROWIDX(q) ((sizeof(T) <= 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
   int it = 0;  // running tile counter of this CTA: the stage ring and its parities continue across phases
   int npre = 0;  // producer warp: tiles of the upcoming phase whose V columns are already in flight
   const int nslots = j + 3;
@@ -106,7 +106,9 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
     }
     if (mode != 0) {
       const T* hb = hbuf_ptr<T>(ctl);
-      if (sizeof(T) == 8) {
+      if (sizeof(T) == 4) {
+        for (int c = tid; c < j; c += blockDim.x) reinterpret_cast<float*>(hs)[c] = __ldcg(reinterpret_cast<const float*>(hb) + c);
+      } else if (sizeof(T) == 8) {
         for (int c = tid; c < j; c += blockDim.x) reinterpret_cast<double*>(hs)[c] = __ldcg(reinterpret_cast<const double*>(hb) + c);
       } else {
         for (int c = tid; c < j; c += blockDim.x) reinterpret_cast<double2*>(hs)[c] = __ldcg(reinterpret_cast<const double2*>(hb) + c);
@@ -156,9 +158,9 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       }
     } else {
       // ---------------- consumers
-      T acc[NC];
+      typename Elem<T>::acc_t acc[NC];
 #pragma unroll
-      for (int i = 0; i < NC; ++i) acc[i] = Elem<T>::zero();
+      for (int i = 0; i < NC; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
       NormAcc nacc;
       nacc.init();
       int itc = it;
@@ -374,6 +376,7 @@ int launch_gs_step(ga_ctx* c, int j) {
   switch (c->dtype) {
     case GA_F64: return launch_step_t<double>(c, j);
     case GA_C64: return launch_step_t<cdbl>(c, j);
+    case GA_F32: return launch_step_t<float>(c, j);
     default: return launch_step_t<ddbl>(c, j);
   }
 }

@@ -80,6 +80,75 @@ __global__ void __launch_bounds__(256) k_lcg_fill(T* __restrict__ x, i64 n, i64 
   }
 }
 
+// ---- Float32 (src/arpack-blas.jl:457-544 with RT = Float32).  The conversion
+// R*(RT(IT1) + R*(RT(IT2) + R*(RT(IT3) + R*RT(IT4)))) is evaluated in binary32: the multiplications by R = 2^-12
+// are exact, the three additions round.  When the four limbs round up to exactly 1 (X >= 2^48 - 2^23, about one
+// draw in 2^25) the reference adds 2 to every limb of the current block's BASE seed and redraws (:520-525): the
+// rest of the stream then continues from the modified seed.  The stream is therefore "pure" (X = s * a^k) between
+// such events.  The device fills from a given origin (seed s, first index g_first, k counted from the origin) and
+// reports the first index whose conversion hits 1; the host then re-bases the stream there and refills the tail.
+__device__ __forceinline__ float lcg_to_unit_f32(unsigned long long x) {
+  const float R = 2.44140625e-4f;   // 1/4096
+  const float t1 = (float)(unsigned)((x >> 36) & 4095ULL), t2 = (float)(unsigned)((x >> 24) & 4095ULL);
+  const float t3 = (float)(unsigned)((x >> 12) & 4095ULL), t4 = (float)(unsigned)(x & 4095ULL);
+  return __fmul_rn(R, __fadd_rn(t1, __fmul_rn(R, __fadd_rn(t2, __fmul_rn(R, __fadd_rn(t3, __fmul_rn(R, t4)))))));
+}
+// x[i], i in [i_first, n): value number k0 + (i - i_first) + 1 of the pure stream from `seed`.
+__global__ void __launch_bounds__(256) k_lcg_fill_f32(float* __restrict__ x, i64 n, i64 i_first, i64 k0,
+                                                      unsigned long long seed, const __grid_constant__ LcgPow tab,
+                                                      unsigned long long* first_hit) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const i64 i0 = i_first + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n) return;
+  unsigned long long X = (seed * dev_apow(tab, (unsigned long long)(k0 + (i0 - i_first) + 1))) & kMask48;
+  const unsigned long long astride = dev_apow(tab, (unsigned long long)stride);
+  for (i64 i = i0; i < n; i += stride) {
+    const float rv = lcg_to_unit_f32(X);
+    if (rv == 1.0f) atomicMin(first_hit, (unsigned long long)i);
+    x[i] = __fadd_rn(__fmul_rn(2.0f, rv), -1.0f);                 // :538
+    X = (X * astride) & kMask48;
+  }
+}
+
+// Float32 start vector on one GPU (row0 = 0).  `iseed` is advanced to what the sequential generator leaves behind.
+static int lcg_fill_f32(ga_ctx* c, i64 iseed[4], const LcgPow& tab) {
+  const i64 n = c->n;
+  const unsigned long long kTwoC = 2ULL * ((1ULL << 36) | (1ULL << 24) | (1ULL << 12) | 1ULL);   // +2 on every limb
+  unsigned long long* hit_dev = reinterpret_cast<unsigned long long*>(c->partial);   // scratch, idle here
+  unsigned long long base = seed_to_u64(iseed);   // seed of the 128-value block that holds index i_first
+  i64 i_first = 0, k0 = 0;                        // first index to (re)fill; its 0-based position inside that block
+  for (int round = 0; round < 64; ++round) {
+    const unsigned long long none = ~0ULL;
+    GA_CUDA(c, cudaMemcpyAsync(hit_dev, &none, sizeof(none), cudaMemcpyHostToDevice, c->stream));
+    const int threads = 256;
+    i64 blocks = (n - i_first + threads - 1) / threads;
+    const i64 maxb = (i64)c->sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    k_lcg_fill_f32<<<(int)blocks, threads, 0, c->stream>>>((float*)c->resid, n, i_first, k0, base, tab, hit_dev);
+    GA_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    unsigned long long hit = none;
+    GA_CUDA(c, cudaMemcpyAsync(&hit, hit_dev, sizeof(hit), cudaMemcpyDeviceToHost, c->stream));
+    GA_CUDA(c, cudaStreamSynchronize(c->stream));
+    // the pure stream from (base, k0) covers indices i_first .. (hit or n-1); block seeds advance by a^128
+    const i64 last = hit == none ? n - 1 : (i64)hit;
+    const i64 kk = k0 + (last - i_first);           // 0-based position of `last` counted from the block start of i_first
+    const unsigned long long blk_seed = (base * lcg_apow((unsigned long long)((kk / 128) * 128))) & kMask48;
+    if (hit == none) {
+      // seed left behind = last value drawn (:543)
+      const unsigned long long xl = (blk_seed * lcg_apow((unsigned long long)(kk % 128 + 1))) & kMask48;
+      iseed[0] = (i64)((xl >> 36) & 4095ULL); iseed[1] = (i64)((xl >> 24) & 4095ULL);
+      iseed[2] = (i64)((xl >> 12) & 4095ULL); iseed[3] = (i64)(xl & 4095ULL);
+      return 0;
+    }
+    // redraw index `hit` and everything after it from the re-based block seed (the +2 may itself hit again: loop)
+    base = (blk_seed + kTwoC) & kMask48;
+    i_first = (i64)hit; k0 = kk % 128;
+  }
+  return set_err(c, GA_ERR_NUMERIC, "lcg: Float32 reseed loop did not terminate");
+}
+
 // resid[0:n) <- dlarnv values for this rank's rows [row0, row0+n)
 int launch_lcg_fill(ga_ctx* c, const i64 iseed[4]) {
   static const LcgPow tab = lcg_pow_table();
@@ -92,10 +161,23 @@ int launch_lcg_fill(ga_ctx* c, const i64 iseed[4]) {
   switch (c->dtype) {
     case GA_F64: k_lcg_fill<double, 1><<<(int)blocks, threads, 0, c->stream>>>((double*)c->resid, c->n, c->row0, seed, tab); break;
     case GA_C64: k_lcg_fill<cdbl, 2><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)c->resid, c->n, c->row0, seed, tab); break;
+    case GA_F32: return set_err(c, GA_ERR_ARG, "lcg: Float32 goes through launch_lcg_fill_advance");
     default: k_lcg_fill<ddbl, 1><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->resid, c->n, c->row0, seed, tab); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
+  return 0;
+}
+
+// Fill resid and leave in iseed what the reference's sequential generator leaves behind (:543).
+int launch_lcg_fill_advance(ga_ctx* c, i64 iseed[4]) {
+  if (c->dtype == GA_F32) {
+    static const LcgPow tab = lcg_pow_table();
+    return lcg_fill_f32(c, iseed, tab);
+  }
+  int rc = launch_lcg_fill(c, iseed);
+  if (rc) return rc;
+  lcg_advance_seed(iseed, (c->dtype == GA_C64 ? 2 : 1) * c->n_global);
   return 0;
 }
 

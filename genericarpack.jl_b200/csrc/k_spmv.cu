@@ -345,12 +345,14 @@ static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool 
     switch (c->dtype) {
       case GA_F64: return spmv_stream_launch_t<double>(c, M, x, y, gated, wait_halo);
       case GA_C64: return spmv_stream_launch_t<cdbl>(c, M, x, y, gated, wait_halo);
+      case GA_F32: return spmv_stream_launch_t<float>(c, M, x, y, gated, wait_halo);
       default: return spmv_stream_launch_t<ddbl>(c, M, x, y, gated, wait_halo);
     }
   }
   switch (c->dtype) {
     case GA_F64: spmv_launch_t<double>(c, M, x, y, gated, wait_halo); break;
     case GA_C64: spmv_launch_t<cdbl>(c, M, x, y, gated, wait_halo); break;
+    case GA_F32: spmv_launch_t<float>(c, M, x, y, gated, wait_halo); break;
     default: spmv_launch_t<ddbl>(c, M, x, y, gated, wait_halo); break;
   }
   GA_CUDA(c, cudaGetLastError());
@@ -440,6 +442,7 @@ static int launch_normal_dist(ga_ctx* c, const void* x, void* y, bool gated, boo
   if (blocks > (i64)c->sm_count * 8) blocks = (i64)c->sm_count * 8;
   if (blocks < 1) blocks = 1;
   const DevComm* cm = peer ? c->devcomm : nullptr;
+  if (c->dtype == GA_F32) return set_err(c, GA_ERR_ARG, "Float32 contexts are single-GPU");
   switch (c->dtype) {
     case GA_F64: k_reduce_scatter<double><<<(int)blocks, threads, 0, c->stream>>>((double*)y, (const double*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
     case GA_C64: k_reduce_scatter<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)y, (const cdbl*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;

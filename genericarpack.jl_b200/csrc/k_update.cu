@@ -152,6 +152,7 @@ int launch_vq(ga_ctx* c, int kplusp, int nout, bool do_resid, const void* sigma,
   switch (c->dtype) {
     case GA_F64: return launch_vq_t<double>(c, kplusp, nout, do_resid, kev);
     case GA_C64: return launch_vq_t<cdbl>(c, kplusp, nout, do_resid, kev);
+    case GA_F32: return launch_vq_t<float>(c, kplusp, nout, do_resid, kev);
     default: return launch_vq_t<ddbl>(c, kplusp, nout, do_resid, kev);
   }
 }

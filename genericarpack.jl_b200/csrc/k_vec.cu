@@ -111,6 +111,10 @@ int launch_normalize(ga_ctx* c, int jcol, bool push_halo) {
       k_normalize<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)c->vs.V + (size_t)jcol * ld,
                                                                (const cdbl*)c->vs.w, n, c->ctl, jcol + 1, cm, c->send_idx);
       break;
+    case GA_F32:
+      k_normalize<float><<<(int)blocks, threads, 0, c->stream>>>((float*)c->vs.V + (size_t)jcol * ld,
+                                                               (const float*)c->vs.w, n, c->ctl, jcol + 1, cm, c->send_idx);
+      break;
     default:
       k_normalize<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)c->vs.V + (size_t)jcol * ld,
                                                                (const ddbl*)c->vs.w, n, c->ctl, jcol + 1, cm, c->send_idx);
@@ -165,6 +169,7 @@ int launch_norm_resid(ga_ctx* c, int decide_kind) {
   switch (c->dtype) {
     case GA_F64: k_norm<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
     case GA_C64: k_norm<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
+    case GA_F32: k_norm<float><<<(int)blocks, threads, 0, c->stream>>>((const float*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
     default: k_norm<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)c->vs.w, n, c->ctl, c->partial, dk, c->ncv, cm); break;
   }
   GA_CUDA(c, cudaGetLastError());

@@ -12,8 +12,11 @@
  * Conventions
  *   - return value: 0 = ok; >0 informational (ARPACK `info`); <0 error.  -1..-13 and -9999
  *     mirror dsaupd's codes (src/dsaupd.jl:885-917); GA_ERR_* are library errors.
- *   - element types: GA_F64 (double), GA_C64 (re,im pairs), GA_DD (hi,lo pairs = Julia Double64).
- *   - "real" scalars (rnorm, H, Q, tol, shifts, Ritz values) are `double` for GA_F64/GA_C64 and
+ *   - element types: GA_F64 (double), GA_C64 (re,im pairs), GA_DD (hi,lo pairs = Julia Double64),
+ *     GA_F32 (float vectors with a Float64 factorisation: the reference's mixed-precision
+ *     symeigs(Float32, Float64, op, nev), src/interface.jl:26-34, README.md:28-35; V, resid, the CSR
+ *     values and every host vector/matrix of elements are `float`; single GPU, modes 1 and normal op).
+ *   - "real" scalars (rnorm, H, Q, tol, shifts, Ritz values) are `double` for GA_F64/GA_C64/GA_F32 and
  *     (hi,lo) pairs of double for GA_DD; pointers to them are `void*`/`double*` documented per call.
  *   - host pointers are caller-owned; the library never keeps them after the call returns.
  *   - matrices are column-major (Julia layout) with explicit leading dimensions.
@@ -29,7 +32,7 @@ extern "C" {
 
 typedef struct ga_ctx ga_ctx;
 
-enum { GA_F64 = 0, GA_C64 = 1, GA_DD = 2 };
+enum { GA_F64 = 0, GA_C64 = 1, GA_DD = 2, GA_F32 = 3 };
 enum { GA_LM = 0, GA_SM = 1, GA_LA = 2, GA_SA = 3, GA_BE = 4 }; /* which::Symbol */
 
 enum {

@@ -170,6 +170,60 @@ static void dlarnv_idist_2(i64 iseed[4], i64 n, T* x) {
   iseed[0] = IT1; iseed[1] = IT2; iseed[2] = IT3; iseed[3] = IT4;
 }
 
+// The same routine for RT = Float32 (mixed precision / Float32 vectors, src/interface.jl:26-34): the conversion
+// R*(RT(IT1)+R*(RT(IT2)+R*(RT(IT3)+R*RT(IT4)))) is evaluated in binary32, where it CAN round up to exactly 1
+// (X >= 2^48 - 2^23, about one draw in 2^25); the reference then adds 2 to every limb of the current block's base
+// seed and redraws (src/arpack-blas.jl:520-525), which changes the rest of the stream.  Built with
+// -ffp-contract=off, so these are plain IEEE binary32 operations.  Also counts the reseeds taken.
+static i64 dlarnv_idist_2_f32(i64 iseed[4], i64 n, float* x) {
+  const LcgTable& tab = lcg_table();
+  const i64 IPW2 = 4096;
+  const float R = 1.0f / 4096.0f;
+  i64 i1 = iseed[0], i2 = iseed[1], i3 = iseed[2], i4 = iseed[3];
+  i64 IT1 = i1, IT2 = i2, IT3 = i3, IT4 = i4;
+  int nrv = 0;
+  i64 reseeds = 0;
+  for (i64 i = 1; i <= n; ++i) {
+    volatile float rv = 1.0f;
+    nrv += 1;
+    if (nrv > 128) {
+      nrv = 1;
+      i1 = IT1; i2 = IT2; i3 = IT3; i4 = IT4;
+    }
+    const int* m = tab.mm[nrv - 1];
+    while (true) {
+      IT4 = i4 * m[3];
+      IT3 = IT4 / IPW2;
+      IT4 = IT4 - IPW2 * IT3;
+      IT3 = IT3 + i3 * m[3] + i4 * m[2];
+      IT2 = IT3 / IPW2;
+      IT3 = IT3 - IPW2 * IT2;
+      IT2 = IT2 + i2 * m[3] + i3 * m[2] + i4 * m[1];
+      IT1 = IT2 / IPW2;
+      IT2 = IT2 - IPW2 * IT1;
+      IT1 = IT1 + i1 * m[3] + i2 * m[2] + i3 * m[1] + i4 * m[0];
+      IT1 = IT1 % IPW2;
+      volatile float a4 = R * (float)IT4;
+      volatile float a3 = (float)IT3 + a4;
+      volatile float b3 = R * a3;
+      volatile float a2 = (float)IT2 + b3;
+      volatile float b2 = R * a2;
+      volatile float a1 = (float)IT1 + b2;
+      rv = R * a1;
+      if (rv == 1.0f) {
+        i1 += 2; i2 += 2; i3 += 2; i4 += 2;
+        reseeds += 1;
+      } else {
+        break;
+      }
+    }
+    volatile float two_rv = 2.0f * rv;
+    x[i - 1] = two_rv - 1.0f;
+  }
+  iseed[0] = IT1; iseed[1] = IT2; iseed[2] = IT3; iseed[3] = IT4;
+  return reseeds;
+}
+
 // ------------------------------------------------------------------ norm2
 // src/arpack-blas-nrm2.jl:272-299 (Float80.mynorm): four x87 accumulators, unrolled by 8.
 static inline double mynorm_x87(const double* a, i64 len) {

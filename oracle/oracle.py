@@ -60,6 +60,8 @@ def lib():
         L.oracle_dsaupd.argtypes = [vp, i32, i32, vp, i32, i32]
         L.oracle_dseupd.argtypes = [vp, i32, vp, vp, i32, i32, vp]
         L.oracle_dlarnv.argtypes = [i32, vp, i64, vp]
+        L.oracle_dlarnv_f32.restype = i64
+        L.oracle_dlarnv_f32.argtypes = [vp, i64, vp]
         L.oracle_lcg_table.argtypes = [vp]
         L.oracle_norm2.argtypes = [i32, vp, i64, vp]
         L.oracle_dstqrb.argtypes = [i32, i32, vp, vp, vp]
@@ -107,6 +109,15 @@ def dlarnv(n, iseed=(1, 3, 5, 7), dtype=F64):
     x = np.zeros((n,) + elem_shape(dtype), dtype=np_dtype(dtype))
     lib().oracle_dlarnv(dtype, _p(seed), n, _p(x))
     return x, tuple(int(s) for s in seed)
+
+
+def dlarnv_f32(n, iseed=(1, 3, 5, 7)):
+    """_dlarnv_idist_2! with RT = Float32 (binary32 conversion, incl. the rv == 1 reseed branch,
+    src/arpack-blas.jl:520-525): returns (x float32, new_iseed, number of reseeds taken)."""
+    seed = np.array(iseed, dtype=np.int64)
+    x = np.zeros(n, dtype=np.float32)
+    k = lib().oracle_dlarnv_f32(_p(seed), n, _p(x))
+    return x, tuple(int(s) for s in seed), int(k)
 
 
 def lcg_table():

@@ -190,6 +190,7 @@ void oracle_dlarnv(int dtype, long long* iseed, long long n, void* x) {
     case 2: dlarnv_idist_2<dd>(iseed, n, (dd*)x); break;
   }
 }
+long long oracle_dlarnv_f32(long long* iseed, long long n, float* x) { return dlarnv_idist_2_f32(iseed, n, x); }
 void oracle_lcg_table(int* out) { memcpy(out, lcg_table().mm, sizeof(int) * 512); }
 void oracle_norm2(int dtype, const void* x, long long n, double* out) {
   out[1] = 0;

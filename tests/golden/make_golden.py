@@ -61,6 +61,41 @@ def dlarnv_uniform11(n, seed=(1, 3, 5, 7)):
     return out, [(x >> 36) & 4095, (x >> 24) & 4095, (x >> 12) & 4095, x & 4095]
 
 
+def dlarnv_uniform11_f32(n, seed):
+    """_dlarnv_idist_2! with RT = Float32 (src/arpack-blas.jl:457-544): binary32 conversion, and the rv == 1 branch
+    (:520-525) that bumps every limb of the block's base seed by 2 and redraws.  numpy float32 scalars round after
+    every operation.  Returns (values, seed left behind, reseeds taken)."""
+    import numpy as np
+
+    a, mask = 0x1EE1429CC9F5, (1 << 48) - 1
+    f = np.float32
+    R = f(1.0) / f(4096.0)
+    base = (seed[0] << 36) | (seed[1] << 24) | (seed[2] << 12) | seed[3]
+    X, nrv, out, reseeds = base, 0, [], 0
+    for _ in range(n):
+        nrv += 1
+        if nrv > 128:
+            nrv, base = 1, X
+        while True:
+            X = (base * pow(a, nrv, 1 << 48)) & mask
+            l1, l2, l3, l4 = (X >> 36) & 4095, (X >> 24) & 4095, (X >> 12) & 4095, X & 4095
+            rv = R * (f(l1) + R * (f(l2) + R * (f(l3) + R * f(l4))))
+            if rv == f(1.0):
+                base = (base + 2 * ((1 << 36) | (1 << 24) | (1 << 12) | 1)) & mask
+                reseeds += 1
+            else:
+                break
+        out.append(f(2.0) * rv - f(1.0))
+    return out, [(X >> 36) & 4095, (X >> 24) & 4095, (X >> 12) & 4095, X & 4095], reseeds
+
+
+def seed_hitting_one(g, t=777):
+    """a seed whose g-th draw is X_g = 2^48 - 1 - 2t, which converts to exactly 1.0f in binary32"""
+    M = 1 << 48
+    s = ((M - 1 - 2 * t) * pow(pow(0x1EE1429CC9F5, g, M), -1, M)) % M
+    return [(s >> 36) & 4095, (s >> 24) & 4095, (s >> 12) & 4095, s & 4095]
+
+
 def collect():
     g = {"_about": "golden vectors literal in the reference's tests; regenerate with tests/golden/make_golden.py"}
 
@@ -90,6 +125,10 @@ def collect():
     i = _find(L, r"121003\.49732902342")
     g["dsdrv3_generalized_n100"] = {"source": "test/interface_high.jl:%d" % (i + 1), "values": _bracket_after(L, i, "≈")}
 
+    L = _lines("test/interface_simple.jl")
+    i = _find(L, r"info\.S ≈ sort\(\[4\.10123E-02")
+    g["svds_arpack_example_500x100_float32"] = {"source": "test/interface_simple.jl:%d" % (i + 1), "values": _bracket_after(L, i, "sort(")}
+
     v, seed = dlarnv_uniform11(10)
     if v != g["dgetv0_start_vector"]["values"]:
         raise SystemExit("closed-form dlarnv does not reproduce the reference's golden start vector")
@@ -98,6 +137,17 @@ def collect():
     for n in (1, 10, 127, 128, 129, 4097):
         v, seed = dlarnv_uniform11(n)
         g["dlarnv_stream"]["cases"].append({"n": n, "last3_hex": [float.hex(x) for x in v[-3:]], "seed_after": seed})
+    # Float32 stream (binary32 conversion): no golden vector exists in the reference's tests (its Float32 dlarnv test
+    # needs LAPACK's slarnv through Arpack_jll), so this is a second, independent restatement in numpy float32 that
+    # the C++ oracle and the device kernel are both checked against -- not a reference-generated vector.
+    g["dlarnv_stream_float32"] = {"source": "independent numpy-float32 restatement of src/arpack-blas.jl:457-544 (RT = Float32)",
+                                  "pinned_by_reference": False, "cases": []}
+    for n, sd in ((10, [1, 3, 5, 7]), (300, [1, 3, 5, 7]), (300, seed_hitting_one(5)), (400, seed_hitting_one(128)),
+                  (400, seed_hitting_one(129)), (700, seed_hitting_one(513))):
+        v, seed, k = dlarnv_uniform11_f32(n, sd)
+        g["dlarnv_stream_float32"]["cases"].append({"n": n, "seed": sd, "reseeds": k, "first3_hex": [float.hex(float(x)) for x in v[:3]],
+                                                    "last3_hex": [float.hex(float(x)) for x in v[-3:]],
+                                                    "sum_hex": float.hex(float(sum(float(x) for x in v))), "seed_after": seed})
     return g
 
 

@@ -29,6 +29,24 @@ def test_golden_dlarnv_stream_fixture(O):
         assert list(seed) == case["seed_after"], case["n"]
 
 
+def test_dlarnv_float32_stream_fixture(O):
+    """_dlarnv_idist_2! with RT = Float32 incl. the rv == 1 reseed branch (src/arpack-blas.jl:520-525): the C++ oracle
+    against the independent numpy-float32 restatement committed in tests/golden (seeds crafted to hit the branch at
+    draws 5, 128, 129 and 513)."""
+    for case in GOLD["dlarnv_stream_float32"]["cases"]:
+        x, seed, k = O.dlarnv_f32(case["n"], tuple(case["seed"]))
+        assert k == case["reseeds"], case
+        assert [float.hex(float(v)) for v in x[:3]] == case["first3_hex"]
+        assert [float.hex(float(v)) for v in x[-3:]] == case["last3_hex"]
+        assert float.hex(float(sum(float(v) for v in x))) == case["sum_hex"]
+        assert list(seed) == case["seed_after"]
+        assert x.dtype == np.float32 and np.all(x < 1.0) and np.all(x >= -1.0)
+    # away from the reseed branch the Float32 stream is the rounded Float64 stream up to one binary32 ulp
+    xf, _, k = O.dlarnv_f32(5000)
+    xd, _ = O.dlarnv(5000)
+    assert k == 0 and np.max(np.abs(xf.astype(np.float64) - xd)) <= 2.0 ** -23
+
+
 def test_lcg_table_rows(O):
     """rows 1, 2, 3, 64, 128 of _dlaruv_mm (src/arpack-blas.jl:281-408) given literally."""
     t = O.lcg_table()

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
 // ---------------------------------------------------------------------------------------------
 // Streamed SpMV: persistent CTAs, TMA-staged row blocks.
 template <class T, int GROUPS_ = 4> struct SpmvStreamCfg {
-  static constexpr int CAP = (sizeof(T) == 8) ? 2048 : 1024;  // non-zeros per row block (one pipeline stage)
+  static constexpr int CAP = (sizeof(T) <= 8) ? 2048 : 1024;  // non-zeros per row block (one pipeline stage)
   static constexpr int MAXROWS = 512;    // rows per row block
   static constexpr int GROUPS = GROUPS_, GT = 128;
   static constexpr int THREADS = GROUPS * GT + 32;      // consumer groups + producer warp
@@ -554,7 +554,7 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
   std::vector<int4> desc;
   std::vector<int> longrow;
   {
-    const int scap = c->esize == 8 ? SpmvStreamCfg<double>::CAP : SpmvStreamCfg<cdbl>::CAP;
+    const int scap = c->esize <= 8 ? SpmvStreamCfg<double>::CAP : SpmvStreamCfg<cdbl>::CAP;   // same rule as the kernels' sizeof(T)
     const int smax = SpmvStreamCfg<double>::MAXROWS;
     desc.reserve((size_t)(nnz / (scap / 2) + nrows / smax + 16));
     i64 r0 = 0;

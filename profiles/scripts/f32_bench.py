@@ -2,7 +2,7 @@
 """Float32-vector variant of BASELINE config C2 on one B200: eigs(Float32, Float64, A, 10; ncv=40), 2-D Laplacian
 m x m (default 4000 -> n = 16M): Lanczos steps/s over `cycles` restart cycles after a warm-up, Gram-Schmidt step
 kernel GB/s (algorithmic bytes, 4-byte elements) and SpMV GB/s, next to the Float64 numbers of the same run.
-    python profiles/scripts/f32_bench.py [m] [cycles]"""
+    python profiles/scripts/f32_bench.py [m] [cycles] [f32,f64]"""
 import importlib, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,12 +11,15 @@ import __graft_entry__ as entry  # noqa: E402
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 cycles = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+only = sys.argv[3].split(",") if len(sys.argv) > 3 else ["f32", "f64"]
 pkg = entry.load_package(); syn = importlib.import_module(entry.PKG_NAME + ".synthetic")
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 rowptr, col, val, shape = syn.laplacian2d(m)
 n, nnz, nev, ncv = m * m, len(col), 10, 40
 out = {"workload": "C2 operator, n=%d, nnz=%d, nev=10, ncv=40, 1 GPU" % (n, nnz), "hbm_peak_measured_GBps": peak}
 for name, S, v in (("f32", 4, val.astype(np.float32)), ("f64", 8, val)):
+    if name not in only:
+        continue
     ctx = pkg.Context(pkg.ArpackSimpleOp((rowptr, col, v, shape), dtype=name), ncv)
     pad = 512 if S == 4 else 256
     n_pad = (n + pad - 1) // pad * pad

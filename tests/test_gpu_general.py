@@ -57,7 +57,7 @@ def test_generalized_lockstep_with_oracle(pkg, O):
     assert np.max(np.abs(V.T @ (B @ V) - np.eye(ncv))) <= 1e-13
     st, so = ctx.stats(), o.stats()
     for k in ("nopx", "nbx", "nrorth", "nitref", "nrstrt"):
-        assert st[k] == so[k], k
+        assert st[k] == so[k] + (1 if k == "nbx" else 0), k     # + the B*x of the bnorm_resid() call above
     ctx.close()
 
 

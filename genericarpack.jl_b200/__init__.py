@@ -611,6 +611,7 @@ def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, t
     (= eigs(Float32, A, k)) and ``symeigs(np.float32, np.float64, A, nev)`` (= eigs(Float32, Float64, A, k), the mixed
     precision of src/interface.jl:26-34; the factorisation type of Float32 vectors is always Float64 here)."""
     lead = []
+    narrow_tf = False
     allargs = (A,) + tuple(args)
     while allargs and _type_arg(allargs[0]) is not None and len(lead) < 2:
         lead.append(_type_arg(allargs[0]))
@@ -625,6 +626,9 @@ def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, t
         if dtype is not None and _DTYPES[dtype] != tv:
             raise ValueError("conflicting element types")
         dtype = tv
+        # eigs(Float32, A, k) means TV = TF = Float32: the values come back as Float32 like the reference's
+        # (the factorisation itself still runs in Float64 here)
+        narrow_tf = tv == GA_F32 and (len(lead) == 1 or lead[1] == GA_F32)
         A, args = allargs[0], allargs[1:]
     if len(args) == 1:
         B, nev = None, args[0]
@@ -659,6 +663,8 @@ def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, t
         st = ctx.stats()
         if isinstance(stats, dict):
             stats.update(st)
+        if narrow_tf:
+            values, bounds = values.astype(np.float32), bounds.astype(np.float32)
         return ArpackEigen(which, iparam, values, vecs, bounds, op, ctx if keep_context else None, st, info)
     finally:
         if not keep_context:

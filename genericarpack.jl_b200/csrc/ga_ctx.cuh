@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -238,6 +239,14 @@ int general_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, i
 int general_resid_bnorm(ga_ctx* c, double* rnorm_out);              // sqrt|resid' B resid| (src/dsaup2.jl:1383-1411)
 // k_update.cu
 int launch_vq(ga_ctx* c, int kplusp, int nout, bool do_resid, const void* sigma, const void* beta, int kev);
+
+// cudaFuncSetAttribute applies to the current device only, and contexts may live on several devices and be
+// driven from several host threads (no globals: src/README "multithread safe"): one flag per device, set atomically.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0ULL};
+  bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ULL) == 0ULL; }
+  void done(int dev) { mask.fetch_or(1ULL << (dev & 63), std::memory_order_release); }
+};
 
 int sync_ctl(ga_ctx* c);  // copy DevCtl to the pinned mirror and synchronise the stream
 

@@ -223,10 +223,10 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
   const i64 ntiles = c->vs.ld / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
   const size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need(c->device)) {
     GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
-    attr_set = true;
+    attr_set.done(c->device);
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
   if (grid > kMaxCtas) grid = kMaxCtas;

@@ -322,10 +322,10 @@ static int launch_step_seg(ga_ctx* c, int j, int nstages) {
   i64 ntiles = c->n_pad / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
   size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need(c->device)) {
     GA_CUDA(c, cudaFuncSetAttribute(k_gs_step<T, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
-    attr_set = true;
+    attr_set.done(c->device);
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
   const T* V = (const T*)c->V;

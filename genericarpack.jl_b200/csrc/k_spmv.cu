@@ -289,11 +289,11 @@ template <class T, int NG>
 static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, int nsplit,
                                 const DevComm* cm, int nst) {
   typedef SpmvStreamCfg<T, NG> C;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need(c->device)) {
     GA_CUDA(c, cudaFuncSetAttribute(k_spmv_stream<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::smem_bytes(C::MAX_STAGES)));
-    attr_set = true;
+    attr_set.done(c->device);
   }
   if (nst < NG) nst = NG;
   const int grid = M.ndesc < c->sm_count ? M.ndesc : c->sm_count;

@@ -116,10 +116,10 @@ static int launch_vq_t(ga_ctx* c, int kplusp, int nout, bool do_resid, int kev) 
   const i64 ntiles = c->n_pad / C::R;
   const int nout_pad = (nout + C::OB - 1) / C::OB * C::OB;
   const size_t smem = (size_t)kplusp * nout_pad * sizeof(TR) + (size_t)kplusp * C::R * sizeof(T);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need(c->device)) {
     GA_CUDA(c, cudaFuncSetAttribute(k_vq<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set.done(c->device);
   }
   if (smem > 200 * 1024) return set_err(c, GA_ERR_ARG, "vq: shared memory budget exceeded");
   int per_sm = (int)((220 * 1024) / (smem + 2048));

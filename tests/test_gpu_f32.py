@@ -111,6 +111,7 @@ def test_f32_eigs_kats(pkg):
     for lead in ((np.float32,), (np.float32, np.float64), ("f32",)):
         res = pkg.eigs(*lead, A, 3, which="LA", ritzvec=False)
         assert res.vectors is None
+        assert res.values.dtype == (np.float64 if len(lead) == 2 else np.float32)     # eltype(vals), test/interface_simple.jl:43
         assert np.allclose(res.values, np.sort(w)[-3:], rtol=3e-6)
     res = pkg.eigs(np.float32, A, 3)
     assert res.vectors.dtype == np.float32

@@ -127,3 +127,49 @@ def test_generalized_large_property(pkg, syn):
     assert np.max(np.abs(Z.T @ (B @ Z) - np.eye(6))) <= 1e-10
     for i in range(6):
         assert np.linalg.norm(A @ Z[:, i] - res.values[i] * (B @ Z[:, i])) <= 1e-9 * np.linalg.norm(A @ Z[:, i])
+
+
+def test_getv0_initv_semantics(pkg):
+    """test/dgetv0_simple.jl:40-69 (bmat = :I, initv = true: resid and the seed are left alone, rnorm = norm2(resid))
+    and :91-147 (bmat = :G, initv = true: resid <- OP resid0, rnorm = sqrt|resid' B resid|, one OP*x, one B*x)."""
+    n = 10
+    M = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    r0 = 2 * np.random.default_rng(0).random(n) - 1
+    ctx = pkg.Context(pkg.ArpackSimpleOp(M), 2)
+    ctx.upload_resid(r0)
+    ierr, rn = ctx.getv0(initv=True, j=1)
+    assert ierr == 0 and np.array_equal(np.asarray(ctx.download_resid()), r0) and tuple(ctx.iseed) == (1, 3, 5, 7)
+    assert abs(rn - np.linalg.norm(r0)) <= 2 * np.spacing(np.linalg.norm(r0))
+    ctx.close()
+    B = sp.diags(np.arange(1, n + 1) / 10.0).tocsr()
+    ctx = pkg.Context(pkg.ArpackSymmetricGeneralizedOp((B @ M).tocsr(), B), 2)      # OP = inv(B) (B M) = M
+    ctx.upload_resid(r0)
+    ierr, rn = ctx.getv0(initv=True, j=1)
+    r = np.asarray(ctx.download_resid())
+    assert ierr == 0 and tuple(ctx.iseed) == (1, 3, 5, 7)
+    assert np.allclose(r, M @ r0, rtol=1e-13, atol=0)
+    assert abs(rn - np.sqrt(abs((M @ r0) @ (B @ (M @ r0))))) <= 1e-13 * rn
+    st = ctx.stats()
+    assert st["nopx"] == 1 and st["nbx"] == 1
+    ctx.close()
+
+
+def test_getv0_generalized_restart_failure(pkg):
+    """test/dgetv0_simple.jl:198-247: OP resid0 lies in the span of the B-orthonormal basis, all six orthogonalisation
+    passes collapse: ierr = -1, resid = 0, one OP*x and 7 B*x (the reference's counts).  Positive definite variant of the
+    reference's singular B, see tests/test_oracle.py::test_dgetv0_generalized_restart_failure."""
+    n, j = 8, 3
+    b = np.arange(1, n + 1) / 4.0
+    a = np.zeros(n); a[:2] = [3.0, -2.0]
+    A = sp.csr_matrix((a, (np.arange(n), np.arange(n))), shape=(n, n))            # explicit zeros kept on the diagonal
+    ctx = pkg.Context(pkg.ArpackSymmetricGeneralizedOp(A, sp.diags(b).tocsr()), j + 1)
+    V = np.zeros((n, j))
+    for i in range(j):
+        V[i, i] = 1 / np.sqrt(b[i])
+    ctx.upload_v(V, 0)
+    ctx.upload_resid(2 * np.random.default_rng(0).random(n) - 1)
+    ierr, rn = ctx.getv0(initv=True, j=j)
+    assert ierr == -1 and rn == 0.0 and np.all(np.asarray(ctx.download_resid()) == 0)
+    st = ctx.stats()
+    assert st["nopx"] == 1 and st["nbx"] == 7
+    ctx.close()

@@ -246,6 +246,46 @@ def test_dgetv0_restart_failure(O):
     assert ierr == 0 and abs(np.sum(o.resid)) <= n * np.finfo(float).eps and o.rnorm > 0
 
 
+def test_dgetv0_initv_semantics(O):
+    """test/dgetv0_simple.jl:40-69 (bmat = :I, initv = true: resid and the seed are left alone, rnorm = norm2(resid))
+    and :91-147 (bmat = :G, initv = true: resid <- OP resid0, rnorm = sqrt|resid' B resid|, one OP*x, one B*x)."""
+    n = 10
+    M = sp.diags(np.arange(1.0, n + 1)).tocsr()
+    r0 = 2 * np.random.default_rng(0).random(n) - 1
+    o = O.Oracle(M, 2)
+    o.resid[:] = r0
+    assert o.dgetv0(itry=1, initv=True, j=1) == 0
+    assert np.array_equal(o.resid, r0) and tuple(o.iseed) == (1, 3, 5, 7)
+    assert o.rnorm == pytest.approx(np.linalg.norm(r0), rel=1e-15)
+    B = sp.diags(np.arange(1, n + 1) / 10.0).tocsr()
+    o = O.Oracle((B @ M).tocsr(), 2, B=B)                  # OP = inv(B) (B M) = M
+    o.resid[:] = r0
+    assert o.dgetv0(itry=1, initv=True, j=1) == 0
+    assert np.allclose(o.resid, M @ r0, rtol=1e-14, atol=0) and tuple(o.iseed) == (1, 3, 5, 7)
+    assert o.rnorm == pytest.approx(np.sqrt(abs((M @ r0) @ (B @ (M @ r0)))), rel=1e-14)
+    st = o.stats()
+    assert st["nopx"] == 1 and st["nbx"] == 1
+
+
+def test_dgetv0_generalized_restart_failure(O):
+    """test/dgetv0_simple.jl:198-247: OP resid0 lies in the span of the (B-orthonormal) basis, so all six
+    orthogonalisation passes collapse: ierr = -1, one OP*x, 7 B*x (the initial one + 6).  The reference uses a singular
+    B = diag(1,1,0,...); the same situation with a positive definite B: A = diag(a1, a2, 0, ...) so that
+    OP resid0 = inv(B) A resid0 has two non-zero entries, and V[:, i] = e_i / sqrt(B_ii)."""
+    n, j = 8, 3
+    b = np.arange(1, n + 1) / 4.0
+    a = np.zeros(n); a[:2] = [3.0, -2.0]
+    o = O.Oracle(sp.diags(a).tocsr(), j + 1, B=sp.diags(b).tocsr())
+    for i in range(j):
+        o.Vt[i] = 0.0
+        o.Vt[i, i] = 1 / np.sqrt(b[i])
+    o.resid[:] = 2 * np.random.default_rng(0).random(n) - 1
+    assert o.dgetv0(itry=1, initv=True, j=j) == -1
+    assert np.all(o.resid == 0) and o.rnorm == 0.0
+    st = o.stats()
+    assert st["nopx"] == 1 and st["nbx"] == 7
+
+
 # ---------------------------------------------------------------- eigenvalue KATs
 def _top(w, k, which="LM"):
     if which == "LM":

@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 __all__ = [
-    "ArpackException", "ArpackSimpleOp", "ArpackNormalOp", "ArpackSymmetricGeneralizedOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
+    "ArpackException", "ArpackSimpleOp", "ArpackSimpleFunctionOp", "ArpackNormalFunctionOp", "ArpackNormalOp", "ArpackSymmetricGeneralizedOp", "B200ArpackOp", "ArpackEigen", "ArpackStats",
     "Context", "comm_unique_id", "DDArr", "as_dd", "dd_to_float", "to_elem", "eigs", "symeigs", "hermeigs", "svds", "lib", "build", "GA_F64", "GA_C64", "GA_DD", "GA_F32",
 ]
 
@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid", "ga_bnorm_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -107,6 +107,8 @@ def lib():
         L.ga_opx.argtypes = [vp, vp, vp]
         L.ga_set_generalized_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32]
         L.ga_set_solve_callback.argtypes = [vp, vp, vp]
+        L.ga_set_op_callback.argtypes = [vp, vp, vp]
+        L.ga_set_normal_op_callbacks.argtypes = [vp, i64, i64, vp, vp, vp]
         L.ga_bx.argtypes = [vp, vp, vp]
         L.ga_get_solve_stats.argtypes = [vp, vp, vp, vp]
         L.ga_upload_resid.argtypes = [vp, vp]
@@ -239,6 +241,77 @@ class ArpackNormalOp(B200ArpackOp):  # src/idonow_ops.jl:216-277
         return "right" if m <= n else "left"
 
 
+_OP_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                          ctypes.c_void_p)    # ga_op_fn
+
+
+class _DevVec:
+    """a device vector handed to an operator callback, exported through __cuda_array_interface__ so that
+    torch.as_tensor(v, device="cuda") / cupy.asarray(v) wrap it without a copy"""
+
+    def __init__(self, ptr, n, dt):
+        shape, typestr = {GA_F64: ((n,), "<f8"), GA_C64: ((n,), "<c16"), GA_DD: ((n, 2), "<f8"), GA_F32: ((n,), "<f4")}[dt]
+        self.ptr, self.n = int(ptr), int(n)
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3,     # torch refuses the read-only flag
+                                         "strides": None}
+
+
+def _wrap_op_fn(F, dt):
+    """ga_op_fn around a Python callable F(y, x): x and y arrive as torch CUDA tensors that alias the library's
+    device vectors, and the call runs under the library's stream so that everything F launches is enqueued there."""
+
+    def thunk(user, x_ptr, y_ptr, nx, ny, stream):
+        try:
+            import torch
+
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                x = torch.as_tensor(_DevVec(x_ptr, nx, dt), device="cuda")   # treat as read-only
+                y = torch.as_tensor(_DevVec(y_ptr, ny, dt), device="cuda")
+                F(y, x)
+            return 0
+        except Exception:  # an exception must not unwind through the C frames
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    return _OP_FN(thunk)
+
+
+class ArpackSimpleFunctionOp(B200ArpackOp):
+    """ArpackSimpleFunctionOp(F, n) (src/idonow_ops.jl:360-368): opx!(y, op, x) = op.F(y, x) with a matrix-free F.
+    Here F(y, x) receives torch CUDA tensors aliasing the library's device vectors (zero copy) and must write y
+    in place with work enqueued on the current torch stream (= the library's stream); the Lanczos loop stays on
+    the device, F is called once per OP*x while the steps are being enqueued."""
+
+    def __init__(self, F, n, dtype="f64"):
+        self.F, self.shape, self.dtype = F, (int(n), int(n)), _DTYPES[dtype]
+        self._cb = _wrap_op_fn(F, self.dtype)          # keeps the ctypes thunk alive as long as the op
+
+    def size(self):
+        return self.shape[0]
+
+
+class ArpackNormalFunctionOp(B200ArpackOp):
+    """ArpackNormalFunctionOp(av, atv, m, n) (src/idonow_ops.jl:406-431): OP = A'A (m > n) or AA' through the two
+    callbacks av(y, x): y = A x and atv(y, x): y = A' x on device tensors (see ArpackSimpleFunctionOp)."""
+
+    normal = True
+
+    def __init__(self, av, atv, m, n, dtype="f64"):
+        self.av, self.atv, self.shape, self.dtype = av, atv, (int(m), int(n)), _DTYPES[dtype]
+        self._cb = (_wrap_op_fn(av, self.dtype), _wrap_op_fn(atv, self.dtype))
+
+    def size(self):
+        m, n = self.shape
+        return m if m <= n else n
+
+    @property
+    def At_side(self):
+        m, n = self.shape
+        return "right" if m <= n else "left"
+
+
 class ArpackSymmetricGeneralizedOp(B200ArpackOp):
     """ArpackSymmetricGeneralizedOp(A, S, B) (src/idonow_ops.jl:462-492): A x = lambda B x in mode 2 with
     bmat = :G.  A and B are full (both triangles) sparse matrices, B Hermitian positive definite.  The
@@ -289,7 +362,16 @@ class Context:
         if rc != 0 or not h:
             raise RuntimeError("ga_create failed with code %d (is a CUDA device present? there is no CPU fallback)" % rc)
         self.h = h
-        if isinstance(op, ArpackSymmetricGeneralizedOp):
+        if isinstance(op, (ArpackSimpleFunctionOp, ArpackNormalFunctionOp)):
+            if world_size != 1:
+                raise ValueError("function operators run on one GPU")
+            if isinstance(op, ArpackSimpleFunctionOp):
+                self._ck(L.ga_set_op_callback(self.h, ctypes.cast(op._cb, ctypes.c_void_p), None))
+            else:
+                m, n = op.shape
+                self._ck(L.ga_set_normal_op_callbacks(self.h, m, n, ctypes.cast(op._cb[0], ctypes.c_void_p),
+                                                      ctypes.cast(op._cb[1], ctypes.c_void_p), None))
+        elif isinstance(op, ArpackSymmetricGeneralizedOp):
             if world_size != 1:
                 raise ValueError("the generalised problem runs on one GPU")
             tol = None if op.cg_tol is None else np.array([float(op.cg_tol), 0.0])

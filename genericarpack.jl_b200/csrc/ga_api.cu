@@ -24,6 +24,11 @@ int set_err(ga_ctx* c, int code, const std::string& msg) {
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+static void clear_operator(ga_ctx* c) {   // before a new operator is installed
+  c->op_kind = 0;
+  c->op_cb = c->av_cb = c->atv_cb = nullptr;
+  c->op_user = nullptr;
+}
 static size_t real_size(const ga_ctx* c) { return c->dtype == GA_DD ? 16 : 8; }
 // rows are padded to whole Gram-Schmidt tiles: 2 KiB column segments = 256 rows of 8 bytes, 512 rows of Float32
 static i64 row_pad(const ga_ctx* c) { return c->dtype == GA_F32 ? 2 * kRowPad : kRowPad; }
@@ -141,7 +146,7 @@ int ga_comm_ipc_import(ga_ctx* c, const void* all) { return (c && all) ? comm_ip
 int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void* val) {
   if (!c || !rowptr || !col || !val) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
-  c->op_kind = 0;
+  clear_operator(c);
   if (c->world != 1) return set_err(c, GA_ERR_ARG, "multi-GPU contexts take ga_set_csr_dist (local columns + halo plan)");
   int rc = csr_upload(c, c->A, c->n, c->n_global, rowptr, col, val, 0);
   if (rc) return rc;
@@ -160,7 +165,7 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
                     const int32_t* send_dest_off) {
   if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
-  c->op_kind = 0;
+  clear_operator(c);
   int rc = csr_upload(c, c->A, c->n, c->n_pad + nhalo, rowptr, col_local, val, 0);
   if (rc) return rc;
   c->send_counts.assign(send_counts, send_counts + c->world);
@@ -188,7 +193,7 @@ int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, co
   const bool left = !(m <= n);  // src/idonow_ops.jl:222-235
   if (c->n != (left ? n : m)) return set_err(c, GA_ERR_ARG, "normal operator: context size must be min(m, n) side");
   GA_CUDA(c, cudaSetDevice(c->device));
-  c->op_kind = 0;
+  clear_operator(c);
   int rc = csr_upload(c, c->A, m, n, rowptr, col, val, 0);
   if (rc) return rc;
   // explicit adjoint (conjugate transpose) CSR, built on the host once
@@ -233,7 +238,7 @@ int ga_set_normal_csr_dist(ga_ctx* c, int64_t mt_local, const int64_t* rowptr, c
   if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0 || mt_local < 0) return GA_ERR_ARG;
   if (c->world < 2) return set_err(c, GA_ERR_ARG, "single-GPU contexts take ga_set_normal_csr");
   GA_CUDA(c, cudaSetDevice(c->device));
-  c->op_kind = 0;
+  clear_operator(c);
   const i64 ncol = c->n_pad + nhalo;                       // local column space [own | halo]
   int rc = csr_upload(c, c->A, mt_local, ncol, rowptr, col_local, val, 0);
   if (rc) return rc;
@@ -319,7 +324,7 @@ int ga_set_generalized_csr(ga_ctx* c, const int64_t* a_rowptr, const int32_t* a_
                            int cg_maxit) {
   if (!c || !a_rowptr || !a_col || !a_val || !b_rowptr || !b_col || !b_val || cg_maxit < 0) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
-  c->op_kind = 0;
+  clear_operator(c);
   if (c->world != 1) return set_err(c, GA_ERR_ARG, "generalised problem: single GPU only");
   if (c->dtype == GA_F32) return set_err(c, GA_ERR_ARG, "generalised problem: Float32 vectors are not supported (mode 1 / normal operator only)");
   c->cg_tol[0] = cg_tol ? cg_tol[0] : 0.0;
@@ -330,6 +335,36 @@ int ga_set_generalized_csr(ga_ctx* c, const int64_t* a_rowptr, const int32_t* a_
   int rc = general_upload(c, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val);
   if (rc) return rc;
   c->op_kind = 3;
+  return 0;
+}
+
+int ga_set_op_callback(ga_ctx* c, ga_op_fn opx, void* user) {
+  if (!c || !opx) return GA_ERR_ARG;
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "function operators: single GPU only");
+  c->A.free_all(); c->At.free_all();
+  c->op_cb = opx; c->av_cb = c->atv_cb = nullptr; c->op_user = user;
+  c->op_kind = 1;
+  return 0;
+}
+
+int ga_set_normal_op_callbacks(ga_ctx* c, int64_t m, int64_t n, ga_op_fn av, ga_op_fn atv, void* user) {
+  if (!c || !av || !atv || m <= 0 || n <= 0) return GA_ERR_ARG;
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "function operators: single GPU only");
+  const bool left = !(m <= n);  // src/idonow_ops.jl:222-235
+  if (c->n != (left ? n : m)) return set_err(c, GA_ERR_ARG, "normal operator: context size must be min(m, n) side");
+  GA_CUDA(c, cudaSetDevice(c->device));
+  clear_operator(c);
+  c->A.free_all(); c->At.free_all();
+  c->normal_m = m; c->normal_n = n; c->normal_left = left; c->normal_dist = false;
+  const i64 extra = left ? m : n;
+  const i64 extra_pad = (extra + row_pad(c) - 1) / row_pad(c) * row_pad(c);
+  cudaFree(c->xfull);
+  c->xfull = nullptr;
+  GA_CUDA(c, cudaMalloc(&c->xfull, (size_t)extra_pad * c->esize));
+  GA_CUDA(c, cudaMemset(c->xfull, 0, (size_t)extra_pad * c->esize));
+  c->xfull_len = extra_pad;
+  c->op_cb = nullptr; c->av_cb = av; c->atv_cb = atv; c->op_user = user;
+  c->op_kind = 2;
   return 0;
 }
 

@@ -148,6 +148,8 @@ struct ga_ctx {
   int cg_maxit = 0;                    // 0: 1000
   ga_solve_fn solve_cb = nullptr; void* solve_user = nullptr;   // optional user solve (device pointers)
   long long solve_count = 0, solve_iters = 0; double solve_max_relres = 0.0;
+  // function operators (ga_set_op_callback / ga_set_normal_op_callbacks): the caller's OP*x on device vectors
+  ga_op_fn op_cb = nullptr, av_cb = nullptr, atv_cb = nullptr; void* op_user = nullptr;
   const void* gs_dotvec = nullptr;     // when set, the MODE 0 sweep forms V' * (this vector) instead of V' * resid
   ga::i64 normal_m = 0, normal_n = 0; bool normal_left = true;
 

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace ga {
@@ -456,6 +457,20 @@ static int launch_normal_dist(ga_ctx* c, const void* x, void* y, bool gated, boo
 
 int comm_halo_exchange(ga_ctx* c, const void* x_local);  // ga_comm.cu
 
+// the caller's operator (function ops): enqueue on the context's stream
+static int call_op_fn(ga_ctx* c, ga_op_fn fn, const void* x, void* y, i64 nx, i64 ny) {
+  const int rc = fn(c->op_user, x, y, (int64_t)nx, (int64_t)ny, (void*)c->stream);
+  if (rc) return set_err(c, GA_ERR_ARG, "the operator callback returned " + std::to_string(rc));
+  c->launches += 1;
+  return 0;
+}
+// one half of the normal operator: y = A x (adjoint = false, x: n entries, y: m) or y = A^H x (x: m, y: n)
+static int normal_half(ga_ctx* c, bool adjoint, const void* x, void* y, bool gated) {
+  if (c->av_cb)
+    return adjoint ? call_op_fn(c, c->atv_cb, x, y, c->normal_m, c->normal_n) : call_op_fn(c, c->av_cb, x, y, c->normal_n, c->normal_m);
+  return spmv_launch(c, adjoint ? c->At : c->A, x, y, gated);
+}
+
 // y = OP x for device vectors of the (local) problem size.
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
@@ -467,18 +482,19 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
     int rc = comm_halo_exchange(c, x);
     if (rc) return rc;
   }
+  if (c->op_kind == 1 && c->op_cb) return call_op_fn(c, c->op_cb, xin, y, c->n, c->n);
   if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated, fused);
   if (c->op_kind == 3) return general_opx(c, xin, y, nullptr);
   if (c->normal_dist) return launch_normal_dist(c, xin, y, gated, fused);
   // normal operator (single GPU): left: y = A^H (A x); right: y = A (A^H x)
   if (c->normal_left) {
-    int rc = spmv_launch(c, c->A, xin, c->xfull, gated);
+    int rc = normal_half(c, false, xin, c->xfull, gated);
     if (rc) return rc;
-    return spmv_launch(c, c->At, c->xfull, y, gated);
+    return normal_half(c, true, c->xfull, y, gated);
   } else {
-    int rc = spmv_launch(c, c->At, xin, c->xfull, gated);
+    int rc = normal_half(c, true, xin, c->xfull, gated);
     if (rc) return rc;
-    return spmv_launch(c, c->A, c->xfull, y, gated);
+    return normal_half(c, false, c->xfull, y, gated);
   }
 }
 
@@ -524,7 +540,7 @@ int launch_normal_half(ga_ctx* c, const void* x, void* y) {
     int rc = comm_halo_exchange(c, x);
     if (rc) return rc;
   }
-  return spmv_launch(c, c->normal_left ? c->A : c->At, x, y, false);
+  return normal_half(c, !c->normal_left, x, y, false);
 }
 
 // Upload a host CSR (int64 rowptr, int32 col, T val) and build the row blocks.

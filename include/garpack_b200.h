@@ -113,6 +113,17 @@ int ga_set_normal_csr(ga_ctx* ctx, int64_t m, int64_t n, const int64_t* rowptr, 
 int ga_set_normal_csr_dist(ga_ctx* ctx, int64_t mt_local, const int64_t* rowptr, const int32_t* col_local,
                            const void* val, int32_t nhalo, const int32_t* recv_counts,
                            const int32_t* send_counts, const int32_t* send_idx, const int32_t* send_dest_off);
+/* Function operators: the caller's own OP*x on DEVICE vectors, the counterpart of ArpackSimpleFunctionOp(F, n)
+ * (src/idonow_ops.jl:360-368, opx!(y, op, x) = op.F(y, x)) and ArpackNormalFunctionOp(av, atv, m, n) (:406-431,
+ * y = atv(av(x)) with the library's scratch vector in between; svds then uses av / atv for the other side's vectors).
+ * The callback must ENQUEUE its work on `cuda_stream` (a cudaStream_t; the stream every kernel of this context runs
+ * on) and return 0; it is called once per OP*x while the library enqueues a batch of Lanczos steps, so it must not
+ * synchronise the device.  x_dev has nx elements, y_dev ny elements of the context's element type; rows beyond ny
+ * of y_dev are padding and must not be written.  Single GPU.  ga_set_normal_op_callbacks needs a context created
+ * with n_global = min(m, n), like ga_set_normal_csr. */
+typedef int (*ga_op_fn)(void* user, const void* x_dev, void* y_dev, int64_t nx, int64_t ny, void* cuda_stream);
+int ga_set_op_callback(ga_ctx* ctx, ga_op_fn opx, void* user);
+int ga_set_normal_op_callbacks(ga_ctx* ctx, int64_t m, int64_t n, ga_op_fn av, ga_op_fn atv, void* user);
 /* Generalised symmetric problem A x = lambda B x in ARPACK's "regular inverse" mode 2 with bmat = :G:
  * the reference's ArpackSymmetricGeneralizedOp(A, S, B) (src/idonow_ops.jl:462-492), reached by
  * eigs(Symmetric(A), Symmetric(B), k) (src/interface.jl:143-163).  A and B are n x n full (both triangles)

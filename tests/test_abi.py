@@ -43,6 +43,31 @@ def test_python_mirror_surface(pkg):
         pkg.symeigs(op, 5, ncv=5)   # nev >= ncv (src/interface.jl:232)
 
 
+def test_python_mirror_types_and_function_ops(pkg):
+    """leading element-type arguments like the reference's symeigs(TV, TF, op, nev) (src/interface.jl:215), parsed
+    before any device work, and the function-operator types of src/idonow_ops.jl:360-431"""
+    assert pkg._type_arg(np.float32) == pkg.GA_F32 and pkg._type_arg("Float32".lower()) == pkg.GA_F32
+    assert pkg._type_arg(np.float64) == pkg.GA_F64 and pkg._type_arg(np.complex128) == pkg.GA_C64
+    assert pkg._type_arg("dd") == pkg.GA_DD and pkg._type_arg(3) is None and pkg._type_arg(np.zeros(2)) is None
+    A = sp.identity(30, format="csr")
+    with pytest.raises(ValueError):
+        pkg.eigs(np.float64, np.float32, A, 3)              # TF narrower than TV
+    with pytest.raises(ValueError):
+        pkg.eigs(np.float32, A, 3, dtype="f64")             # conflicting element types
+    with pytest.raises(TypeError):
+        pkg.eigs(np.float32)
+    assert pkg.ArpackSimpleOp(A.astype(np.float32)).dtype == pkg.GA_F32
+    assert pkg.ArpackSimpleOp(A, dtype="f32").val.dtype == np.float32
+    fop = pkg.ArpackSimpleFunctionOp(lambda y, x: None, 12)
+    assert fop.size() == 12 and fop.arpack_mode == 1 and fop.bmat == "I" and not fop.normal
+    nop = pkg.ArpackNormalFunctionOp(lambda y, x: None, lambda y, x: None, 20, 8, dtype="c64")
+    assert nop.size() == 8 and nop.At_side == "left" and nop.normal and nop.dtype == pkg.GA_C64
+    gop = pkg.ArpackSymmetricGeneralizedOp(A, 2 * A)
+    assert gop.arpack_mode == 2 and gop.bmat == "G" and gop.is_arpack_mode_valid_for_op(2) and not gop.is_arpack_mode_valid_for_op(1)
+    v = pkg._DevVec(4096, 5, pkg.GA_C64).__cuda_array_interface__
+    assert v["shape"] == (5,) and v["typestr"] == "<c16" and v["data"] == (4096, False)
+
+
 def test_no_cpu_fallback(pkg):
     """Without a CUDA device ga_create must fail (GA_ERR_CUDA); eigs must raise, not compute."""
     L = pkg.lib()

@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid", "ga_bnorm_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_host_tridiag_eig", "ga_host_ritz_and_bounds", "ga_host_sort_pair", "ga_host_select_shifts", "ga_host_count_converged", "ga_host_chase_shifts", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -135,6 +135,12 @@ def lib():
         L.ga_debug_spmv_check.argtypes = [vp, vp]
         L.ga_tune_spmv.argtypes = [vp, i32, i32]
         L.ga_symeigs.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
+        L.ga_host_tridiag_eig.argtypes = [i32, i32, vp, vp, vp, i32, i32]
+        L.ga_host_ritz_and_bounds.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp]
+        L.ga_host_sort_pair.argtypes = [i32, i32, i32, vp, vp]
+        L.ga_host_select_shifts.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
+        L.ga_host_count_converged.argtypes = [i32, i32, vp, vp, vp]
+        L.ga_host_chase_shifts.argtypes = [i32, i32, i32, vp, vp, i32, vp, i32]
         L.ga_symeigs_begin.argtypes = [vp, i32, i32, vp, i32, vp]
         L.ga_symeigs_iterate.argtypes = [vp, i32]
         L.ga_symeigs_end.argtypes = [vp, i32, vp, vp, vp, i64, vp]

@@ -298,6 +298,47 @@ int ga_symeigs_end(ga_ctx* c, int ritzvec, void* values, void* bounds, void* vec
   return rc;
 }
 
+// ---- host-only pieces of the control flow (csrc/host/*.hpp), exported so that CPU tests can hold them against the
+// oracle and the reference's analytic known answers without a device.  use_dd != 0: reals are (hi, lo) pairs.
+#define GA_HOST_DISPATCH(expr_double, expr_dd) \
+  try {                                        \
+    if (use_dd) { expr_dd; } else { expr_double; } \
+  } catch (const std::exception&) {            \
+    return GA_ERR_TRIDIAG;                     \
+  }                                            \
+  return 0
+
+int ga_host_tridiag_eig(int use_dd, int n, void* d, void* e, void* z, int want_full, int ldz) {
+  if (n < 1 || !d || !z || (n > 1 && !e) || (want_full && ldz < n)) return GA_ERR_ARG;
+  const host::Vecs w = want_full ? host::Vecs::Full : host::Vecs::LastRow;
+  GA_HOST_DISPATCH((host::TridiagEig<double>(n, (double*)d, (double*)e, (double*)z, want_full ? ldz : 1, w).solve()),
+                   (host::TridiagEig<ddbl>(n, (ddbl*)d, (ddbl*)e, (ddbl*)z, want_full ? ldz : 1, w).solve()));
+}
+int ga_host_ritz_and_bounds(int use_dd, const void* rnorm, int n, const void* H, int ldh, void* eig, void* bounds, void* work) {
+  if (n < 1 || !rnorm || !H || !eig || !bounds || !work || ldh < n) return GA_ERR_ARG;
+  GA_HOST_DISPATCH((host::ritz_and_bounds<double>(*(const double*)rnorm, n, (const double*)H, ldh, (double*)eig, (double*)bounds, (double*)work)),
+                   (host::ritz_and_bounds<ddbl>(*(const ddbl*)rnorm, n, (const ddbl*)H, ldh, (ddbl*)eig, (ddbl*)bounds, (ddbl*)work)));
+}
+int ga_host_sort_pair(int use_dd, int which, int n, void* x1, void* x2) {
+  if (n < 0 || !x1 || !x2 || which < GA_LM || which > GA_SA) return GA_ERR_ARG;
+  GA_HOST_DISPATCH((host::sort_pair<double>(which, n, (double*)x1, (double*)x2)), (host::sort_pair<ddbl>(which, n, (ddbl*)x1, (ddbl*)x2)));
+}
+int ga_host_select_shifts(int use_dd, int ishift, int which, int kev, int np, void* ritz, void* bounds, void* shifts) {
+  if (kev < 0 || np < 0 || !ritz || !bounds || !shifts || which < GA_LM || which > GA_BE) return GA_ERR_ARG;
+  GA_HOST_DISPATCH((host::select_shifts<double>(ishift, which, kev, np, (double*)ritz, (double*)bounds, (double*)shifts)),
+                   (host::select_shifts<ddbl>(ishift, which, kev, np, (ddbl*)ritz, (ddbl*)bounds, (ddbl*)shifts)));
+}
+int ga_host_count_converged(int use_dd, int n, const void* ritz, const void* bounds, const void* tol) {
+  if (n < 0 || !ritz || !bounds || !tol) return GA_ERR_ARG;
+  if (use_dd) return host::count_converged<ddbl>(n, (const ddbl*)ritz, (const ddbl*)bounds, *(const ddbl*)tol);
+  return host::count_converged<double>(n, (const double*)ritz, (const double*)bounds, *(const double*)tol);
+}
+int ga_host_chase_shifts(int use_dd, int kev, int np, const void* shift, void* H, int ldh, void* Q, int ldq) {
+  if (kev < 1 || np < 0 || !shift || !H || !Q || ldh < kev + np || ldq < kev + np) return GA_ERR_ARG;
+  GA_HOST_DISPATCH((host::chase_shifts<double>(kev, np, (const double*)shift, (double*)H, ldh, (double*)Q, ldq)),
+                   (host::chase_shifts<ddbl>(kev, np, (const ddbl*)shift, (ddbl*)H, ldh, (ddbl*)Q, ldq)));
+}
+
 int ga_symeigs(ga_ctx* c, int which, int nev, const double* tol, int maxiter, const void* v0_host, int ritzvec,
                void* values, void* bounds, void* vectors_host, int64_t ldz, int64_t iparam_out[11]) {
   const double t0 = hnow();

@@ -205,6 +205,25 @@ int ga_bnorm_resid(ga_ctx* ctx, double* out);
 int ga_get_stats(const ga_ctx* ctx, ga_stats* out);
 int ga_reset_stats(ga_ctx* ctx);
 
+/* ---- host-only pieces of the control flow -------------------------------------------------------
+ * The O(ncv^2) scalar work BASELINE.json's north_star keeps on the host (with Julia it is the reference's own
+ * code; here csrc/host/*.hpp mirrors it for ga_symeigs*).  Exported without any device dependency so that the
+ * `-m "not gpu"` tests can hold it against the oracle and the reference's analytic known answers.
+ * use_dd = 0: reals are double; != 0: (hi, lo) pairs.  Return 0, GA_ERR_ARG, or GA_ERR_TRIDIAG (-8).
+ *   ga_host_tridiag_eig     dstqrb! (src/dstqrb.jl:607-1052; z[n] <- last row of the eigenvector matrix) and, with
+ *                           want_full, simple_dsteqr! (src/simple.jl; z[ldz x n] <- eigenvectors); d, e overwritten
+ *   ga_host_ritz_and_bounds dseigt! (src/simple.jl:968-1035): H is ldh x 2 (col 0 sub-diagonal, col 1 diagonal)
+ *   ga_host_sort_pair       dsortr (src/simple.jl:255-308), companion array always applied
+ *   ga_host_select_shifts   dsgets (src/simple.jl:603-702)
+ *   ga_host_count_converged dsconv (src/simple.jl:37-80); returns nconv
+ *   ga_host_chase_shifts    the bulge chase of dsapps! (src/dsapps.jl:609-805): H updated, Q (ldq x kplusp) formed */
+int ga_host_tridiag_eig(int use_dd, int n, void* d, void* e, void* z, int want_full, int ldz);
+int ga_host_ritz_and_bounds(int use_dd, const void* rnorm, int n, const void* H, int ldh, void* eig, void* bounds, void* work);
+int ga_host_sort_pair(int use_dd, int which, int n, void* x1, void* x2);
+int ga_host_select_shifts(int use_dd, int ishift, int which, int kev, int np, void* ritz, void* bounds, void* shifts);
+int ga_host_count_converged(int use_dd, int n, const void* ritz, const void* bounds, const void* tol);
+int ga_host_chase_shifts(int use_dd, int kev, int np, const void* shift, void* H, int ldh, void* Q, int ldq);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * ga_timer_start/stop: CUDA events recorded on the library's own stream (the stream every kernel of
  * this context is launched on); stop synchronises and returns milliseconds.

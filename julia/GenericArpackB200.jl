@@ -15,9 +15,10 @@ import GenericArpack: ArpackOp, ArpackNormalSVDOp, AbstractArpackState, ArpackSt
                       _adjust_nev_which_for_svd, _adjust_eigenvalues_to_singular_values!
 
 const lib = "libgarpack_b200.so"
-const GA_F64, GA_C64, GA_DD = Cint(0), Cint(1), Cint(2)
+const GA_F64, GA_C64, GA_DD, GA_F32 = Cint(0), Cint(1), Cint(2), Cint(3)
 ga_dtype(::Type{Float64}) = GA_F64
 ga_dtype(::Type{ComplexF64}) = GA_C64
+ga_dtype(::Type{Float32}) = GA_F32      # Float32 vectors; the state stays B200ArpackState{Float64}: eigs(Float32, Float64, op, k)
 # DoubleFloats.Double64 is two adjacent Float64 (hi, lo): pass pointers as-is with GA_DD.
 
 check(rc, ctx) = rc < -99 ? error("garpack_b200: ", unsafe_string(ccall((:ga_last_error, lib), Cstring, (Ptr{Cvoid},), ctx))) : rc
@@ -233,5 +234,30 @@ symeigs(::Type{TV}, ::Type{TF}, op::B200GeneralizedOp{TV}, nev::Integer; ncv::In
   V = DeviceMatrix{TV}(op.ctx, op.n, ncv); resid = DeviceVector{TV}(op.ctx, op.n); workd = DeviceVector{TV}(op.ctx, 3op.n)
   GenericArpack._symeigs_with_arrays(TV, TF, op, nev, V, resid, workd; ncv, state, kwargs...)
 end
+
+# ---- function operators (src/idonow_ops.jl:360-368): the user's opx! as a callback on DEVICE vectors.  `F(y, x, stream)`
+# receives CuPtr-backed views (e.g. CUDA.unsafe_wrap(CuArray, ...)) and must launch its kernels on `stream`.
+mutable struct B200FunctionOp{T} <: ArpackOp
+  ctx::Ptr{Cvoid}; n::Int; ncv::Int; F::Function; cfun::Base.CFunction
+end
+function _op_thunk(user::Ptr{Cvoid}, x::Ptr{Cvoid}, y::Ptr{Cvoid}, nx::Int64, ny::Int64, stream::Ptr{Cvoid})::Cint
+  op = unsafe_pointer_to_objref(user)::B200FunctionOp
+  try op.F(y, x, nx, ny, stream); return Cint(0) catch; return Cint(1) end
+end
+function B200FunctionOp(::Type{T}, F::Function, n::Int, ncv::Int; device::Int=0) where T
+  ctxref = Ref{Ptr{Cvoid}}(C_NULL)
+  rc = ccall((:ga_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Cint, Int64, Int64, Int64, Cint, Cint, Cint, Cint),
+             ctxref, ga_dtype(T), n, n, 0, ncv, device, 0, 1)
+  rc == 0 || error("ga_create failed ($rc)")
+  cfun = @cfunction(_op_thunk, Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}))
+  op = B200FunctionOp{T}(ctxref[], n, ncv, F, cfun)
+  check(ccall((:ga_set_op_callback, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Any), op.ctx, cfun, op), op.ctx)
+  finalizer(o -> ccall((:ga_destroy, lib), Cvoid, (Ptr{Cvoid},), o.ctx), op)
+  return op
+end
+Base.size(op::B200FunctionOp) = op.n
+arpack_mode(::B200FunctionOp) = 1
+bmat(::B200FunctionOp) = Val(:I)
+is_arpack_mode_valid_for_op(mode::Int, ::B200FunctionOp) = mode == 1
 
 end # module

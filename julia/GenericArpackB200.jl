@@ -238,7 +238,7 @@ end
 # ---- function operators (src/idonow_ops.jl:360-368): the user's opx! as a callback on DEVICE vectors.  `F(y, x, stream)`
 # receives CuPtr-backed views (e.g. CUDA.unsafe_wrap(CuArray, ...)) and must launch its kernels on `stream`.
 mutable struct B200FunctionOp{T} <: ArpackOp
-  ctx::Ptr{Cvoid}; n::Int; ncv::Int; F::Function; cfun::Base.CFunction
+  ctx::Ptr{Cvoid}; n::Int; ncv::Int; F::Function; cfun::Ptr{Cvoid}
 end
 function _op_thunk(user::Ptr{Cvoid}, x::Ptr{Cvoid}, y::Ptr{Cvoid}, nx::Int64, ny::Int64, stream::Ptr{Cvoid})::Cint
   op = unsafe_pointer_to_objref(user)::B200FunctionOp

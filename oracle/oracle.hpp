@@ -31,6 +31,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dd.hpp"
@@ -42,6 +43,7 @@ using cplx = std::complex<double>;
 
 // ------------------------------------------------------------------ scalar helpers
 static inline double abs(double x) { return std::fabs(x); }
+static inline double abs(float x) { return std::fabs((double)x); }   // abs feeding a Float64 accumulator
 static inline double abs(std::complex<double> x) { return std::abs(x); }
 static inline double sqrt(double x) { return std::sqrt(x); }
 static inline bool isnan(double x) { return std::isnan(x); }
@@ -71,6 +73,15 @@ template <> struct vt<double> {
   static constexpr bool is_complex = false;
   static double re(double x) { return x; }
   static double conj(double x) { return x; }
+};
+// Float32 vectors with a Float64 factorisation: symeigs(Float32, Float64, op, nev) (src/interface.jl:26-34).  Element
+// arithmetic (dot products, axpy, products of the sparse matrix) runs in binary32 like the reference's
+// mul!(::Vector{Float32}, ...) calls; H, norms and every host quantity are Float64 (TR = TF).
+template <> struct vt<float> {
+  using real_t = double;
+  static constexpr bool is_complex = false;
+  static double re(float x) { return (double)x; }
+  static float conj(float x) { return x; }
 };
 template <> struct vt<cplx> {
   using real_t = double;
@@ -269,6 +280,18 @@ static TA norm2_lassq(const TA* v, i64 n) {
 static inline double norm2(const double* v, i64 n) { return mynorm_x87(v, n); }        // :368
 static inline double norm2(const cplx* v, i64 n) { return mynorm_x87((const double*)v, 2 * n); }  // :369
 static inline dd norm2(const dd* v, i64 n) { return norm2_lassq<dd>(v, n); }           // :355-365
+static inline double norm2(const float* v, i64 n) {   // norm2(Float64, ::Vector{Float32}): _dlassq with TA = Float64 (:333-365)
+  if (n == 1) return std::fabs((double)v[0]);
+  double scale = 0.0, ssq = 1.0;
+  for (i64 i = 0; i < n; ++i) {
+    if (v[i] != 0.0f) {
+      const double absxi = std::fabs((double)v[i]);
+      if (scale < absxi) { const double val = scale / absxi; ssq = 1.0 + ssq * val * val; scale = absxi; }
+      else { const double val = absxi / scale; ssq += val * val; }
+    }
+  }
+  return scale * std::sqrt(ssq);
+}
 
 // ------------------------------------------------------------------ dlascl / dscal
 // src/arpack-blas.jl:25-59
@@ -303,23 +326,30 @@ static void dlascl_factor(TR cfrom, TR cto, TR& mul, TR& cfromc, TR& ctoc, bool&
   }
 }
 // src/arpack-blas.jl:61-72
+// v .*= a as the reference's broadcast!(*, v, v, a) evaluates it: for Float32 vectors and a Float64 factor the
+// product is formed in Float64 and rounded on store
+template <class T, class TS>
+static inline T scale_elem(T v, TS a) {
+  if constexpr (std::is_same<T, float>::value) return (float)((double)v * (double)a);
+  else return v * T(a);
+}
 template <class T, class TR>
 static void scale_from_to(TR from, TR to, T* v, i64 n) {
   if (from == to) return;
   TR mul, cfromc, ctoc;
   bool done;
   dlascl_factor(from, to, mul, cfromc, ctoc, done);
-  for (i64 i = 0; i < n; ++i) v[i] = v[i] * T(mul);
+  for (i64 i = 0; i < n; ++i) v[i] = scale_elem(v[i], mul);
   while (!done) {
     TR f = cfromc, t = ctoc;
     dlascl_factor(f, t, mul, cfromc, ctoc, done);
-    for (i64 i = 0; i < n; ++i) v[i] = v[i] * T(mul);
+    for (i64 i = 0; i < n; ++i) v[i] = scale_elem(v[i], mul);
   }
 }
 template <class T, class TS>
 static void dscal(TS a, T* v, i64 n) {  // src/arpack-blas.jl:74-76
 #pragma omp parallel for schedule(static) if (n > 100000)
-  for (i64 i = 0; i < n; ++i) v[i] = v[i] * T(a);
+  for (i64 i = 0; i < n; ++i) v[i] = scale_elem(v[i], a);
 }
 template <class T>
 static void vcopy(T* dst, const T* src, i64 n) {
@@ -910,7 +940,10 @@ static int dgetv0(Problem<T>& P, int itry, bool initv, int j) {
   double t0 = now_s();
   T* resid = P.resid.data(); T* workd = P.workd.data(); const T* V = P.V.data();
   int ierr = 0, iter = 0;
-  if (!initv) dlarnv_idist_2<T>(P.iseed, n, resid);                 // :551-553
+  if (!initv) {                                                     // :551-553
+    if constexpr (std::is_same<T, float>::value) dlarnv_idist_2_f32(P.iseed, n, resid);
+    else dlarnv_idist_2<T>(P.iseed, n, resid);
+  }
   TR rnorm0;
   if (G) {
     P.stats.nopx++;                                                 // :566-576: force the vector into the range of OP

@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-F64, C64, DD = 0, 1, 2
+F64, C64, DD, F32 = 0, 1, 2, 3   # F32: Float32 vectors with a Float64 factorisation (symeigs(Float32, Float64, ...))
 WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
 
 
@@ -82,7 +82,7 @@ def _p(a):
 
 
 def np_dtype(dtype):
-    return np.complex128 if dtype == C64 else np.float64
+    return np.complex128 if dtype == C64 else (np.float32 if dtype == F32 else np.float64)
 
 
 def elem_shape(dtype):

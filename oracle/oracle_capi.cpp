@@ -28,6 +28,7 @@ template <> dd make_real<dd>(const double* p) { return dd(p[0], p[1]); }
     case 0: { using T = double; auto* H_ = (Handle<T>*)(h); CALL; } break; \
     case 1: { using T = cplx; auto* H_ = (Handle<T>*)(h); CALL; } break;   \
     case 2: { using T = dd; auto* H_ = (Handle<T>*)(h); CALL; } break;     \
+    case 3: { using T = float; auto* H_ = (Handle<T>*)(h); CALL; } break;  \
     default: break;                                                    \
   }
 
@@ -52,6 +53,7 @@ void* oracle_create(int dtype, long long n, int ncv, const long long* rowptr, co
       MK(0, double)
       MK(1, cplx)
       MK(2, dd)
+      MK(3, float)
 #undef MK
     }
   } catch (...) {
@@ -107,6 +109,7 @@ void oracle_get_rnorm(void* h, double* out) {
   switch (((HandleBase*)h)->dtype) {
     case 0: out[0] = ((Handle<double>*)h)->P->rnorm; out[1] = 0; break;
     case 1: out[0] = ((Handle<cplx>*)h)->P->rnorm; out[1] = 0; break;
+    case 3: out[0] = ((Handle<float>*)h)->P->rnorm; out[1] = 0; break;
     case 2: out[0] = ((Handle<dd>*)h)->P->rnorm.hi; out[1] = ((Handle<dd>*)h)->P->rnorm.lo; break;
   }
 }
@@ -114,6 +117,7 @@ void oracle_set_rnorm(void* h, const double* in) {
   switch (((HandleBase*)h)->dtype) {
     case 0: ((Handle<double>*)h)->P->rnorm = in[0]; break;
     case 1: ((Handle<cplx>*)h)->P->rnorm = in[0]; break;
+    case 3: ((Handle<float>*)h)->P->rnorm = in[0]; break;
     case 2: ((Handle<dd>*)h)->P->rnorm = dd(in[0], in[1]); break;
   }
 }
@@ -197,6 +201,7 @@ void oracle_norm2(int dtype, const void* x, long long n, double* out) {
   switch (dtype) {
     case 0: out[0] = norm2((const double*)x, n); break;
     case 1: out[0] = norm2((const cplx*)x, n); break;
+    case 3: out[0] = norm2((const float*)x, n); break;
     case 2: { dd r = norm2((const dd*)x, n); out[0] = r.hi; out[1] = r.lo; } break;
   }
 }

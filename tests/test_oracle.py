@@ -357,6 +357,45 @@ def test_kat_double64(O):
     assert max(abs(g - e) / e for g, e in zip(got, exact)) < mp.mpf(10) ** -28
 
 
+def test_kat_float32_vectors(O, syn):
+    """Float32 vectors with a Float64 factorisation, symeigs(Float32, Float64, op, nev) (src/interface.jl:26-34):
+    the reference's own Float32 bars -- `vals ≈ Float32.(...)` on the 15 x 15 KAT with which = :LA
+    (test/interface_simple.jl:36-49) and the docstring example symeigs(Float32, ArpackSimpleOp(Diagonal(1.0:n)), 5;
+    which=:SA) (src/interface.jl:105-106) -- plus the start vector (binary32 dlarnv), a lock step against the Float64
+    instantiation and the analytic 2-D Laplacian."""
+    A = kat15()
+    w = np.linalg.eigvalsh(A.toarray())
+    r = O.Oracle(A, 15, dtype=O.F32).symeigs(3, which="LA", ritzvec=False)
+    assert r["info"] == 0 and np.allclose(r["values"], np.sort(w)[-3:], rtol=1e-5)
+    r = O.Oracle(A, 15, dtype=O.F32).symeigs(3, tol=2.0 ** -24)
+    assert r["vectors"].dtype == np.float32
+    Z = r["vectors"].astype(np.float64)
+    assert np.allclose(r["values"], _top(w, 3), rtol=1e-5)
+    assert np.max(np.abs(A @ Z - Z * r["values"])) <= 2e-5 and np.max(np.abs(Z.T @ Z - np.eye(3))) <= 1e-5
+    D = sp.diags(np.arange(1.0, 101.0)).tocsr()
+    r = O.Oracle(D, 20, dtype=O.F32).symeigs(5, which="SA", tol=2.0 ** -24)
+    assert r["info"] == 0 and np.allclose(r["values"], np.arange(1.0, 6.0), rtol=1e-5)
+    m = 60
+    L = syn.to_scipy(syn.laplacian2d(m))
+    r = O.Oracle(L, 40, dtype=O.F32).symeigs(10, tol=2.0 ** -24)
+    exact = syn.laplacian2d_eigs(m, 10)
+    assert r["info"] == 0 and np.max(np.abs(r["values"] - exact) / exact) <= 1e-6
+    o32 = O.Oracle(L, 12, dtype=O.F32)
+    assert o32.dgetv0(1, False, 1) == 0
+    ref, seed, _ = O.dlarnv_f32(m * m)
+    assert np.asarray(o32.resid).tobytes() == ref.tobytes() and tuple(o32.iseed) == seed
+    v0 = np.asarray(o32.resid).astype(np.float64).copy()
+    assert o32.dsaitr(0, 12) == 0
+    o64 = O.Oracle(L, 12)
+    o64.resid[:] = v0
+    o64.dgetv0(1, True, 1)
+    o64.dsaitr(0, 12)
+    assert np.max(np.abs(np.asarray(o32.H) - np.asarray(o64.H))) <= 1e-5
+    V = np.asarray(o32.Vt, dtype=np.float64)
+    assert np.max(np.abs(V @ V.T - np.eye(12))) <= 1e-5
+    assert o32.stats()["nrorth"] == o64.stats()["nrorth"]
+
+
 def test_svds_normal_op(O):
     """test/interface_simple.jl:100-105 style: ArpackNormalOp eigenvalues = squared singular values."""
     rng = np.random.default_rng(5)

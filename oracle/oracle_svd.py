@@ -138,8 +138,10 @@ def eigenvecs_to_singvecs(A, Z):
     return U, V, norms, warnthresh
 
 
-def svds(A, k, which="LM", ncv=None, **kw):
-    """svds(A, k; which) (src/interface.jl:312-337) -> (U, S, V)."""
+def svds(A, k, which="LM", ncv=None, dtype=None, **kw):
+    """svds(A, k; which) (src/interface.jl:312-337) -> (U, S, V).  dtype = oracle.F32: svds(Float32, op, k) -- the
+    eigen-solve runs on Float32 vectors with tol = eps(Float32)/2 (what TF = Float32 gives in the reference); the
+    vector post-processing below is carried out in Float64 on the widened eigenvectors."""
     import scipy.sparse as sp
 
     A = sp.csr_matrix(A)
@@ -148,7 +150,9 @@ def svds(A, k, which="LM", ncv=None, **kw):
     arwhich = {"LM": "LM", "LA": "LM", "SM": "SA", "SA": "SA", "BE": "BE"}[which]   # src/idonow_ops.jl:240-253
     if ncv is None:
         ncv = min(size, max(2 * k, 20))
-    ora = O.Oracle(A, ncv, normal=True)
+    if dtype == O.F32:
+        kw.setdefault("tol", 2.0 ** -24)
+    ora = O.Oracle(A, ncv, normal=True, dtype=dtype)
     res = ora.symeigs(k, which=arwhich, **kw)
     if res["info"] not in (0, 1) or res["values"] is None:
         raise ArithmeticError("symmetric aupd gave error code info=%d" % res["info"])

@@ -69,6 +69,18 @@ def test_golden_arpack_svd_example():
     check_svd(A, U, s, V, tol=3)
 
 
+def test_golden_arpack_svd_example_float32():
+    """svds(Float32, op, 4; ncv=10) ≈ [4.10123E-02, 6.04880E-02, 1.17844E-01, 5.57234E-01] (test/interface_simple.jl:221-222)"""
+    from oracle import oracle as O
+
+    A = arpack_svd_example()
+    U, s, V, res = OS.svds(sp.csr_matrix(A), 4, ncv=10, dtype=O.F32)
+    gold = sorted(GOLD["svds_arpack_example_500x100_float32"]["values"], reverse=True)
+    assert res["vectors"].dtype == np.float32
+    assert np.allclose(s, gold, rtol=2e-4)            # Julia's ≈ on Float32: rtol = sqrt(eps(Float32)) = 3.5e-4
+    assert np.max(np.abs(A @ V - U * s)) <= 1e-4
+
+
 def test_wide_matrix_right_side():
     A = mytestmat(10, 8).T.tocsr()          # m <= n: OP = A A', eigenvectors are U
     U, s, V, _ = OS.svds(A, 2, which="BE")

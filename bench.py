@@ -342,6 +342,12 @@ def run_reference(args):
         return
     syn = importlib.import_module(entry.load_package().__name__ + ".synthetic")
     O = entry.load_oracle()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; only rank 0 works here, with all the host cores it may use
+        try:
+            O.set_num_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            O.set_num_threads(os.cpu_count() or 1)
     m, nev, ncv = args.m, args.nev, args.ncv
     n = m * m
     A = syn.to_scipy(syn.laplacian2d(m))

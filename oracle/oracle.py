@@ -73,6 +73,7 @@ def lib():
         L.oracle_dseigt.argtypes = [dbl, i32, vp, i32, vp, vp, vp]
         L.oracle_dd_op.argtypes = [i32, vp, vp, vp]
         L.oracle_num_threads.restype = i32
+        L.oracle_set_num_threads.argtypes = [i32]
         _LIB = L
     return _LIB
 
@@ -374,6 +375,12 @@ class Oracle:
         out.update(values=d, vectors=Z, ierr=ierr, bounds=self.workl[5 * ncv : 5 * ncv + out["nconv"]].copy(),
                    stats=self.stats())
         return out
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's sweeps / SpMV (torchrun exports OMP_NUM_THREADS=1 to every rank; the
+    reference arm of bench.py runs on rank 0 alone and may use all host cores)."""
+    lib().oracle_set_num_threads(int(n))
 
 
 def num_threads():

@@ -235,6 +235,13 @@ void oracle_dd_op(int op, const double* a, const double* b, double* out) {
   switch (op) { case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = x / y; break; default: r = sqrt(x); }
   out[0] = r.hi; out[1] = r.lo;
 }
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int oracle_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

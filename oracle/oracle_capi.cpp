@@ -148,6 +148,7 @@ int oracle_dsaitr(void* h, int k, int np) {
 }
 // shifts: np reals (2 doubles each for Double64).  H in workl[0:2ncv), Q in workl[4ncv : 4ncv+ncv^2).
 void oracle_dsapps(void* h, int kev, int np, const void* shifts) {
+  if (kev < 1 || np < 1) return;   // outside dsapps!'s domain: dsaup2! never calls it with np = 0 (H[kev+1,1] would not exist)
   DISPATCH(h, {
     using TR = typename vt<T>::real_t;
     int ncv = H_->P->ncv;

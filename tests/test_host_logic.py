@@ -220,3 +220,36 @@ def test_tridiag_fuzz_bitwise_vs_oracle(pkg, O):
         d, z = host_tridiag(pkg, d0, e0)
         do, zo = O.dstqrb(d0, e0)
         assert np.array_equal(d, do) and np.array_equal(np.abs(z), np.abs(zo))
+
+
+def test_chase_shifts_fuzz_bitwise_vs_oracle(pkg, O):
+    """300 random Lanczos tridiagonals (exact zeros and 1e-18 couplings that trigger the splitting / deflation logic of
+    src/dsapps.jl:661-673,781-805, diagonal scales 1e-3..1e3, exact or arbitrary shifts): H and the first kev+1 columns of Q
+    from the product's bulge chase equal the oracle's dsapps! bit for bit."""
+    rng = np.random.default_rng(7)
+    oracles = {}
+    for _ in range(300):
+        kev, np_ = int(rng.integers(1, 20)), int(rng.integers(1, 25))
+        k = kev + np_
+        if k not in oracles:
+            oracles[k] = O.Oracle(sp.diags(np.arange(1.0, k + 3)).tocsr(), k)
+        o = oracles[k]
+        H = np.zeros((k, 2))
+        H[:, 1] = rng.standard_normal(k) * rng.choice([1, 1e3, 1e-3])
+        H[1:, 0] = np.abs(rng.standard_normal(k - 1))
+        if rng.random() < 0.4:
+            H[rng.integers(1, k, size=2), 0] = 0.0
+        if rng.random() < 0.3:
+            H[rng.integers(1, k, size=2), 0] = 1e-18
+        T = np.diag(H[:, 1]) + np.diag(H[1:, 0], 1) + np.diag(H[1:, 0], -1)
+        sh = (np.sort(np.linalg.eigvalsh(T))[:np_] if rng.random() < 0.5 else rng.standard_normal(np_)).copy()
+        o.H[...] = H
+        o.resid[:] = 1.0
+        o.dsapps(kev, np_, sh)
+        Hf = np.asfortranarray(H.copy())
+        Q = np.zeros((k, k), order="F")
+        assert pkg.lib().ga_host_chase_shifts(0, kev, np_, _p(sh), _p(Hf), k, _p(Q), k) == 0
+        assert np.array_equal(Hf[:kev + 1], np.asarray(o.H)[:kev + 1])
+        assert np.array_equal(Q[:, :kev + 1], np.asarray(o.Q)[:, :kev + 1])
+        assert np.max(np.abs(Q.T @ Q - np.eye(k))) <= 1e-13
+

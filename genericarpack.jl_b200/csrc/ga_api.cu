@@ -189,7 +189,7 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
 
 int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col, const void* val) {
   if (!c || !rowptr || !col || !val || m <= 0 || n <= 0) return GA_ERR_ARG;
-  if (c->world != 1) return set_err(c, GA_ERR_ARG, "normal operator: multi-GPU sharding not implemented yet");
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "multi-GPU contexts take ga_set_normal_csr_dist (this rank's rows of the tall orientation + halo plan)");
   const bool left = !(m <= n);  // src/idonow_ops.jl:222-235
   if (c->n != (left ? n : m)) return set_err(c, GA_ERR_ARG, "normal operator: context size must be min(m, n) side");
   GA_CUDA(c, cudaSetDevice(c->device));

@@ -207,7 +207,7 @@ int ga_reset_stats(ga_ctx* ctx);
 
 /* ---- host-only pieces of the control flow -------------------------------------------------------
  * The O(ncv^2) scalar work BASELINE.json's north_star keeps on the host (with Julia it is the reference's own
- * code; here csrc/host/*.hpp mirrors it for ga_symeigs*).  Exported without any device dependency so that the
+ * code; here csrc/host/ (tridiag.hpp, irl.hpp) mirrors it for the ga_symeigs family).  Exported without any device dependency so that the
  * `-m "not gpu"` tests can hold it against the oracle and the reference's analytic known answers.
  * use_dd = 0: reals are double; != 0: (hi, lo) pairs.  Return 0, GA_ERR_ARG, or GA_ERR_TRIDIAG (-8).
  *   ga_host_tridiag_eig     dstqrb! (src/dstqrb.jl:607-1052; z[n] <- last row of the eigenvector matrix) and, with

@@ -68,6 +68,26 @@ def test_python_mirror_types_and_function_ops(pkg):
     assert v["shape"] == (5,) and v["typestr"] == "<c16" and v["data"] == (4096, False)
 
 
+def test_header_is_plain_c_and_example_links(pkg, tmp_path):
+    """include/garpack_b200.h is a C header (C99, -pedantic -Werror) and a plain-C caller links against the library;
+    without a device the example reports GA_ERR_CUDA and computes nothing (exit 0), with one it prints eigenvalues."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no gcc")
+    pkg.build()
+    exe = str(tmp_path / "c_abi_example")
+    libdir = os.path.join(ROOT, "genericarpack.jl_b200")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", libdir, "-lgarpack_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    assert "GA_ERR_CUDA" in out.stdout or "lambda[2]" in out.stdout
+
+
 def test_no_cpu_fallback(pkg):
     """Without a CUDA device ga_create must fail (GA_ERR_CUDA); eigs must raise, not compute."""
     L = pkg.lib()

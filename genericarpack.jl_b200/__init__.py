@@ -29,7 +29,7 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libgarpack_b200.so")
+_SO = os.environ.get("GA_B200_LIB") or os.path.join(_HERE, "libgarpack_b200.so")   # GA_B200_LIB: development A/B builds only
 _LIB = None
 
 GA_F64, GA_C64, GA_DD, GA_F32 = 0, 1, 2, 3

@@ -18,6 +18,12 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libgarpack_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# development A/B builds: GA_B200_DEFS="-DGA_DOT2_FAST" GA_B200_VARIANT=alt -> libgarpack_b200_alt.so (loaded with GA_B200_LIB=...)
+EXTRA = os.environ.get("GA_B200_DEFS", "").split()
+_VARIANT = os.environ.get("GA_B200_VARIANT", "")
+if _VARIANT:
+    OBJ = os.path.join(HERE, "build_" + _VARIANT)
+    SO = os.path.join(HERE, "libgarpack_b200_%s.so" % _VARIANT)
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
@@ -33,7 +39,7 @@ def _deps():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     return src, obj, p.returncode, p.stdout
 

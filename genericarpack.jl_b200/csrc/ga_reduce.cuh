@@ -125,6 +125,11 @@ __device__ __forceinline__ double2 warp_sum_slot_fast(double v) {
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
   return make_double2(v, 0.0);
 }
+__device__ __forceinline__ double2 warp_sum_slot_fast(dot2 v) {   // Dot2 accumulator: renormalise, then double-double tree
+  ddbl a;
+  two_sum(v.hi, v.lo, a.hi, a.lo);
+  return warp_sum_slot(a);
+}
 __device__ __forceinline__ double2 warp_sum_slot_fast(cdbl v) { return warp_sum_slot(v); }
 __device__ __forceinline__ double2 warp_sum_slot_fast(ddbl v) { return warp_sum_slot(v); }
 

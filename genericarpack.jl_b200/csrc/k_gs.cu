@@ -22,7 +22,9 @@
 
 namespace ga {
 
-template <class T, int MODE, int SEG>
+// NCT = register accumulators per consumer thread; the launcher picks the smallest instantiation covering j
+// columns (the binary64 kernel's Dot2 accumulators are two doubles each, see ga_types.cuh).
+template <class T, int MODE, int SEG, int NCT>
 __global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
 k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevCtl* ctl, double2* partial,
      int nstages, int gate_phase, int decide_kind, int ncv, const DevComm* cm, unsigned long long* trace, int reverse) {
@@ -63,9 +65,9 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
   __syncthreads();
   GA_TRACE(1, blockIdx.x == 0 && threadIdx.x == 0)
 
-  typename Elem<T>::acc_t acc[NC];
+  typename Elem<T>::acc_t acc[NCT];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
+  for (int i = 0; i < NCT; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
   NormAcc nacc;
   nacc.init();
 
@@ -107,7 +109,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
 #pragma unroll
         for (int q = 0; q < RPT; ++q) p0[q] = Elem<T>::zero();
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
+        for (int i = 0; i < NCT; ++i) {
           const int c = g + TG * i;
           if (c >= j) break;
           const T hc = hs[c];
@@ -130,7 +132,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
       }
       if (MODE != 2) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
+        for (int i = 0; i < NCT; ++i) {
           const int c = g + TG * i;
           if (c >= j) break;
 #pragma unroll
@@ -149,7 +151,7 @@ k_gs(const T* __restrict__ V, i64 ldv, int j, const T* w, T* r, i64 ntiles, DevC
     // warp-level reduction of this warp's accumulators (only the columns this group owns)
     if (MODE != 2) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
+      for (int i = 0; i < NCT; ++i) {
         if (g + TG * i < j) {
           double2 sl = warp_sum_slot_fast(acc[i]);
           if (lane == 0) redw[warp * (NC + 3) + i] = sl;
@@ -217,15 +219,15 @@ __global__ void k_decide(DevCtl* ctl, const double2* gathered, int world, int j,
   gs_decide<T>(ctl, red, j, ncv, decide_kind);
 }
 
-template <class T, int MODE, int SEG>
-static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int nstages) {
+template <class T, int MODE, int SEG, int NCT>
+static int launch_gs_nct(ga_ctx* c, int j, int gate_phase, int decide_kind, int nstages) {
   typedef GsCfg<T, SEG> C;
   const i64 ntiles = c->vs.ld / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
   const size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
   static PerDeviceOnce attr_set;
   if (attr_set.need(c->device)) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
+    GA_CUDA(c, cudaFuncSetAttribute(k_gs<T, MODE, SEG, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
     attr_set.done(c->device);
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
@@ -244,7 +246,7 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
     c->prof_used += 2;
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
-  k_gs<T, MODE, SEG><<<grid, C::THREADS, smem, c->stream>>>(V, c->vs.ld, j, wv, r, ntiles, c->ctl, c->partial, nstages,
+  k_gs<T, MODE, SEG, NCT><<<grid, C::THREADS, smem, c->stream>>>(V, c->vs.ld, j, wv, r, ntiles, c->ctl, c->partial, nstages,
                                                            gate_phase, fused ? decide_kind : DK_NONE, c->ncv,
                                                            c->world > 1 ? c->devcomm : nullptr, c->trace,
                                                            (int)(c->gs_flip++ & 1));
@@ -252,6 +254,18 @@ static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int 
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
   return 0;
+}
+
+template <class T, int MODE, int SEG>
+static int launch_gs_seg(ga_ctx* c, int j, int gate_phase, int decide_kind, int nstages) {
+  typedef GsCfg<T, SEG> C;
+  if (sizeof(T) == 8 && MODE != 2) {   // binary64 sweeps with dots: Dot2 accumulators, register-bound -> three widths
+    if (j <= C::TG * (C::NC / 2))
+      return launch_gs_nct<T, MODE, SEG, (sizeof(T) == 8 && MODE != 2 ? C::NC / 2 : C::NC)>(c, j, gate_phase, decide_kind, nstages);
+    if (j <= C::TG * (3 * C::NC / 4))
+      return launch_gs_nct<T, MODE, SEG, (sizeof(T) == 8 && MODE != 2 ? 3 * C::NC / 4 : C::NC)>(c, j, gate_phase, decide_kind, nstages);
+  }
+  return launch_gs_nct<T, MODE, SEG, C::NC>(c, j, gate_phase, decide_kind, nstages);
 }
 
 template <class T, int MODE>

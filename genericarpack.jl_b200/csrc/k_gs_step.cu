@@ -52,7 +52,10 @@ __device__ __forceinline__ void grid_barrier(DevCtl* ctl) {
   __syncthreads();
 }
 
-template <class T, int SEG>
+// NCT = register accumulators per consumer thread (columns g, g+TG, ... of the thread's group): the launcher
+// picks the smallest instantiation that covers j columns, so short bases do not pay registers for 64 columns
+// (the Dot2 accumulators of the binary64 kernel are two doubles each).
+template <class T, int SEG, int NCT>
 __global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
 k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ctl, double2* partial, int nstages,
           int ncv, const DevComm* cm, unsigned long long* trace, int xprefetch) {
@@ -158,9 +161,9 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       }
     } else {
       // ---------------- consumers
-      typename Elem<T>::acc_t acc[NC];
+      typename Elem<T>::acc_t acc[NCT];
 #pragma unroll
-      for (int i = 0; i < NC; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
+      for (int i = 0; i < NCT; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
       NormAcc nacc;
       nacc.init();
       int itc = it;
@@ -178,7 +181,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
 #pragma unroll
           for (int q = 0; q < RPT; ++q) p0[q] = Elem<T>::zero();
 #pragma unroll
-          for (int i = 0; i < NC; ++i) {
+          for (int i = 0; i < NCT; ++i) {
             const int c = g + TG * i;
             if (c >= j) break;
             const T hc = hs[c];
@@ -201,7 +204,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
         }
         if (mode != 2) {
 #pragma unroll
-          for (int i = 0; i < NC; ++i) {
+          for (int i = 0; i < NCT; ++i) {
             const int c = g + TG * i;
             if (c >= j) break;
 #pragma unroll
@@ -218,7 +221,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       GA_TRACE(2 + 8 * ph, blockIdx.x == 0 && tid == 0)
       if (mode != 2) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
+        for (int i = 0; i < NCT; ++i) {
           if (g + TG * i < j) {
             double2 sl = warp_sum_slot_fast(acc[i]);
             if (lane == 0) redw[warp * (NC + 3) + i] = sl;
@@ -316,15 +319,15 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
 #undef ROWIDX
 }
 
-template <class T, int SEG>
-static int launch_step_seg(ga_ctx* c, int j, int nstages) {
+template <class T, int SEG, int NCT>
+static int launch_step_nct(ga_ctx* c, int j, int nstages) {
   typedef GsCfg<T, SEG> C;
   i64 ntiles = c->n_pad / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
   size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
   static PerDeviceOnce attr_set;
   if (attr_set.need(c->device)) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_gs_step<T, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
+    GA_CUDA(c, cudaFuncSetAttribute(k_gs_step<T, SEG, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
     attr_set.done(c->device);
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
@@ -349,10 +352,20 @@ static int launch_step_seg(ga_ctx* c, int j, int nstages) {
   }
   void* args[] = {(void*)&V, (void*)&ldv, (void*)&j, (void*)&wr, (void*)&ntiles, (void*)&ctl, (void*)&partial,
                   (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace, (void*)&xprefetch};
-  GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
+  GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG, NCT>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
   return 0;
+}
+
+template <class T, int SEG>
+static int launch_step_seg(ga_ctx* c, int j, int nstages) {
+  typedef GsCfg<T, SEG> C;
+  if (sizeof(T) == 8) {   // binary64: Dot2 accumulators, register-bound -> three widths
+    if (j <= C::TG * (C::NC / 2)) return launch_step_nct<T, SEG, (sizeof(T) == 8 ? C::NC / 2 : C::NC)>(c, j, nstages);
+    if (j <= C::TG * (3 * C::NC / 4)) return launch_step_nct<T, SEG, (sizeof(T) == 8 ? 3 * C::NC / 4 : C::NC)>(c, j, nstages);
+  }
+  return launch_step_nct<T, SEG, C::NC>(c, j, nstages);
 }
 
 template <class T>

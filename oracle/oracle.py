@@ -377,6 +377,30 @@ class Oracle:
         return out
 
 
+def set_arith(mode):
+    """"plain" (default: plain binary64 sweeps, x87 norm) or "exact" (error-free dots, the reference's double-double
+    norm variant, fixed update order: the trajectory then does not depend on blocking or thread count)."""
+    lib().oracle_set_arith(1 if mode in (1, "exact") else 0)
+
+
+def get_arith():
+    return "exact" if lib().oracle_get_arith() == 1 else "plain"
+
+
+class arith:
+    """Context manager: `with oracle.arith("exact"): ...`"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_arith()
+        set_arith(self.mode)
+
+    def __exit__(self, *a):
+        set_arith(self.prev)
+
+
 def set_num_threads(n):
     """OpenMP threads of the oracle's sweeps / SpMV (torchrun exports OMP_NUM_THREADS=1 to every rank; the
     reference arm of bench.py runs on rank 0 alone and may use all host cores)."""

@@ -236,6 +236,9 @@ void oracle_dd_op(int op, const double* a, const double* b, double* out) {
   switch (op) { case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = x / y; break; default: r = sqrt(x); }
   out[0] = r.hi; out[1] = r.lo;
 }
+// 0 = plain binary64 sweeps + x87 norm (default), 1 = exact dots / double-double norm / fixed update order (oracle.hpp)
+void oracle_set_arith(int mode) { oracle::arith_mode() = mode == 1 ? oracle::ARITH_EXACT : oracle::ARITH_PLAIN; }
+int oracle_get_arith() { return oracle::arith_mode(); }
 void oracle_set_num_threads(int n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);

@@ -38,6 +38,15 @@ int sync_ctl(ga_ctx* c) {
   GA_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
+// Library-level failures recorded by the kernels in the control block (call after sync_ctl): a peer that never
+// raised its flag / a broken grid barrier is GA_ERR_COMM, a non-finite norm GA_ERR_NUMERIC.  ST_BREAKDOWN (an
+// invariant subspace, the reference's rnorm == 0 restart) is not an error and is left to the caller.
+int status_error(ga_ctx* c, const char* where) {
+  const int st = c->ctl_host->status;
+  if (st == ST_COMM) return set_err(c, GA_ERR_COMM, std::string(where) + ": a peer GPU did not answer in time (halo flag / mailbox / grid barrier timeout)");
+  if (st == ST_NUMERIC) return set_err(c, GA_ERR_NUMERIC, std::string(where) + ": non-finite value met on the device");
+  return 0;
+}
 static void host_real_to_pair(const ga_ctx* c, const double* in, double out[2]) {
   out[0] = in[0];
   out[1] = c->dtype == GA_DD ? in[1] : 0.0;
@@ -165,7 +174,18 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
                     const int32_t* send_dest_off) {
   if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
+  if (c->ipc_exported || c->devcomm) return set_err(c, GA_ERR_ARG, "the sharded operator cannot be replaced after ga_comm_ipc_export (peers hold the halo buffer's handle): create a new context");
+  {  // the plan indexes device memory directly: validate it here
+    int ns = 0;
+    for (int q = 0; q < c->world; ++q) {
+      if (send_counts[q] < 0 || recv_counts[q] < 0) return set_err(c, GA_ERR_ARG, "ga_set_csr_dist: negative count in the halo plan");
+      ns += send_counts[q];
+    }
+    for (int k = 0; send_idx && k < ns; ++k)
+      if (send_idx[k] < 0 || send_idx[k] >= c->n) return set_err(c, GA_ERR_ARG, "ga_set_csr_dist: send_idx outside the local rows");
+  }
   clear_operator(c);
+  c->normal_dist = false;
   int rc = csr_upload(c, c->A, c->n, c->n_pad + nhalo, rowptr, col_local, val, 0);
   if (rc) return rc;
   c->send_counts.assign(send_counts, send_counts + c->world);
@@ -238,6 +258,7 @@ int ga_set_normal_csr_dist(ga_ctx* c, int64_t mt_local, const int64_t* rowptr, c
   if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0 || mt_local < 0) return GA_ERR_ARG;
   if (c->world < 2) return set_err(c, GA_ERR_ARG, "single-GPU contexts take ga_set_normal_csr");
   GA_CUDA(c, cudaSetDevice(c->device));
+  if (c->ipc_exported || c->devcomm) return set_err(c, GA_ERR_ARG, "the sharded operator cannot be replaced after ga_comm_ipc_export (peers hold the halo buffer's handle): create a new context");
   clear_operator(c);
   const i64 ncol = c->n_pad + nhalo;                       // local column space [own | halo]
   int rc = csr_upload(c, c->A, mt_local, ncol, rowptr, col_local, val, 0);
@@ -487,6 +508,7 @@ int ga_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm) {
     if (rc) return rc;
     rc = sync_ctl(c);
     if (rc) return rc;
+    if ((rc = status_error(c, "ga_getv0"))) return rc;
     pair_to_host_real(c, c->ctl_host->rnorm, rnorm);
   } else {
     // s = V[:,1:j-1]' r ; r -= V s ; repeat while ||r|| <= 0.717 ||r_prev||, at most 5 refinements
@@ -496,12 +518,14 @@ int ga_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm) {
     double rnorm0[2], rn[2];
     rc = sync_ctl(c);
     if (rc) return rc;
+    if ((rc = status_error(c, "ga_getv0"))) return rc;
     rnorm0[0] = c->ctl_host->rnorm0[0]; rnorm0[1] = c->ctl_host->rnorm0[1];
     while (true) {
       rc = launch_gs(c, 1, j - 1, -1, DK_GETV0_UPD);           // :665,700 (+ next dots)
       if (rc) return rc;
       rc = sync_ctl(c);
       if (rc) return rc;
+      if ((rc = status_error(c, "ga_getv0"))) return rc;
       rn[0] = c->ctl_host->rnorm[0]; rn[1] = c->ctl_host->rnorm[1];
       if (real_gt_717(c, rn, rnorm0)) break;                   // :711
       iter += 1;
@@ -573,7 +597,8 @@ int ga_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, int64_
       c->stats.nopx += jlast - jfirst + 1;
       break;
     }
-    if (hc->status == ST_NUMERIC) return set_err(c, GA_ERR_NUMERIC, "non-finite residual norm in the Lanczos step");
+    if ((rc = status_error(c, "ga_lanczos"))) return rc;
+    if (hc->status != ST_BREAKDOWN) return set_err(c, GA_ERR_CUDA, "ga_lanczos: unknown device status " + std::to_string(hc->status));
     // ---- invariant subspace at step jb: restart with dgetv0 (src/dsaitr.jl:1061-1087,1497-1525)
     const int jb = hc->j_break;
     c->stats.nopx += jb - jfirst;
@@ -601,6 +626,7 @@ int ga_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, int64_
   }
   // results: H rows k..k+np-1 (both columns), rnorm
   if ((rc = sync_ctl(c))) return rc;
+  if ((rc = status_error(c, "ga_lanczos"))) return rc;
   if (hc->zero_resid) {                                         // :1442-1443 on the last step
     if ((rc = launch_zero_resid(c))) return rc;
     GA_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -633,6 +659,7 @@ int ga_apply_shifts(ga_ctx* c, int kev, int np, const void* Q, int ldq, const do
   rc = launch_vq(c, kplusp, nout, true, nullptr, beta, kev);
   if (rc) return rc;
   if ((rc = sync_ctl(c))) return rc;
+  if ((rc = status_error(c, "ga_apply_shifts"))) return rc;
   pair_to_host_real(c, c->ctl_host->rnorm, rnorm_out);
   if (c->op_kind == 3 && (rc = general_resid_bnorm(c, rnorm_out))) return rc;   // bmat = :G: the B-norm (src/dsaup2.jl:1383-1411)
   c->stats.tapps += now_s() - t0;
@@ -697,6 +724,7 @@ int ga_svd_vectors(ga_ctx* c, int nvec, const int32_t* perm, void* w_host, int64
   }
   c->vs = saved;
   if (rc == 0) rc = sync_ctl(c);
+  if (rc == 0) rc = status_error(c, "ga_svd_vectors");
   if (rc == 0 && c->ctl_host->status != ST_OK)
     rc = set_err(c, GA_ERR_NUMERIC, "svd vectors: a column of A*V vanished or is not finite");
   if (rc == 0) {
@@ -723,6 +751,7 @@ int ga_norm2_resid(ga_ctx* c, double* out) {
   if (rc) return rc;
   if ((rc = launch_norm_resid(c, DK_NORM))) return rc;
   if ((rc = sync_ctl(c))) return rc;
+  if ((rc = status_error(c, "ga_norm2_resid"))) return rc;
   pair_to_host_real(c, c->ctl_host->rnorm, out);
   return 0;
 }

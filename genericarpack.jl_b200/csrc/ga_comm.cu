@@ -100,9 +100,10 @@ int comm_ipc_export(ga_ctx* c, void* out128) {
     GA_CUDA(c, cudaMalloc(&c->mbox, sizeof(Mailbox)));
     GA_CUDA(c, cudaMemset(c->mbox, 0, sizeof(Mailbox)));
   }
-  if (!c->halo) {  // a rank without remote columns still needs a valid allocation to export
-    GA_CUDA(c, cudaMalloc(&c->halo, 256));
-  }
+  // The halo buffer is allocated by ga_set_csr_dist / ga_set_normal_csr_dist (at least one element even without
+  // remote columns): the operator comes first, so that the exported allocation is the one the peers will push into.
+  if (!c->halo) return set_err(c, GA_ERR_ARG, "ga_comm_ipc_export: set the sharded operator first (ga_set_csr_dist / ga_set_normal_csr_dist)");
+  c->ipc_exported = true;
   cudaIpcMemHandle_t h[2];
   GA_CUDA(c, cudaIpcGetMemHandle(&h[0], c->mbox));
   GA_CUDA(c, cudaIpcGetMemHandle(&h[1], c->halo));

@@ -177,6 +177,7 @@ struct ga_ctx {
   ga::DevComm* devcomm = nullptr;   // device copy; nullptr -> NCCL fallback (or single GPU)
   ga::DevComm hostcomm{};
   void* ipc_mapped[2 * ga::kMaxWorld] = {nullptr};
+  bool ipc_exported = false;        // the halo buffer's handle is out: the sharded operator can no longer be replaced
 
   // host-side solve state for ga_symeigs_begin/iterate/end
   void* solve = nullptr;
@@ -251,5 +252,6 @@ struct PerDeviceOnce {
 };
 
 int sync_ctl(ga_ctx* c);  // copy DevCtl to the pinned mirror and synchronise the stream
+int status_error(ga_ctx* c, const char* where);  // after sync_ctl: ST_COMM -> GA_ERR_COMM, ST_NUMERIC -> GA_ERR_NUMERIC
 
 }  // namespace ga

@@ -200,6 +200,21 @@ __device__ __forceinline__ double2 ld_sys_d2(const double2* p) {
 __device__ __forceinline__ void st_sys_d2(double2* p, double2 v) {
   asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+// Halo entries are written by the peers with P2P stores while the consuming kernel is already resident and
+// spinning on the sequence flag: they must not travel through the read-only (.nc) path, whose contract is
+// "constant for the kernel's lifetime".  ld.global.cg reads L2 (the point of coherence for peer writes).
+template <class T> __device__ __forceinline__ T ld_halo(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    const float v = __ldcg(reinterpret_cast<const float*>(p));
+    return *reinterpret_cast<const T*>(&v);
+  } else if constexpr (sizeof(T) == 8) {
+    const double v = __ldcg(reinterpret_cast<const double*>(p));
+    return *reinterpret_cast<const T*>(&v);
+  } else {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return *reinterpret_cast<const T*>(&v);
+  }
+}
 // bounded spin: ~seconds; on expiry the status word flags a communication failure instead of hanging
 __device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int want) {
   for (long long it = 0; it < (1LL << 25); ++it) {

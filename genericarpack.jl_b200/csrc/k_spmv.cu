@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
                                                               const int* __restrict__ rowptr,
                                                               const int* __restrict__ col,
                                                               const T* __restrict__ val, const T* __restrict__ x,
-                                                              const T* __restrict__ xh, int nsplit,
-                                                              T* __restrict__ y, const DevCtl* ctl, int gated,
+                                                              const T* xh, int nsplit,
+                                                              T* __restrict__ y, DevCtl* ctl, int gated,
                                                               const DevComm* cm) {
   typedef SpmvCfg<T> C;
   if (gated && ctl->status != ST_OK) return;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
     // fused multi-GPU path: the peers' normalisation kernels push our halo entries; wait for their
     // sequence flags (set after a system-scope fence) before touching xh
     if (threadIdx.x < (unsigned)cm->world && cm->recv_counts[threadIdx.x] > 0)
-      spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq);
+      if (!spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq)) ctl->status = ST_COMM;
     __syncthreads();
   }
   __shared__ T prod[C::CAP];
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
   const int tid = threadIdx.x;
   // x entry for (remapped) column c: own rows live in x[0, nsplit), halo entries received from
   // the peers in xh (single GPU: nsplit = INT_MAX, xh unused)
-  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
+  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : ld_halo(xh + (c - nsplit)); };
   if (k1 - k0 <= C::CAP) {
     // coalesced segment pass, 4 independent gathers in flight per thread
     int k = k0 + tid;
@@ -138,8 +138,8 @@ __device__ __forceinline__ void wait_stage(uint64_t* full_s, const volatile int*
 template <class T, int NG>
 __global__ void __launch_bounds__(SpmvStreamCfg<T, NG>::THREADS, 1)
 k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ rowptr, const int* __restrict__ col,
-              const T* __restrict__ val, const T* __restrict__ x, const T* __restrict__ xh, int nsplit,
-              T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm, int NST, unsigned int* chk) {
+              const T* __restrict__ val, const T* __restrict__ x, const T* xh, int nsplit,
+              T* __restrict__ y, DevCtl* ctl, int gated, const DevComm* cm, int NST, unsigned int* chk) {
   typedef SpmvStreamCfg<T, NG> C;
   constexpr int GT = C::GT, GROUPS = C::GROUPS;
   if (gated && ctl->status != ST_OK) return;
@@ -194,10 +194,10 @@ k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ 
     // fused multi-GPU path: the peers' normalisation kernels push our halo entries; wait for their
     // sequence flags (set after a system-scope fence) before touching xh (the producer warp is
     // already streaming the matrix meanwhile)
-    if (gt < cm->world && cm->recv_counts[gt] > 0) spin_until(&cm->peer[cm->rank]->hflags[gt], ctl->hseq);
+    if (gt < cm->world && cm->recv_counts[gt] > 0 && !spin_until(&cm->peer[cm->rank]->hflags[gt], ctl->hseq)) ctl->status = ST_COMM;
     named_bar_sync(1 + g, GT);
   }
-  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
+  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : ld_halo(xh + (c - nsplit)); };
   int b = b_begin + g;
   int4 d = b < b_end ? __ldg(&desc[b]) : make_int4(0, 0, 0, 0);
   for (int it = g; b < b_end; b += GROUPS, it += GROUPS) {
@@ -255,17 +255,17 @@ k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ 
 template <class T>
 __global__ void __launch_bounds__(256) k_spmv_long(const int* __restrict__ longrow, const int* __restrict__ rowptr,
                                                    const int* __restrict__ col, const T* __restrict__ val,
-                                                   const T* __restrict__ x, const T* __restrict__ xh, int nsplit,
-                                                   T* __restrict__ y, const DevCtl* ctl, int gated, const DevComm* cm) {
+                                                   const T* __restrict__ x, const T* xh, int nsplit,
+                                                   T* __restrict__ y, DevCtl* ctl, int gated, const DevComm* cm) {
   if (gated && ctl->status != ST_OK) return;
   if (cm) {
     if (threadIdx.x < (unsigned)cm->world && cm->recv_counts[threadIdx.x] > 0)
-      spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq);
+      if (!spin_until(&cm->peer[cm->rank]->hflags[threadIdx.x], ctl->hseq)) ctl->status = ST_COMM;
     __syncthreads();
   }
   __shared__ T red[256];
   const int r = longrow[blockIdx.x], k0 = rowptr[r], k1 = rowptr[r + 1], tid = threadIdx.x;
-  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : xh[c - nsplit]; };
+  auto xat = [&](int c) -> T { return c < nsplit ? x[c] : ld_halo(xh + (c - nsplit)); };
   T s = Elem<T>::zero();
   for (int k = k0 + tid; k < k1; k += 256) Elem<T>::add(s, Elem<T>::mul(val[k], xat(col[k])));
   red[tid] = s;
@@ -554,6 +554,13 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
   const int maxrows = SpmvCfg<double>::MAXROWS;
   std::vector<int> rp((size_t)nrows + 1);
   const int64_t base = rowptr[0];
+  // the kernels gather x[col] unchecked: a bad index must be an argument error here, not a device fault there
+  for (i64 i = 0; i < nrows; ++i)
+    if (rowptr[i + 1] < rowptr[i]) return set_err(c, GA_ERR_ARG, "csr: rowptr is not non-decreasing");
+  for (i64 k = 0; k < nnz; ++k) {
+    const i64 cc = (i64)col[base + k] - col_shift;
+    if (cc < 0 || cc >= ncols) return set_err(c, GA_ERR_ARG, "csr: column index outside [0, ncols)");
+  }
   for (i64 i = 0; i <= nrows; ++i) rp[(size_t)i] = (int)(rowptr[i] - base);
   std::vector<int> blk;
   blk.reserve((size_t)(nnz / (cap / 2) + nrows / maxrows + 16));

@@ -134,8 +134,8 @@ def run_b200(args):
 
     def make_ctx():
         if world == 1:
-            return pkg.Context(op, ncv, device=local)
-        ctx = pkg.Context(op, ncv, device=local, rank=rank, world_size=world, n_global=n, row_offset=r0, plan=plan)
+            return pkg.Context(op, ncv, device=local, dots=args.dots)
+        ctx = pkg.Context(op, ncv, device=local, rank=rank, world_size=world, n_global=n, row_offset=r0, plan=plan, dots=args.dots)
         gdist.setup_comm(ctx, pkg.comm_unique_id, rank, world, fused=not args.nccl_only)
         return ctx
 
@@ -404,6 +404,7 @@ def main():
     ap.add_argument("--tts-tol", type=float, default=1e-10, help="tolerance of the time-to-solution solve (north_star: eigenvalues to 1e-10)")
     ap.add_argument("--tts-maxiter", type=int, default=0, help="restart cap of the time-to-solution solve (0: 4 x grid side)")
     ap.add_argument("--tts-budget", type=float, default=420.0, help="wall-clock guard of the time-to-solution solve, seconds")
+    ap.add_argument("--dots", default="exact", choices=["exact", "plain"], help="Float64 dot-product accumulators of the sweeps (library default: exact = Dot2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--trace", action="store_true", help="add the in-kernel timeline of one Gram-Schmidt step kernel (debug)")
     ap.add_argument("--no-cpu", action="store_true")

@@ -38,10 +38,11 @@ _DTYPES = {"f64": GA_F64, "float64": GA_F64, "c64": GA_C64, "complex128": GA_C64
            "f32": GA_F32, "float32": GA_F32,   # Float32 vectors, Float64 factorisation: symeigs(Float32, Float64, ...)
            GA_F64: GA_F64, GA_C64: GA_C64, GA_DD: GA_DD, GA_F32: GA_F32}
 _WHICH = {"LM": 0, "SM": 1, "LA": 2, "SA": 3, "BE": 4}
+GA_OPT_DOT_MODE, GA_DOT_EXACT, GA_DOT_PLAIN = 1, 0, 1   # include/garpack_b200.h
 
 # every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
-    "ga_create", "ga_destroy", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
+    "ga_create", "ga_destroy", "ga_set_option", "ga_get_option", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid", "ga_bnorm_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_host_tridiag_eig", "ga_host_ritz_and_bounds", "ga_host_sort_pair", "ga_host_select_shifts", "ga_host_count_converged", "ga_host_chase_shifts", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
@@ -99,6 +100,8 @@ def lib():
         L.ga_comm_unique_id.argtypes = [vp]
         L.ga_comm_init.argtypes = [vp, vp]
         L.ga_set_csr.argtypes = [vp, vp, vp, vp]
+        L.ga_set_option.argtypes = [vp, i32, i64]
+        L.ga_get_option.argtypes = [vp, i32, vp]
         L.ga_comm_ipc_export.argtypes = [vp, vp]
         L.ga_comm_ipc_import.argtypes = [vp, vp]
         L.ga_set_csr_dist.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
@@ -348,9 +351,10 @@ class Context:
     """One device problem instance = the arrays symeigs allocates (src/interface.jl:245-251) on
     the GPU, plus the operator.  Thin, 1:1 over the C ABI; used by the tests and by eigs."""
 
-    def __init__(self, op, ncv, device=0, rank=0, world_size=1, n_global=None, row_offset=0, plan=None):
+    def __init__(self, op, ncv, device=0, rank=0, world_size=1, n_global=None, row_offset=0, plan=None, dots=None):
         """world_size > 1: `op` holds this rank's rows (global columns) and `plan` is the halo plan
-        of dist.halo_plan(...) for them."""
+        of dist.halo_plan(...) for them.  dots: "exact" (default; Dot2 accumulators, results independent of the row
+        partition) or "plain" (one FMA per product) for the Float64 sweeps -- ga_set_option(GA_OPT_DOT_MODE)."""
         L = lib()
         self.op = op
         self.dtype = op.dtype
@@ -404,6 +408,19 @@ class Context:
         else:
             self._ck(L.ga_set_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val)))
         self.iseed = np.array([1, 3, 5, 7], dtype=np.int64)  # src/macros.jl:291
+        if dots is not None:
+            self.set_dots(dots)
+
+    def set_dots(self, mode):
+        """GA_OPT_DOT_MODE: "exact" (Dot2, the default) or "plain" (FMA accumulation) in the Float64 sweeps."""
+        if mode not in ("exact", "plain"):
+            raise ValueError('dots must be "exact" or "plain"')
+        self._ck(lib().ga_set_option(self.h, GA_OPT_DOT_MODE, GA_DOT_PLAIN if mode == "plain" else GA_DOT_EXACT))
+
+    def get_dots(self):
+        v = ctypes.c_longlong(0)
+        self._ck(lib().ga_get_option(self.h, GA_OPT_DOT_MODE, ctypes.byref(v)))
+        return "plain" if v.value == GA_DOT_PLAIN else "exact"
 
     def close(self):
         if getattr(self, "h", None):
@@ -690,7 +707,7 @@ def _as_op(A, dtype=None, normal=False, B=None):
 
 
 def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, tol=0.0, ritzvec=True,
-            failonmaxiter=True, dtype=None, device=0, keep_context=False):
+            failonmaxiter=True, dtype=None, device=0, keep_context=False, dots=None):
     """symeigs(TV, TF, op, nev; which, maxiter, ncv, v0, stats, tol, ritzvec, failonmaxiter)
     (src/interface.jl:215-290) on the B200.  ``symeigs(A, nev)``: scipy sparse matrix (full storage) or a
     B200ArpackOp; ``symeigs(A, B, nev)``: the generalised problem A x = lambda B x through
@@ -735,7 +752,7 @@ def symeigs(A, *args, which="LM", maxiter=None, ncv=None, v0=None, stats=None, t
         raise ValueError("ncv=%d must be at most n=%d" % (ncv, n))  # :231
     if not nev < ncv:
         raise ValueError("nev=%d must be strictly less than ncv=%d" % (nev, ncv))  # :232
-    ctx = Context(op, ncv, device=device)
+    ctx = Context(op, ncv, device=device, dots=dots)
     try:
         rc = ctx.symeigs_begin(nev, which, tol, maxiter, v0)
         if rc != 0:

@@ -100,6 +100,8 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   c->coop = prop.cooperativeLaunch != 0;
   if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
   if (const char* e = getenv("GA_SPMV_V1")) c->use_spmv_stream = !(e[0] == '1');
+  if (const char* e = getenv("GA_GS_XPREFETCH")) c->gs_xprefetch = !(e[0] == '0');
+  if (const char* e = getenv("GA_GS_SEG1024_FROM")) c->gs_seg1024_from = atoi(e) > 0 ? atoi(e) : c->gs_seg1024_from;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -141,6 +143,25 @@ void ga_destroy(ga_ctx* c) {
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+int ga_set_option(ga_ctx* c, int key, int64_t value) {
+  if (!c) return GA_ERR_ARG;
+  switch (key) {
+    case GA_OPT_DOT_MODE:
+      if (value != GA_DOT_EXACT && value != GA_DOT_PLAIN) return set_err(c, GA_ERR_ARG, "ga_set_option: GA_OPT_DOT_MODE takes GA_DOT_EXACT or GA_DOT_PLAIN");
+      c->dot_plain = value == GA_DOT_PLAIN;
+      return 0;
+    default:
+      return set_err(c, GA_ERR_ARG, "ga_set_option: unknown key");
+  }
+}
+int ga_get_option(const ga_ctx* c, int key, int64_t* value) {
+  if (!c || !value) return GA_ERR_ARG;
+  switch (key) {
+    case GA_OPT_DOT_MODE: *value = c->dot_plain ? GA_DOT_PLAIN : GA_DOT_EXACT; return 0;
+    default: return GA_ERR_ARG;
+  }
 }
 
 const char* ga_last_error(const ga_ctx* c) { return c ? c->err.c_str() : "null context"; }

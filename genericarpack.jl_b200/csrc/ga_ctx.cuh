@@ -192,6 +192,9 @@ struct ga_ctx {
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   bool coop = false;                    // device supports cooperative launches (persistent step kernel)
   bool use_step_kernel = true;
+  bool dot_plain = false;               // GA_OPT_DOT_MODE = GA_DOT_PLAIN: one FMA per product in the Float64 step kernel (default: Dot2)
+  int gs_seg1024_from = 1 << 30;        // step kernel: 1 KiB column segments from this many columns on (default: only when 2 KiB stages no longer fit twice)
+  bool gs_xprefetch = true;             // cross-phase V prefetch of the step kernel (GA_GS_XPREFETCH=0 at ga_create: debug A/B switch)
   bool use_spmv_stream = true;          // TMA-staged persistent SpMV (GA_SPMV_V1=1 selects the first kernel)
   unsigned int gs_flip = 0;             // consecutive sweeps traverse the row tiles in opposite directions (L2 reuse)
   unsigned int* spmv_chk = nullptr;     // device, 128 words: stale-stage self-check of the streamed SpMV (debug)

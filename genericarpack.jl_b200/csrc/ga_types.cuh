@@ -187,8 +187,10 @@ GA_HD double mul_rn(double a, double b) {
 // are collected in `lo`.  hi + lo is the dot product as if computed in twice the working precision,
 // so the coefficients h = V'w do not depend (to ~1e-30 |v|'|w|) on how rows are split over threads,
 // CTAs or GPUs: restart counts are reproducible across 1/2/4/8 GPUs and against the oracle, whose
-// gemv_adj accumulates the same way.  10 FP64 instructions per product instead of 1; the sweeps
-// are HBM-bound with the FP64 pipe at ~10 %, which is what pays for it (profiles/r02).
+// gemv_adj accumulates the same way (ARITH_EXACT).  10 FP64 instructions per product instead of 1; the
+// sweeps are HBM-bound with FP64-pipe headroom, which is what pays for it (profiles/r02).
+// GA_DOT_PLAIN (ga_set_option) selects one fused multiply-add per product instead, the arithmetic of an
+// ordinary BLAS dgemv: faster, but the last bits of h then depend on the row partition.
 struct dot2 {
   double hi, lo;
   GA_HD dot2() {}
@@ -197,33 +199,18 @@ struct dot2 {
 
 template <> struct Elem<double> {
   typedef double real_t;
-#ifdef GA_DOT_PLAIN   /* development A/B only: the round-1 plain binary64 accumulators */
-  typedef double acc_t;
-  static GA_HD void acc_conj_mul(double& acc, double v, double w) { acc = fma(v, w, acc); }
-#else
   typedef dot2 acc_t;
-#endif
   static constexpr int dtype = 0;
   static constexpr bool is_complex = false;
   static GA_HD double zero() { return 0.0; }
   static GA_HD double re(double x) { return x; }
   static GA_HD double from_real(double r) { return r; }
   static GA_HD void add(double& a, double b) { a += b; }
+  static GA_HD void acc_conj_mul(double& acc, double v, double w) { acc = fma(v, w, acc); }    // plain: acc += v w
   static GA_HD void acc_conj_mul(dot2& acc, double v, double w) {                              // acc += conj(v) w
     double p, e, s, t;
     two_prod(v, w, p, e);
-#if defined(__CUDA_ARCH__) && defined(GA_DOT2_FAST)
-    // FastTwoSum (3 FP64 adds instead of TwoSum's 6) after ordering the operands by exponent with integer
-    // compares/selects of the high words (ALU pipe, idle in these kernels).  FastTwoSum is exact whenever
-    // exponent(big) >= exponent(sml); equal high words imply equal exponents.
-    const int ha = __double2hiint(acc.hi) & 0x7fffffff, hp = __double2hiint(p) & 0x7fffffff;
-    const bool sw = hp > ha;
-    const double big = sw ? p : acc.hi, sml = sw ? acc.hi : p;
-    s = big + sml;
-    t = sml - (s - big);
-#else
     two_sum(acc.hi, p, s, t);
-#endif
     acc.hi = s;
     acc.lo += (e + t);
   }

@@ -1,396 +1,23 @@
-// All Gram-Schmidt sweeps of ONE Lanczos step in a single persistent, cooperative launch.
-//
-// k_gs.cu runs one sweep per launch and lets the last CTA reduce and decide; the measured fixed
-// cost per sweep (profiles/RESULTS.md, in-kernel timeline) is ~23 us: last-CTA reduction + decision
-// logic + launch gap + pipeline refill.  At n = 16M that is 4 % of a sweep, at 2M rows per GPU
-// (8-GPU strong scaling) 25 %, and for L2-resident problems it dominates.  Here the 148 CTAs stay
-// resident for the whole step and the phases
-//     0  s = V'w, ||w||                      (dsaitr.jl:1208,1227)
-//     1  r = w - V h, s = V'r, ||r||         (:1240-1324)
-//     2  r -= V s,  s = V'r, ||r||   only if the 0.717 test asked for DGKS          (:1352-1434)
-//     3  r -= V s, ||r||             only if a second refinement is needed         (:1424-1446)
-// are separated by grid-wide barriers: CTA partials -> barrier -> CTA 0 sums them in fixed order,
-// (multi-GPU: exchanges the slots with the peers over NVLink peer memory), runs the step's
-// decision logic -> barrier -> everybody reads the verdict and the new coefficients and goes on.
-// Same arithmetic, same fixed summation order as k_gs.cu, bit-identical results.
-#include <cooperative_groups.h>
-
-#include <cstdlib>
-
-#include "ga_gs_cfg.cuh"
+// Dispatcher of the persistent Gram-Schmidt step kernel (k_gs_step.cuh; instantiated per element type in
+// k_gs_step_*.cu).
+#include "ga_ctx.cuh"
 
 namespace ga {
 
-__device__ __forceinline__ unsigned int ld_gpu_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_gpu_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// sense-reversing grid barrier on two words of the control block; all CTAs are co-resident
-// (cooperative launch).  Bounded spin: a broken barrier flags ST_COMM instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier(DevCtl* ctl) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int gen = ld_gpu_u32(&ctl->gbar_gen);
-    if (atomicAdd(&ctl->gbar_count, 1u) == gridDim.x - 1) {
-      ctl->gbar_count = 0u;
-      __threadfence();
-      st_gpu_u32(&ctl->gbar_gen, gen + 1u);
-    } else {
-      long long it = 0;
-      while (ld_gpu_u32(&ctl->gbar_gen) == gen) {
-        if (++it > (1LL << 27)) { ctl->status = ST_COMM; break; }
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// NCT = register accumulators per consumer thread (columns g, g+TG, ... of the thread's group): the launcher
-// picks the smallest instantiation that covers j columns, so short bases do not pay registers for 64 columns
-// (the Dot2 accumulators of the binary64 kernel are two doubles each).
-template <class T, int SEG, int NCT>
-__global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
-k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ctl, double2* partial, int nstages,
-          int ncv, const DevComm* cm, unsigned long long* trace, int xprefetch) {
-  typedef GsCfg<T, SEG> C;
-#define GA_TRACE(slot, cond)                                                        \
-  if (trace != nullptr && (cond)) {                                                 \
-    unsigned long long t_;                                                          \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
-    trace[slot] = t_;                                                               \
-  }
-  GA_TRACE(0, blockIdx.x == 0 && threadIdx.x == 0)
-  constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS, RPT = C::RPT, ROWL = C::ROWL;
-  constexpr uint32_t SEGB = C::SEG_BYTES;
-  constexpr bool CPLX = Elem<T>::is_complex;
-
-  if (__ldcg(&ctl->status) != ST_OK) return;  // uniform across the grid: nobody reaches a barrier
-
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t stage_bytes = (uint32_t)(j + 1) * SEGB;
-  unsigned char* p = smem + (size_t)nstages * stage_bytes;
-  T* hs = reinterpret_cast<T*>(p);                  p += kMaxNcv * 16;
-  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * SEGB;
-  double2* redw = reinterpret_cast<double2*>(p);    p += CWARPS * (NC + 3) * 16;
-  uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += C::MAX_STAGES * 8;
-  uint64_t* empty = reinterpret_cast<uint64_t*>(p); p += C::MAX_STAGES * 8;
-  int* sh_ctl = reinterpret_cast<int*>(p);          // [0] status, [1] phase
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CWARPS); }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int slice = warp % SLICES, g = warp / SLICES, rl = slice * 32 + lane;
-#define ROWIDX(q) ((sizeof(T) <= 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
-  int it = 0;  // running tile counter of this CTA: the stage ring and its parities continue across phases
-  int npre = 0;  // producer warp: tiles of the upcoming phase whose V columns are already in flight
-  const int nslots = j + 3;
-
-  for (int ph = 0; ph < 4; ++ph) {
-    const int mode = ph == 0 ? 0 : (ph == 3 ? 2 : 1);
-    if (ph >= 1) {
-      // verdict of the previous phase (written by CTA 0 before the barrier); identical in every CTA
-      if (tid == 0) { sh_ctl[0] = __ldcg(&ctl->status); sh_ctl[1] = __ldcg(&ctl->phase); }
-      __syncthreads();
-      const int st = sh_ctl[0], phs = sh_ctl[1];
-      __syncthreads();
-      if (st != ST_OK) break;
-      if (ph >= 2 && phs != (ph == 2 ? PH_ORTH1 : PH_ORTH2)) break;
-    }
-    if (mode != 0) {
-      const T* hb = hbuf_ptr<T>(ctl);
-      if (sizeof(T) == 4) {
-        for (int c = tid; c < j; c += blockDim.x) reinterpret_cast<float*>(hs)[c] = __ldcg(reinterpret_cast<const float*>(hb) + c);
-      } else if (sizeof(T) == 8) {
-        for (int c = tid; c < j; c += blockDim.x) reinterpret_cast<double*>(hs)[c] = __ldcg(reinterpret_cast<const double*>(hb) + c);
-      } else {
-        for (int c = tid; c < j; c += blockDim.x) reinterpret_cast<double2*>(hs)[c] = __ldcg(reinterpret_cast<const double2*>(hb) + c);
-      }
-      __syncthreads();
-    }
-
-    if (warp == CWARPS) {
-      // ---------------- producer warp.  The first `npre` tiles of this phase already have their V
-      // columns in flight (issued while the previous phase was being reduced); they only lack the
-      // column of the vector being orthogonalised, which the previous phase has just rewritten.
-      int itp = it;
-      int k = 0;
-      for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++itp, ++k) {
-        const int s = itp % nstages;
-        unsigned char* st = smem + (size_t)s * stage_bytes;
-        const i64 row0 = t * R;
-        if (k < npre) {
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&full[s], SEGB);
-            bulk_g2s(st + (size_t)j * SEGB, wr + row0, SEGB, &full[s]);
-          }
-          continue;
-        }
-        const uint32_t phb = (uint32_t)(itp / nstages) & 1u;
-        mbar_wait(&empty[s], phb ^ 1u);
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], stage_bytes);
-        __syncwarp();
-        for (int c = lane; c <= j; c += 32) {
-          const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (wr + row0);
-          bulk_g2s(st + (size_t)c * SEGB, src, SEGB, &full[s]);
-        }
-      }
-      // prefetch for the next phase: V does not change between the phases of a step
-      npre = 0;
-      if (ph < 3 && xprefetch) {
-        for (i64 t = blockIdx.x; t < ntiles && npre < nstages; t += gridDim.x, ++itp, ++npre) {
-          const int s = itp % nstages;
-          const uint32_t phb = (uint32_t)(itp / nstages) & 1u;
-          mbar_wait(&empty[s], phb ^ 1u);
-          if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)j * SEGB);
-          __syncwarp();
-          unsigned char* st = smem + (size_t)s * stage_bytes;
-          const i64 row0 = t * R;
-          for (int c = lane; c < j; c += 32) bulk_g2s(st + (size_t)c * SEGB, V + (size_t)c * ldv + row0, SEGB, &full[s]);
-        }
-      }
-    } else {
-      // ---------------- consumers
-      typename Elem<T>::acc_t acc[NCT];
-#pragma unroll
-      for (int i = 0; i < NCT; ++i) acc[i] = typename Elem<T>::acc_t(Elem<T>::zero());
-      NormAcc nacc;
-      nacc.init();
-      int itc = it;
-      for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x, ++itc) {
-        const int s = itc % nstages;
-        const uint32_t phb = (uint32_t)(itc / nstages) & 1u;
-        mbar_wait(&full[s], phb);
-        GA_TRACE(1 + 8 * ph, blockIdx.x == 0 && tid == 0 && itc == it)
-        const T* tile = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
-        T rr[RPT];
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) rr[q] = tile[(size_t)j * R + ROWIDX(q)];
-        if (mode != 0) {
-          T p0[RPT];
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) p0[q] = Elem<T>::zero();
-#pragma unroll
-          for (int i = 0; i < NCT; ++i) {
-            const int c = g + TG * i;
-            if (c >= j) break;
-            const T hc = hs[c];
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) Elem<T>::sub_mul(p0[q], tile[(size_t)c * R + ROWIDX(q)], hc);
-          }
-          T* prb = pr + (size_t)(itc & 1) * TG * R;
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) prb[g * R + ROWIDX(q)] = p0[q];
-          named_bar_sync(1 + slice, TG * 32);
-#pragma unroll
-          for (int g2 = 0; g2 < TG; ++g2) {
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) Elem<T>::add(rr[q], prb[g2 * R + ROWIDX(q)]);
-          }
-          if (g == 0) {
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) wr[t * R + ROWIDX(q)] = rr[q];
-          }
-        }
-        if (mode != 2) {
-#pragma unroll
-          for (int i = 0; i < NCT; ++i) {
-            const int c = g + TG * i;
-            if (c >= j) break;
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) Elem<T>::acc_conj_mul(acc[i], tile[(size_t)c * R + ROWIDX(q)], rr[q]);
-          }
-        }
-        if (g == 0) {
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) nacc.add(rr[q]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
-      GA_TRACE(2 + 8 * ph, blockIdx.x == 0 && tid == 0)
-      if (mode != 2) {
-#pragma unroll
-        for (int i = 0; i < NCT; ++i) {
-          if (g + TG * i < j) {
-            double2 sl = warp_sum_slot_fast(acc[i]);
-            if (lane == 0) redw[warp * (NC + 3) + i] = sl;
-          }
-        }
-      }
-      if (g == 0) {
-        ddbl m = warp_sum_dd(nacc.med), b = warp_sum_dd(nacc.big), sm = warp_sum_dd(nacc.sml);
-        if (lane == 0) {
-          redw[warp * (NC + 3) + NC + 0] = make_double2(m.hi, m.lo);
-          redw[warp * (NC + 3) + NC + 1] = make_double2(b.hi, b.lo);
-          redw[warp * (NC + 3) + NC + 2] = make_double2(sm.hi, sm.lo);
-        }
-      }
-      // r was written with generic-proxy stores; the next phase reads it with TMA (async proxy)
-      if (mode != 0) asm volatile("fence.proxy.async;" ::: "memory");
-    }
-    // every warp advances the running tile counter identically
-    it += (int)((ntiles - (i64)blockIdx.x + (i64)gridDim.x - 1) / (i64)gridDim.x);
-    __syncthreads();
-    // CTA partials -> global
-    for (int s = tid; s < nslots; s += blockDim.x) {
-      double2 a = make_double2(0.0, 0.0);
-      if (s < j) {
-        if (mode != 2) {
-          const int gg = s % TG, i = s / TG;
-          for (int sl = 0; sl < SLICES; ++sl) {
-            double2 v = redw[(gg * SLICES + sl) * (NC + 3) + i];
-            a = CPLX ? slot_add<true>(a, v) : slot_add<false>(a, v);
-          }
-        }
-      } else {
-        const int k = s - j;
-        for (int sl = 0; sl < SLICES; ++sl) a = slot_add<false>(a, redw[sl * (NC + 3) + NC + k]);
-      }
-      partial[(size_t)blockIdx.x * kMaxSlots + s] = a;
-    }
-    GA_TRACE(3 + 8 * ph, blockIdx.x == 0 && tid == 0)
-    grid_barrier(ctl);                       // all partials are in global memory
-    GA_TRACE(4 + 8 * ph, blockIdx.x == 0 && tid == 0)
-    if (blockIdx.x == 0) {
-      // fixed-order sum over the CTAs, all threads busy: SUB sub-lanes per slot each sum a strided
-      // subset of the CTAs (independent loads in flight), then one thread per slot adds the SUB
-      // partial sums in order.  redw (the CTA's own scratch) is free at this point.
-      constexpr int SUB = 12;
-      const unsigned int G = gridDim.x;
-      double2* scratch = reinterpret_cast<double2*>(pr);   // >= 1024 slots, idle between the phases
-      for (int idx = tid; idx < nslots * SUB; idx += blockDim.x) {
-        const int s = idx / SUB, u = idx % SUB;
-        const bool cplx = CPLX && s < j;
-        double2 v[13];   // 13 * SUB >= 148 CTAs; all loads are issued before the first add
-#pragma unroll
-        for (int k = 0; k < 13; ++k) {
-          const unsigned int b = u + k * SUB;
-          v[k] = b < G ? __ldcg(&partial[(size_t)b * kMaxSlots + s]) : make_double2(0.0, 0.0);
-        }
-        double2 a = v[0];
-#pragma unroll
-        for (int k = 1; k < 13; ++k) a = cplx ? slot_add<true>(a, v[k]) : slot_add<false>(a, v[k]);
-        for (unsigned int b = u + 13 * SUB; b < G; b += SUB) {   // larger grids (not on B200)
-          const double2 w2 = __ldcg(&partial[(size_t)b * kMaxSlots + s]);
-          a = cplx ? slot_add<true>(a, w2) : slot_add<false>(a, w2);
-        }
-        scratch[idx] = a;
-      }
-      __syncthreads();
-      if (tid < nslots) {
-        const bool cplx = CPLX && tid < j;
-        double2 a = scratch[tid * SUB];
-        for (int u = 1; u < SUB; ++u) a = cplx ? slot_add<true>(a, scratch[tid * SUB + u]) : slot_add<false>(a, scratch[tid * SUB + u]);
-        ctl->red[tid] = a;
-      }
-      __syncthreads();
-      GA_TRACE(5 + 8 * ph, tid == 0)
-      if (tid == 0) { ctl->prof_runs += 1u; ctl->prof_units += (unsigned long long)(j + 1 + (mode != 0 ? 1 : 0)); }
-      if (cm) comm_exchange_slots<CPLX>(ctl, cm, j, nslots);
-      gs_decide<T>(ctl, ctl->red, j, ncv, ph == 0 ? DK_DOT : ph == 1 ? DK_CGS : ph == 2 ? DK_ORTH1 : DK_ORTH2);
-    }
-    GA_TRACE(6 + 8 * ph, blockIdx.x == 0 && tid == 0)
-    grid_barrier(ctl);                       // verdict + coefficients published
-    GA_TRACE(7 + 8 * ph, blockIdx.x == 0 && tid == 0)
-  }
-  // a gated-off phase leaves prefetched V columns in flight: close those barrier phases and wait
-  // for the copies to land before the CTA (and its shared memory) goes away
-  if (warp == CWARPS && npre > 0) {
-    for (int k = 0; k < npre; ++k) {
-      const int itp = it + k, s = itp % nstages;
-      const uint32_t phb = (uint32_t)(itp / nstages) & 1u;
-      if (lane == 0) mbar_arrive(&full[s]);
-      __syncwarp();
-      mbar_wait(&full[s], phb);
-    }
-  }
-#undef GA_TRACE
-#undef ROWIDX
-}
-
-template <class T, int SEG, int NCT>
-static int launch_step_nct(ga_ctx* c, int j, int nstages) {
-  typedef GsCfg<T, SEG> C;
-  i64 ntiles = c->n_pad / C::R;
-  const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
-  size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
-  static PerDeviceOnce attr_set;
-  if (attr_set.need(c->device)) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_gs_step<T, SEG, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
-    attr_set.done(c->device);
-  }
-  int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
-  const T* V = (const T*)c->V;
-  T* wr = (T*)c->resid;
-  i64 ldv = c->n_pad;
-  DevCtl* ctl = c->ctl;
-  double2* partial = c->partial;
-  int ncv = c->ncv;
-  const DevComm* cm = c->world > 1 ? c->devcomm : nullptr;
-  unsigned long long* trace = c->trace;
-  static int xprefetch = -1;   // GA_GS_XPREFETCH=0 disables the cross-phase V prefetch (debug / A-B switch)
-  if (xprefetch < 0) { const char* e = getenv("GA_GS_XPREFETCH"); xprefetch = (e && e[0] == '0') ? 0 : 1; }
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->prof) {
-    if (c->prof_used + 2 > c->prof_ev.size()) {
-      for (int i = 0; i < 2; ++i) { cudaEvent_t e; GA_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e); }
-    }
-    e0 = c->prof_ev[c->prof_used]; e1 = c->prof_ev[c->prof_used + 1];
-    c->prof_used += 2;
-    GA_CUDA(c, cudaEventRecord(e0, c->stream));
-  }
-  void* args[] = {(void*)&V, (void*)&ldv, (void*)&j, (void*)&wr, (void*)&ntiles, (void*)&ctl, (void*)&partial,
-                  (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace, (void*)&xprefetch};
-  GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG, NCT>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
-  c->launches += 1;
-  if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
-  return 0;
-}
-
-template <class T, int SEG>
-static int launch_step_seg(ga_ctx* c, int j, int nstages) {
-  typedef GsCfg<T, SEG> C;
-  if (sizeof(T) == 8) {   // binary64: Dot2 accumulators, register-bound -> three widths
-    if (j <= C::TG * (C::NC / 2)) return launch_step_nct<T, SEG, (sizeof(T) == 8 ? C::NC / 2 : C::NC)>(c, j, nstages);
-    if (j <= C::TG * (3 * C::NC / 4)) return launch_step_nct<T, SEG, (sizeof(T) == 8 ? 3 * C::NC / 4 : C::NC)>(c, j, nstages);
-  }
-  return launch_step_nct<T, SEG, C::NC>(c, j, nstages);
-}
-
-template <class T>
-static int launch_step_t(ga_ctx* c, int j) {
-  const size_t budget2 = kGsSmemBytes - GsCfg<T, 2048>::FIXED_SMEM;
-  int nst = (int)(budget2 / ((size_t)(j + 1) * 2048));
-  if (nst >= 2) {
-    if (nst > GsCfg<T, 2048>::MAX_STAGES) nst = GsCfg<T, 2048>::MAX_STAGES;
-    return launch_step_seg<T, 2048>(c, j, nst);
-  }
-  const size_t budget1 = kGsSmemBytes - GsCfg<T, 1024>::FIXED_SMEM;
-  nst = (int)(budget1 / ((size_t)(j + 1) * 1024));
-  if (nst > GsCfg<T, 1024>::MAX_STAGES) nst = GsCfg<T, 1024>::MAX_STAGES;
-  if (nst < 2) return set_err(c, GA_ERR_ARG, "gs: too many columns for the shared-memory pipeline");
-  return launch_step_seg<T, 1024>(c, j, nst);
-}
+int launch_step_f64(ga_ctx* c, int j);
+int launch_step_f64_plain(ga_ctx* c, int j);
+int launch_step_f32(ga_ctx* c, int j);
+int launch_step_c64(ga_ctx* c, int j);
+int launch_step_dd(ga_ctx* c, int j);
 
 // All Gram-Schmidt phases of Lanczos step j (j basis columns) on c->resid, decisions on the device.
 int launch_gs_step(ga_ctx* c, int j) {
   if (j < 1 || j > kMaxNcv) return set_err(c, GA_ERR_ARG, "gs: j out of range");
   switch (c->dtype) {
-    case GA_F64: return launch_step_t<double>(c, j);
-    case GA_C64: return launch_step_t<cdbl>(c, j);
-    case GA_F32: return launch_step_t<float>(c, j);
-    default: return launch_step_t<ddbl>(c, j);
+    case GA_F64: return c->dot_plain ? launch_step_f64_plain(c, j) : launch_step_f64(c, j);
+    case GA_C64: return launch_step_c64(c, j);
+    case GA_F32: return launch_step_f32(c, j);
+    default: return launch_step_dd(c, j);
   }
 }
 

@@ -66,6 +66,19 @@ void ga_destroy(ga_ctx* ctx);
 const char* ga_last_error(const ga_ctx* ctx);
 int ga_device_sm_count(const ga_ctx* ctx);
 
+/* Per-context options (no process-global state).
+ *   GA_OPT_DOT_MODE  how the Float64 Gram-Schmidt sweeps accumulate h = V'w (the reference calls LinearAlgebra.mul! ->
+ *                    OpenBLAS dgemv, src/dsaitr.jl:1227,1352, whose summation order is unspecified):
+ *       GA_DOT_EXACT (default)  error-free products and sums (Dot2): h is the exact dot product rounded once, so it does
+ *                               not depend on the row partition -- Lanczos trajectories and restart counts are identical
+ *                               on 1/2/4/8 GPUs and equal to the oracle's (oracle/oracle.hpp ARITH_EXACT).
+ *       GA_DOT_PLAIN            one fused multiply-add per product (what a BLAS dgemv does); ~15 % faster sweeps, last
+ *                               bits of h depend on the partition.  Other element types are not affected. */
+enum { GA_OPT_DOT_MODE = 1 };
+enum { GA_DOT_EXACT = 0, GA_DOT_PLAIN = 1 };
+int ga_set_option(ga_ctx* ctx, int key, int64_t value);
+int ga_get_option(const ga_ctx* ctx, int key, int64_t* value);
+
 /* Multi-GPU plumbing.  The caller owns rendezvous (torch.distributed / MPI / Julia Distributed):
  * rank 0 calls ga_comm_unique_id, broadcasts the 128 bytes, every rank calls ga_comm_init.
  * Collectives are then issued by the library on its own stream (NCCL over NVLink 5 / NVSwitch). */

@@ -1,6 +1,8 @@
 # GenericArpackB200.jl -- the binding a GenericArpack.jl maintainer adds to route the Lanczos hot path
-# to libgarpack_b200.so.  NOT executable in the build image (no Julia there); it mirrors, call for
-# call, what genericarpack.jl_b200/csrc/ga_host.cu does in C++.  Written against GenericArpack v0.2.1:
+# to libgarpack_b200.so.  NOT executable in the build image (no Julia there: never parsed or run); it mirrors,
+# call for call, what genericarpack.jl_b200/csrc/ga_host.cu does in C++.  It binds the UNMODIFIED GenericArpack
+# v0.2.1 -- every GenericArpack name used below exists in /root/reference/src (cited at its use); nothing has to be
+# added to or factored out of the reference:
 #   * operator hook   abstract type ArpackOp                      src/idonow_ops.jl:50
 #   * state hook      abstract type AbstractArpackState{T}        src/macros.jl:356
 #     (every inner routine takes `state` positionally so a subtype can override it:
@@ -12,7 +14,8 @@ using GenericArpack, LinearAlgebra, SparseArrays
 import GenericArpack: ArpackOp, ArpackNormalSVDOp, AbstractArpackState, ArpackState, AitrState, Getv0State, Saup2State,
                       dgetv0!, dsaitr!, dsapps!, dorm2r!, norm2, opx!, arpack_mode, bmat,
                       is_arpack_mode_valid_for_op, symeigs, eigenvecs_to_singvecs!, _uv_size,
-                      _adjust_nev_which_for_svd, _adjust_eigenvalues_to_singular_values!
+                      _adjust_nev_which_for_svd, _adjust_eigenvalues_to_singular_values!,
+                      dsaupd!, simple_dseupd!, shift, ArpackEigen, ArpackException   # src/dsaupd.jl:921, src/dseupd.jl:986, src/idonow_ops.jl:54, src/interface.jl:170-203,125-127
 
 const lib = "libgarpack_b200.so"
 const GA_F64, GA_C64, GA_DD, GA_F32 = Cint(0), Cint(1), Cint(2), Cint(3)
@@ -61,19 +64,49 @@ Base.@kwdef mutable struct B200ArpackState{T} <: AbstractArpackState{T}
   ctx::Ptr{Cvoid} = C_NULL
 end
 
-# ---- device-resident stand-ins for V / resid / workd: sizes for the check macros
-# (src/macros.jl:208-231), no host data.  The few host-side touches outside the overridden
-# routines (SURVEY.md 8b: copyto!(workd, resid) src/dsaup2.jl:1397 and norm2(resid) :1414) are
-# absorbed by ga_apply_shifts, so they become no-ops / cached values here.
-struct DeviceVector{T} <: AbstractVector{T}; ctx::Ptr{Cvoid}; n::Int; end
-struct DeviceMatrix{T} <: AbstractMatrix{T}; ctx::Ptr{Cvoid}; n::Int; ncv::Int; end
-Base.size(v::DeviceVector) = (v.n,); Base.size(V::DeviceMatrix) = (V.n, V.ncv)
-Base.view(v::DeviceVector, ::UnitRange) = v
-Base.copyto!(d::DeviceVector, ::DeviceVector) = d            # src/dsaup2.jl:1397 (fused on the device)
-Base.copyto!(d::DeviceVector{T}, v0::AbstractVector{T}) where T =
-  (ccall((:ga_upload_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), d.ctx, v0); d)   # src/interface.jl:260
-function norm2(::Type{TR}, v::DeviceVector) where TR           # src/dsaup2.jl:1414
-  out = Ref{TR}(zero(TR)); ccall((:ga_norm2_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.ctx, out); out[]
+# ---- device-resident stand-ins for V / resid / workd: sizes for the check macros (src/macros.jl:208-231), no host data.
+# Host code outside the overridden routines touches the big arrays in exactly the places SURVEY.md 8(b) lists; each of
+# them gets ONE method below, keyed on which array and which range is addressed, and anything else is an error (scalar
+# indexing included) -- if a future reference version touches the arrays differently the binding fails loudly instead
+# of computing on stale data.
+struct DeviceVector{T} <: AbstractVector{T}; ctx::Ptr{Cvoid}; n::Int; len::Int; kind::Symbol; end    # kind = :resid (len n) | :workd (len 3n)
+struct DeviceMatrix{T} <: AbstractMatrix{T}; ctx::Ptr{Cvoid}; n::Int; ncv::Int; end                  # the Lanczos basis V
+struct DeviceVecView{T} <: AbstractVector{T}; parent::DeviceVector{T}; r::UnitRange{Int}; end        # @view(x[a:b])
+struct DeviceMatView{T} <: AbstractMatrix{T}; parent::DeviceMatrix{T}; rows::UnitRange{Int}; cols::UnitRange{Int}; end
+Base.size(v::DeviceVector) = (v.len,); Base.size(V::DeviceMatrix) = (V.n, V.ncv)
+Base.size(v::DeviceVecView) = (length(v.r),); Base.size(V::DeviceMatView) = (length(V.rows), length(V.cols))
+const _DeviceArray = Union{DeviceVector,DeviceMatrix,DeviceVecView,DeviceMatView}
+Base.getindex(::_DeviceArray, i...) = error("GenericArpackB200: device-resident array, no host indexing (unexpected host access to V/resid/workd)")
+Base.setindex!(::_DeviceArray, v, i...) = error("GenericArpackB200: device-resident array, no host indexing")
+Base.view(v::DeviceVector, r::UnitRange{Int}) = DeviceVecView(v, r)                                   # what @view(x[a:b]) lowers to
+Base.view(V::DeviceMatrix, rows::UnitRange{Int}, cols::UnitRange{Int}) = DeviceMatView(V, rows, cols)
+_is(v::DeviceVecView, kind::Symbol, r::UnitRange{Int}) = v.parent.kind === kind && v.r == r
+
+# src/dsaup2.jl:1397  copyto!(@view(workd[1:n]), @view(resid[1:n]))   and   :1386 (bmat = :G)  workd[n+1:2n] <- resid:
+# the library's next Lanczos step reads resid itself (ga_apply_shifts leaves it ready), nothing to move.
+function Base.copyto!(d::DeviceVecView{T}, s::DeviceVecView{T}) where T
+  n = s.parent.n
+  (_is(s, :resid, 1:n) && (_is(d, :workd, 1:n) || _is(d, :workd, n+1:2n))) ||
+    error("GenericArpackB200: unexpected device copy $(d.parent.kind)[$(d.r)] <- $(s.parent.kind)[$(s.r)]")
+  return d
+end
+# src/interface.jl:260  copyto!(resid, v0)
+function Base.copyto!(d::DeviceVector{T}, v0::AbstractVector{T}) where T
+  (d.kind === :resid && length(v0) == d.n) || error("GenericArpackB200: v0 must have n entries")
+  h = Vector{T}(v0)
+  check(ccall((:ga_upload_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), d.ctx, h), d.ctx); d
+end
+# src/dsaup2.jl:1414  rnorm = norm2(TR, @view(resid[1:n]));  src/dseupd.jl:1180 (bmat = :G only)  bnorm2 = norm2(TR, @view(workd[1:n]))
+function norm2(::Type{TR}, v::DeviceVecView) where TR
+  n = v.parent.n; out = Ref{TR}(zero(TR))
+  if _is(v, :resid, 1:n)
+    check(ccall((:ga_norm2_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.parent.ctx, out), v.parent.ctx)
+  elseif _is(v, :workd, 1:n)       # ||B resid||: only feeds the Ritz-vector purification of modes 3-5 (src/dseupd.jl:1526-1529), unused in mode 2
+    check(ccall((:ga_bnorm_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.parent.ctx, out), v.parent.ctx)
+  else
+    error("GenericArpackB200: unexpected device norm of $(v.parent.kind)[$(v.r)]")
+  end
+  return out[]
 end
 
 # ---- dgetv0! (src/dgetv0.jl:504-753)
@@ -103,41 +136,80 @@ function dsaitr!(ido::Ref{Int}, ::Val{:I}, n::Int, k::Int, np::Int, mode::Int, r
   return Int(check(info, state.ctx))
 end
 
-# ---- dsapps! (src/dsapps.jl:577-869): the reference's bulge chase runs unchanged on the host
-# (call the generic method on zero-length stand-ins to get Q and the updated H), then the device tail.
+# ---- dsapps! (src/dsapps.jl:577-869).  The np implicit QR shifts on the tridiagonal H (:609-805) are host work on
+# kplusp x kplusp data and stay in the reference: its own GENERIC method is called on zero-row stand-ins (n = 0: a
+# 1 x kplusp matrix satisfies the length checks :597-607 with ldv = 0, and every mul!/copyto!/axpy! of the tail :813-854
+# runs on empty views), which leaves Q and the updated H exactly as the full call would.  The n-row tail is then one
+# library call.  `state = nothing` is what the reference's own callers pass outside dsaup2! (test/dsapps_simple.jl).
 function dsapps!(n::Int, kev::Int, np::Int, shift::AbstractVecOrMat{TR}, V::DeviceMatrix{T}, ldv::Int,
-                 H::AbstractMatrix{TR}, ldh::Int, resid::DeviceVector{T}, Q::AbstractMatrix{TR}, ldq::Int, workd,
+                 H::AbstractMatrix{TR}, ldh::Int, resid::DeviceVector{T}, Q::AbstractMatrix{TR}, ldq::Int, workd::DeviceVector{T},
                  state::B200ArpackState{TR}; stats=nothing, debug=nothing) where {T,TR}
-  GenericArpack._dsapps_chase!(kev, np, shift, H, ldh, Q, ldq)   # = src/dsapps.jl:609-805 factored out (host, ncv x ncv)
+  kplusp = kev + np
+  dsapps!(0, kev, np, shift, zeros(T, 1, kplusp), 0, H, ldh, T[], Q, ldq, T[], nothing; stats, debug)   # host chase only
   beta = Ref(H[kev+1, 1]); rn = Ref(zero(TR))
   check(ccall((:ga_apply_shifts, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
               state.ctx, kev, np, Q, ldq, beta, rn), state.ctx)   # V*Q, resid update, ||resid|| (src/dsapps.jl:813-854, dsaup2.jl:1397-1414)
   return nothing
 end
 
-# ---- dorm2r!(:R,:N) on V inside simple_dseupd! (src/dseupd.jl:1431-1434)
+# ---- dorm2r!(:R,:N) on V inside simple_dseupd! (src/dseupd.jl:1431-1432: C = @view(V[1:n,1:ncv]), work = @view(workd[n+1:2n]))
 function dorm2r!(::Val{:R}, ::Val{:N}, m::Integer, n::Integer, k::Integer, A::AbstractMatrix{TR}, tau::AbstractVector{TR},
-                 C::DeviceMatrix{T}, work) where {T,TR}
+                 C::DeviceMatView{T}, work::DeviceVecView{T}) where {T,TR}
+  (C.rows == 1:C.parent.n && C.cols == 1:C.parent.ncv) || error("GenericArpackB200: dorm2r! on an unexpected block of V")
   Qh = Matrix{TR}(I, n, n)
-  GenericArpack.dorm2r!(Val(:R), Val(:N), n, n, k, A, tau, Qh, Vector{TR}(undef, n))   # Qh = H(1)...H(k), ncv x ncv on the host
-  check(ccall((:ga_ritz_vectors, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), C.ctx, k, Qh, n, C_NULL, 0), C.ctx)
+  GenericArpack.dorm2r!(Val(:R), Val(:N), n, n, k, A, tau, Qh, Vector{TR}(undef, n))   # Qh = H(1)...H(k), ncv x ncv on the host (src/arpack-blas-qr.jl:409-476)
+  check(ccall((:ga_ritz_vectors, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), C.parent.ctx, k, Qh, n, C_NULL, 0), C.parent.ctx)
   return C
 end
-Base.copyto!(Z::AbstractMatrix{T}, V::DeviceMatrix{T}) where T =       # Z <- V[:,1:nconv]  (src/dseupd.jl:1434)
-  (ccall((:ga_download_v, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Int64), V.ctx, 0, size(Z, 2), Z, size(Z, 1)); Z)
+# src/dseupd.jl:1434  copyto!(@view(Z[1:n, 1:nconv]), @view(V[1:n, 1:nconv]))
+function Base.copyto!(Z::SubArray{T,2,Matrix{T}}, V::DeviceMatView{T}) where T
+  (V.rows == 1:V.parent.n && first(V.cols) == 1 && size(Z) == size(V)) || error("GenericArpackB200: unexpected device -> host copy of V")
+  check(ccall((:ga_download_v, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Int64), V.parent.ctx, 0, size(Z, 2), pointer(Z), stride(Z, 2)), V.parent.ctx)
+  return Z
+end
 
 struct ga_stats_t; nopx::Int64; nbx::Int64; nrorth::Int64; nitref::Int64; nrstrt::Int64
   taupd::Float64; taup2::Float64; taitr::Float64; teigt::Float64; tgets::Float64; tapps::Float64; tconv::Float64
   tmvopx::Float64; tmvbx::Float64; tgetv0::Float64; titref::Float64; trvec::Float64; end
 ga_stats(ctx) = (r = Ref{ga_stats_t}(); ccall((:ga_get_stats, lib), Cint, (Ptr{Cvoid}, Ptr{ga_stats_t}), ctx, r); r[])
 
-# ---- the drop-in: a more specific symeigs method (src/interface.jl:215-290) that allocates device
-# handles instead of host arrays and then calls the UNCHANGED dsaupd!/simple_dseupd!.
-function symeigs(::Type{TV}, ::Type{TF}, op::B200ArpackOp{TV}, nev::Integer; ncv::Int=op.ncv, kwargs...) where {TV,TF}
+# ---- the drop-in: a more specific symeigs method.  Its body is the reference's own (src/interface.jl:215-290) with the
+# three big allocations (:245-246,249) replaced by device handles; dsaupd! and simple_dseupd! are the UNCHANGED
+# reference routines, which reach the GPU through the dgetv0!/dsaitr!/dsapps!/dorm2r! methods above.
+function _b200_symeigs(::Type{TV}, ::Type{TF}, op, nev::Integer;
+    which::Symbol=:LM, maxiter::Int=max(300, ceil(Int, sqrt(size(op)))), bmat=bmat(op), ncv::Int=op.ncv,
+    mode=arpack_mode(op), v0=nothing, stats=nothing, debug=nothing, tol::TF=zero(TF), ritzvec::Bool=true,
+    failonmaxiter::Bool=true) where {TV,TF}
+  n = size(op)
+  ncv == op.ncv || throw(ArgumentError("ncv=$ncv differs from the device context's ncv=$(op.ncv)"))
+  ncv <= n || throw(ArgumentError("ncv=$ncv must be at most n=$n"))                          # :231
+  nev < ncv || throw(ArgumentError("nev=$nev must be strictly less than ncv=$ncv"))           # :232
+  is_arpack_mode_valid_for_op(mode, op) || @warn("mode $mode is not valid for op with type $(typeof(op))")   # :239-241
   state = B200ArpackState{TF}(ctx=op.ctx)
-  V = DeviceMatrix{TV}(op.ctx, op.n, ncv); resid = DeviceVector{TV}(op.ctx, op.n); workd = DeviceVector{TV}(op.ctx, 3op.n)
-  return GenericArpack._symeigs_with_arrays(TV, TF, op, nev, V, resid, workd; ncv, state, kwargs...)  # body of :245-289 with the allocations hoisted
+  V = DeviceMatrix{TV}(op.ctx, n, ncv)                                                         # :245
+  resid = DeviceVector{TV}(op.ctx, n, n, :resid)                                               # :246
+  iparam = zeros(Int, 11); ipntr = zeros(Int, 11)                                              # :247-248
+  workd = DeviceVector{TV}(op.ctx, n, 3n, :workd)                                              # :249
+  lworkl = ncv*ncv + 8*ncv; workl = Vector{TF}(undef, lworkl)                                  # :250-251
+  iparam[1] = 1; iparam[4] = 1; iparam[3] = maxiter; iparam[7] = mode                          # :253-256
+  info_initv = 0
+  if v0 !== nothing; copyto!(resid, v0); info_initv = 1; end                                   # :258-262
+  ido = Ref{Int}(0)
+  info = dsaupd!(ido, bmat, n, which, nev, tol, resid, ncv, V, size(V, 1), iparam, ipntr, workd, workl, lworkl, info_initv;
+                 state, stats, debug, idonow=op)[1]                                            # :264-267
+  if info == 1 && failonmaxiter                                                                # :269-273
+    throw(ArpackException("symmetric aupd hit maxiter=$maxiter with $(iparam[5]) < $nev eigenvalues converged"))
+  elseif (info != 0 && info != 1) || ido[] != 99
+    throw(ArpackException("symmetric aupd gave error code info=$info with ido=$(ido[])"))
+  end
+  nconv = iparam[5]; nvectors = ritzvec ? min(nev, nconv) : 0                                  # :276-277
+  vectors = Matrix{TV}(undef, n, nvectors); values = Vector{TF}(undef, nconv); select = Vector{Int}(undef, ncv)
+  ierr = simple_dseupd!(ritzvec, select, values, vectors, shift(TF, op), bmat, n, which, nev, tol, resid, ncv, V,
+                        iparam, ipntr, workd, workl; debug, stats, state)                      # :281-283
+  ierr == 0 || throw(ArpackException("symmetric eupd gave error code ierr=$ierr"))              # :285-287
+  return ArpackEigen(which, ipntr, iparam, V, workd, workl, resid, values, vectors, bmat, op, state)   # :289
 end
+symeigs(::Type{TV}, ::Type{TF}, op::B200ArpackOp{TV}, nev::Integer; kwargs...) where {TV,TF} = _b200_symeigs(TV, TF, op, nev; kwargs...)
 
 # ---- svds: ArpackNormalOp on the device (src/idonow_ops.jl:216-333).  `svds(B200NormalOp(A, ncv), k)` runs the
 # reference's own svds (src/interface.jl:312-337): symeigs on A'A / AA' through the methods above, then
@@ -164,20 +236,26 @@ bmat(::B200NormalOp) = Val(:I)
 _uv_size(op::B200NormalOp) = (op.m, op.n)
 # _adjust_nev_which_for_svd / _adjust_eigenvalues_to_singular_values! are inherited from ArpackNormalSVDOp (:240-260)
 
-# eigenvecs_to_singvecs!(U, V, OP, Z) (src/idonow_ops.jl:295-333): Z holds the (re-sorted) eigenvectors; the
-# device still holds them as basis columns, `perm` says which column is Z[:,i].  The reference's check_norm
-# thresholds are applied to the norms the library returns.
-function eigenvecs_to_singvecs!(U::AbstractMatrix{T}, V::AbstractMatrix{T}, op::B200NormalOp{T}, Z::AbstractMatrix{T};
-                                perm::Vector{Int32}=Int32.(size(Z, 2)-1:-1:0)) where T
+symeigs(::Type{TV}, ::Type{TF}, op::B200NormalOp{TV}, nev::Integer; kwargs...) where {TV,TF} = _b200_symeigs(TV, TF, op, nev; kwargs...)
+
+# eigenvecs_to_singvecs!(U, V, OP, Z) (src/idonow_ops.jl:295-333), called by the reference's svds (src/interface.jl:333)
+# with the eigenvectors already re-sorted on the host (:321-328).  Z goes back into the first k basis columns (one
+# n x k upload per solve -- no assumption about how the host permuted it), then ONE library call forms the other
+# side's vectors on the device: A*v_i (or A'*u_i), norms, scaling and orth!.  The reference's check_norm thresholds
+# (:299-307) are applied to the norms the library returns.
+function eigenvecs_to_singvecs!(U::AbstractMatrix{T}, V::AbstractMatrix{T}, op::B200NormalOp{T}, Z::AbstractMatrix{T}) where T
   k = size(Z, 2); left = op.m > op.n
   W = left ? U : V; copyto!(left ? V : U, Z)
+  Zh = Matrix{T}(Z)
+  check(ccall((:ga_upload_v, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Int64), op.ctx, 0, k, Zh, size(Zh, 1)), op.ctx)
+  perm = Int32.(0:k-1)
   norms = Vector{real(T)}(undef, k)
   rc = ccall((:ga_svd_vectors, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
              op.ctx, k, perm, W, size(W, 1), norms)
-  rc == -104 && throw(GenericArpack.ArpackException("encountered σ ≈ 0 when computing $(left ? "U" : "V") subspace"))
+  rc == -104 && throw(ArpackException("encountered σ ≈ 0 when computing $(left ? "U" : "V") subspace"))
   check(rc, op.ctx)
-  any(norms .<= eps(real(T))/2) && throw(GenericArpack.ArpackException("encountered σ ≈ $(minimum(norms))"))
-  any(norms .<= GenericArpack._eps23(real(T))) && @warn "subspace may be inaccurate due to small singular value"
+  any(norms .<= eps(real(T))/2) && throw(ArpackException("encountered σ ≈ $(minimum(norms)) when computing $(left ? "U" : "V") subspace"))
+  any(norms .<= GenericArpack._eps23(real(T))) && @warn "$(left ? "U" : "V") subspace may be inaccurate due to small singular value"
   return nothing
 end
 
@@ -223,17 +301,15 @@ end
 # workd (src/dsaup2.jl:1383-1390, `_i_do_now_bx!`) and rnorm = sqrt(abs(dot(resid, workd))) (:1410-1411) collapse into one
 # library call, ga_bnorm_resid; simple_dseupd!'s bnorm2 = norm2(workd[1:n]) (src/dseupd.jl:1178-1180) only feeds the
 # mode 3-5 Ritz-vector purification and is not used for mode 2.
-GenericArpack._i_do_now_bx!(idonow, ipntr, workd::DeviceVector, n) = nothing
-function LinearAlgebra.dot(r::DeviceVector{T}, ::DeviceVector{T}) where T
+GenericArpack._i_do_now_bx!(idonow::B200GeneralizedOp, ipntr, workd::DeviceVector, n) = nothing    # src/idonow_ops.jl:86-88, called at src/dsaup2.jl:1394
+function LinearAlgebra.dot(r::DeviceVecView{T}, w::DeviceVecView{T}) where T                             # src/dsaup2.jl:1410
+  n = r.parent.n
+  (_is(r, :resid, 1:n) && _is(w, :workd, 1:n)) || error("GenericArpackB200: unexpected device dot product")
   out = Ref{real(T)}(zero(real(T)))
-  check(ccall((:ga_bnorm_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), r.ctx, out), r.ctx)
-  return out[] * out[]                                         # the caller applies sqrt(abs(.))
+  check(ccall((:ga_bnorm_resid, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), r.parent.ctx, out), r.parent.ctx)
+  return out[] * out[]                                         # the caller applies sqrt(abs(.))  (:1411)
 end
-symeigs(::Type{TV}, ::Type{TF}, op::B200GeneralizedOp{TV}, nev::Integer; ncv::Int=op.ncv, kwargs...) where {TV,TF} = begin
-  state = B200ArpackState{TF}(ctx=op.ctx)
-  V = DeviceMatrix{TV}(op.ctx, op.n, ncv); resid = DeviceVector{TV}(op.ctx, op.n); workd = DeviceVector{TV}(op.ctx, 3op.n)
-  GenericArpack._symeigs_with_arrays(TV, TF, op, nev, V, resid, workd; ncv, state, kwargs...)
-end
+symeigs(::Type{TV}, ::Type{TF}, op::B200GeneralizedOp{TV}, nev::Integer; kwargs...) where {TV,TF} = _b200_symeigs(TV, TF, op, nev; kwargs...)
 
 # ---- function operators (src/idonow_ops.jl:360-368): the user's opx! as a callback on DEVICE vectors.  `F(y, x, stream)`
 # receives CuPtr-backed views (e.g. CUDA.unsafe_wrap(CuArray, ...)) and must launch its kernels on `stream`.
@@ -259,5 +335,6 @@ Base.size(op::B200FunctionOp) = op.n
 arpack_mode(::B200FunctionOp) = 1
 bmat(::B200FunctionOp) = Val(:I)
 is_arpack_mode_valid_for_op(mode::Int, ::B200FunctionOp) = mode == 1
+symeigs(::Type{TV}, ::Type{TF}, op::B200FunctionOp{TV}, nev::Integer; kwargs...) where {TV,TF} = _b200_symeigs(TV, TF, op, nev; kwargs...)
 
 end # module

@@ -15,7 +15,7 @@ elif dt == "dd":
 else:
     op = pkg.ArpackSimpleOp(syn.laplacian2d(m)); S = 8
 n = m * m; n_pad = (n + 255) // 256 * 256
-ctx = pkg.Context(op, ncv)
+ctx = pkg.Context(op, ncv, dots=os.environ.get('GA_DOTS') if dt == 'f64' else None)
 ctx.getv0(); rn = ctx.norm2_resid()
 H = np.zeros((ncv, 2) + ((2,) if dt == "dd" else ()))
 info, rn = ctx.lanczos(0, ncv, H, rn)       # warm-up pass over all j

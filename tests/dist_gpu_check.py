@@ -71,7 +71,7 @@ def main():
         ok["ritz_orthonormal"] = bool(np.allclose(Z.T @ Z, np.eye(nev), atol=1e-12))
         single = pkg.eigs(pkg.ArpackSimpleOp(syn.laplacian2d(m)), nev, ncv=ncv, device=local)
         ok["vs_single_gpu_values"] = bool(np.max(np.abs(single.values - values) / np.abs(values)) <= 1e-12)
-        ok["vs_single_gpu_restarts"] = bool(abs(int(single.iparam[2]) - int(iparam[2])) <= max(2, int(iparam[2]) // 8))  # exactly double eigenvalues: count is sensitive to summation order
+        ok["vs_single_gpu_restarts"] = bool(abs(int(single.iparam[2]) - int(iparam[2])) <= 1)   # north_star: +-1 (Dot2 sweeps: independent of the row partition)
         out = {"world": world, "n": n, "fused_peer_memory": fused, "checks": ok, "restarts": int(iparam[2]), "restarts_single_gpu": int(single.iparam[2]),
                "nopx": int(ctx.stats()["nopx"]), "halo": int(plan["nhalo"])}
         print(json.dumps(out))

@@ -14,6 +14,15 @@ pytestmark = pytest.mark.gpu
 DT = {"f64": 0, "c64": 1, "dd": 2}
 
 
+@pytest.fixture(autouse=True)
+def _oracle_exact_arithmetic(O):
+    """The library's Float64 sweeps accumulate h = V'w error-free (Dot2, GA_DOT_EXACT, the default); the oracle is run
+    the same way (oracle.hpp ARITH_EXACT), so both sides sit within one rounding of the exact dot products and the
+    Lanczos trajectories -- 0.717 tests, deflations, restart counts -- agree step for step."""
+    with O.arith("exact"):
+        yield
+
+
 def _dd_float(x):
     return x[..., 0] + x[..., 1]
 
@@ -410,16 +419,89 @@ def test_eigs_kat_diagonal(pkg, O, n, nev, ncv):
     assert np.allclose(res.values, np.arange(n - nev + 1, n + 1), rtol=1e-12)
 
 
-def test_eigs_kat_issue5(pkg):
+def test_eigs_kat_issue5(pkg, O):
+    """test/interface_simple.jl:15-24: a rank-4 matrix with nev = 5, ncv = 8.  The Krylov space of this matrix has
+    dimension 2, so what happens after step 2 is decided by rounding noise alone: with the plain (BLAS-like) dot
+    products the noise keeps the factorisation going and the reference's assertions hold; with error-free dot products
+    the residual and the Ritz estimates vanish exactly, dsaup2 finds no shift to apply (src/dsaup2.jl:1177-1183,1293-1295)
+    and dsaupd reports info = 3 -- on the device and in the oracle alike."""
     A = sp.lil_matrix((10, 10))
     for i in (0, 1, 4, 5):
         A[i, i] = 1.0
     A = A.tocsr()
-    res = pkg.eigs(A, 5, ncv=8)
+    res = pkg.eigs(A, 5, ncv=8, dots="plain")
     Z, lam = res.vectors, res.values
     assert np.allclose(A @ Z, Z * lam, atol=1e-12)
     assert np.allclose(Z.T @ Z, np.eye(5), atol=1e-12)
     assert np.sum(lam) == pytest.approx(4.0, rel=1e-12)
+    ora = O.Oracle(A, 8, dtype=O.F64).symeigs(5)          # exact arithmetic (module fixture)
+    assert ora["info"] == 3
+    with pytest.raises(pkg.ArpackException, match="info=3"):
+        pkg.eigs(A, 5, ncv=8)
+
+
+@pytest.mark.parametrize("m,ncv", [(48, 24), (300, 40)])
+def test_exact_dots_lockstep_bitwise(pkg, syn, O, m, ncv):
+    """dgetv0 + ncv Lanczos steps on the 2-D Laplacian, device (Dot2 sweeps, double-double norms) vs the oracle in its
+    exact-arithmetic mode: H, every basis column, the residual and rnorm are the same bits, although the device splits
+    the rows over 148 CTAs x 16 warps and the oracle sums them in order."""
+    A = syn.to_scipy(syn.laplacian2d(m))
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), ncv)
+    assert ctx.get_dots() == "exact"
+    ora = O.Oracle(A, ncv)
+    ctx.getv0(); ora.dgetv0()
+    rn = ctx.norm2_resid()
+    H = np.zeros((ncv, 2))
+    info, rn = ctx.lanczos(0, ncv, H, rn)
+    ora.dsaitr(0, ncv)
+    V = np.asarray(ctx.download_v()); Vo = np.swapaxes(np.asarray(ora.Vt), 0, 1)
+    assert info == 0
+    assert np.array_equal(H, np.asarray(ora.H))
+    assert all(np.array_equal(V[:, c], Vo[:, c]) for c in range(ncv))
+    assert np.array_equal(np.asarray(ctx.download_resid()), np.asarray(ora.resid))
+    assert rn == ora.rnorm
+    assert ctx.stats()["nrorth"] == ora.stats()["nrorth"] and ctx.stats()["nitref"] == ora.stats()["nitref"]
+    ctx.close()
+
+
+@pytest.mark.parametrize("m,nev,ncv", [(64, 4, 20), (100, 4, 20), (100, 10, 40)])
+def test_exact_dots_restart_counts_equal(pkg, syn, O, m, nev, ncv):
+    """north_star: restart counts within +-1 of the reference on the same matrix and seed.  On the 2-D Laplacian the
+    wanted eigenvalues are exactly double, which makes the count sensitive to the last bits of h (round 1: 55 vs 53,
+    108 vs 105 with plain accumulators); with error-free dots on both sides the counts, the operator applications and
+    the eigenvalues (bit for bit) are equal."""
+    csr = syn.laplacian2d(m)
+    res = pkg.eigs(pkg.ArpackSimpleOp(csr), nev, ncv=ncv)
+    ora = O.Oracle(syn.to_scipy(csr), ncv).symeigs(nev)
+    assert abs(int(res.iparam[2]) - ora["niter"]) <= 1
+    assert int(res.iparam[2]) == ora["niter"] and res.stats["nopx"] == ora["stats"]["nopx"]
+    assert np.array_equal(np.asarray(res.values), np.asarray(ora["values"]))
+    exact = syn.laplacian2d_eigs(m, nev)
+    assert np.max(np.abs(res.values - exact) / exact) <= 1e-10
+
+
+def test_plain_dots_option(pkg, syn, O):
+    """GA_OPT_DOT_MODE = GA_DOT_PLAIN: one FMA per product (BLAS-like).  Same eigenvalues to 1e-10, H within a few ulps
+    of the exact-dots H over one pass, and the option is per context."""
+    m, ncv = 64, 20
+    A = syn.to_scipy(syn.laplacian2d(m))
+    Hs = {}
+    for mode in ("exact", "plain"):
+        ctx = pkg.Context(pkg.ArpackSimpleOp(A), ncv, dots=mode)
+        assert ctx.get_dots() == mode
+        ctx.getv0()
+        rn = ctx.norm2_resid()
+        H = np.zeros((ncv, 2))
+        info, rn = ctx.lanczos(0, ncv, H, rn)
+        assert info == 0
+        Hs[mode] = H.copy()
+        ctx.close()
+    assert np.allclose(Hs["exact"], Hs["plain"], rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        pkg.Context(pkg.ArpackSimpleOp(A), ncv, dots="fast")
+    res = pkg.eigs(pkg.ArpackSimpleOp(A), 4, ncv=ncv, dots="plain")
+    exact = syn.laplacian2d_eigs(m, 4)
+    assert np.max(np.abs(res.values - exact) / exact) <= 1e-10
 
 
 def test_eigs_laplacian_analytic(pkg, syn, O):

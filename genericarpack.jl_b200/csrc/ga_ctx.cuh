@@ -32,7 +32,8 @@ enum : int {
   DK_GETV0_DOT = 5,  // getv0 restart: h <- dots, rnorm0 <- norm       (src/dgetv0.jl:630,662)
   DK_GETV0_UPD = 6,  // getv0 restart: rnorm <- norm, h <- dots        (:665,700)
   DK_NORM = 7,    // rnorm <- norm                                    (src/dsaup2.jl:1414)
-  DK_TAKE = 8     // h <- dots, nothing else (bmat = :G: the host runs the step's scalar logic)
+  DK_TAKE = 8,    // h <- dots, nothing else (bmat = :G: the host runs the step's scalar logic)
+  DK_ORTH1_NODOTS = 9   // DK_ORTH1 after a sweep that did not compute the next dots (step kernel: they are only formed if the 0.717 test asks for them)
 };
 
 // Small control block in device memory.  Reals are stored as (hi, lo); lo = 0 for F64/C64.

@@ -52,7 +52,7 @@ __device__ void gs_decide(DevCtl* ctl, const double2* red, int j, int ncv, int k
     } else if (t == 3) {
       sh[4] = ctl->wnorm[0]; sh[5] = ctl->wnorm[1];
     } else if (t == 4) {
-      TR hd = (j >= 1 && (kind == DK_ORTH1 || kind == DK_ORTH2)) ? H[ncv + jc] : TR(0.0);
+      TR hd = (j >= 1 && (kind == DK_ORTH1 || kind == DK_ORTH1_NODOTS || kind == DK_ORTH2)) ? H[ncv + jc] : TR(0.0);
       store_real(&sh[6], hd);
     } else if (t >= 5 && t < 8) {
       const double2 v = red[j + (t - 5)];
@@ -81,7 +81,8 @@ __device__ void gs_decide(DevCtl* ctl, const double2* red, int j, int ncv, int k
         if (nrm > TR(0.717) * wn) ctl->phase = PH_DONE;               // :1324
         else { ctl->phase = PH_ORTH1; ctl->nrorth += 1; }             // :1328,1335
       } break;
-      case DK_ORTH1: {  // r -= V s done (:1363)
+      case DK_ORTH1:
+      case DK_ORTH1_NODOTS: {  // r -= V s done (:1363)
         if (first) H[jc] = TR(0.0);                                   // :1364-1366
         H[ncv + jc] = hdiag_in + hj;                                  // :1367
         const TR rn = rnorm_in;

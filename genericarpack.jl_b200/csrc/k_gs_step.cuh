@@ -7,8 +7,12 @@
 // resident for the whole step and the phases
 //     0  s = V'w, ||w||                      (dsaitr.jl:1208,1227)
 //     1  r = w - V h, s = V'r, ||r||         (:1240-1324)
-//     2  r -= V s,  s = V'r, ||r||   only if the 0.717 test asked for DGKS          (:1352-1434)
-//     3  r -= V s, ||r||             only if a second refinement is needed         (:1424-1446)
+//     2  r -= V s, ||r||             only if the 0.717 test asked for DGKS          (:1352-1434)
+//     3  s = V'r                     only if a second refinement is needed         (:1352 of the second round)
+//     4  r -= V s, ||r||             "                                             (:1424-1446)
+// (round 1 formed the second round's dots inside sweep 2 to save a sweep in the rare case; with error-free dot
+// products that speculation costs 10 FP64 instructions per element in EVERY step, so the dots now get their own sweep
+// when -- and only when -- the 0.717 test asks for them; same numbers either way)
 // are separated by grid-wide barriers: CTA partials -> barrier -> CTA 0 sums them in fixed order,
 // (multi-GPU: exchanges the slots with the peers over NVLink peer memory), runs the step's
 // decision logic -> barrier -> everybody reads the verdict and the new coefficients and goes on.
@@ -111,8 +115,8 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
   const int nslots = j + 3;
   const int my_tiles = (int)((ntiles - (i64)blockIdx.x + (i64)gridDim.x - 1) / (i64)gridDim.x);
 
-  for (int ph = 0; ph < 4; ++ph) {
-    const int mode = ph == 0 ? 0 : (ph == 3 ? 2 : 1);
+  for (int ph = 0; ph < 5; ++ph) {
+    const int mode = (ph == 0 || ph == 3) ? 0 : (ph == 1 ? 1 : 2);
     if (ph >= 1) {
       // verdict of the previous phase (written by CTA 0 before the barrier); identical in every CTA
       if (tid == 0) { sh_ctl[0] = __ldcg(&ctl->status); sh_ctl[1] = __ldcg(&ctl->phase); }
@@ -120,7 +124,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       const int st = sh_ctl[0], phs = sh_ctl[1];
       __syncthreads();
       if (st != ST_OK) break;
-      if (ph >= 2 && phs != (ph == 2 ? PH_ORTH1 : PH_ORTH2)) break;
+      if (ph >= 2 && phs != (ph == 2 ? PH_ORTH1 : PH_ORTH2)) break;   // phases 3 and 4 both belong to the second refinement
     }
     if (mode != 0) {
       // coefficients of this sweep, zero beyond the basis (the branch-free column loops read up to NCT * TG of them)
@@ -168,7 +172,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       }
       // prefetch for the next phase: V does not change between the phases of a step
       npre = 0;
-      if (ph < 3 && xprefetch) {
+      if (ph < 4 && xprefetch) {
         for (i64 t = blockIdx.x; t < ntiles && npre < nstages; t += gridDim.x, ++npre) {
           mbar_wait(&empty[s], par ^ 1u);
           if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)j * SEGB);
@@ -323,7 +327,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       GA_TRACE(5 + 8 * ph, tid == 0)
       if (tid == 0) { ctl->prof_runs += 1u; ctl->prof_units += (unsigned long long)(j + 1 + (mode != 0 ? 1 : 0)); }
       if (cm) comm_exchange_slots<CPLX>(ctl, cm, j, nslots);
-      gs_decide<T>(ctl, ctl->red, j, ncv, ph == 0 ? DK_DOT : ph == 1 ? DK_CGS : ph == 2 ? DK_ORTH1 : DK_ORTH2);
+      gs_decide<T>(ctl, ctl->red, j, ncv, ph == 0 ? DK_DOT : ph == 1 ? DK_CGS : ph == 2 ? DK_ORTH1_NODOTS : ph == 3 ? DK_TAKE : DK_ORTH2);
     }
     GA_TRACE(6 + 8 * ph, blockIdx.x == 0 && tid == 0)
     grid_barrier(ctl);                       // verdict + coefficients published

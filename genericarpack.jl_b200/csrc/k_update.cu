@@ -7,100 +7,165 @@
 //   - device tail of simple_dseupd! (src/dseupd.jl:1413-1435): V <- V Qh where Qh is the product of
 //     the nconv Householder reflectors the reference applies one at a time with dorm2r!.
 //
-// A CTA stages R rows x kplusp columns of V in shared memory (coalesced 16-byte loads), then each
-// thread owns one row and OB = 4 consecutive output columns at a time: one shared-memory read of
-// x = V[row,c] and OB reads of Q[c, o..o+3] feed OB FMAs.  Q sits in shared memory transposed to
-// [c][o] so the OB values are contiguous.
+// Persistent, warp-specialised kernel (one CTA per SM).  A tile is R rows (one 2 KiB column segment: the TMA bulk-copy
+// issue rate makes shorter copies slow, ga_gs_cfg.cuh) of all kplusp columns and one stage of a shared-memory ring;
+// a producer warp keeps the ring full with TMA bulk copies (completion on an mbarrier per stage), the consumer warps
+// take the stages in order.  A consumer thread owns ONE ROW of the tile and keeps 4*NOB outputs of that row in
+// registers: per basis column one shared-memory read of x = V[row,c] and 2*NOB broadcast reads of Q[c, o..] (Q sits in
+// shared memory transposed to [c][o]) feed 4*NOB FMAs.  Results go straight to global memory (V is updated in place:
+// every row is in the ring before it is written, rows are independent); outputs beyond 4*NOB take further passes over
+// the resident tile.
+// Why this shape (profiles/r02/README.md): round 1's kernel loaded the tile synchronously (load -> __syncthreads -> compute
+// -> store) and re-read x once per block of four outputs; its ncu capture shows 3.45 TB/s, long-scoreboard and barrier
+// stalls, the FP64 pipe at 23 % and the LSU pipe at 42 % -- counting shared-memory wavefronts, that mapping needs 3840 per
+// 256-row tile against 4180 cycles of HBM time, i.e. it is shared-memory bound right at the roofline.  More outputs per
+// thread cut the x re-reads (2560 wavefronts for 12 outputs); the FP64 pipe needs 46 % at the roofline, so the answer
+// is register blocking + the asynchronous ring, not tensor cores: DMMA would not add FP64 throughput on this part (same
+// rate as the FMA pipe) and would change the rounding order of V*Q away from the reference's dgemv.
 #include "ga_decide.cuh"
+#include "ga_tma.cuh"
 
 namespace ga {
 
+constexpr size_t kVqSmemBytes = 216 * 1024;
+
 template <class T> struct VqCfg {
-  static constexpr int R = (sizeof(T) == 8) ? 128 : 64;  // rows per CTA tile
-  static constexpr int OG = (sizeof(T) == 8) ? 2 : 4;    // output groups (threads per row)
-  static constexpr int THREADS = R * OG;
+  static constexpr int SEG = 2048;                       // bytes of one column segment of a tile
+  static constexpr int R = SEG / (int)sizeof(T);         // rows per tile
+  static constexpr int RPT = (sizeof(T) == 16) ? 1 : 2;  // adjacent rows per consumer thread (one 16-byte shared-memory read)
+  static constexpr int CTHREADS = R / RPT;
+  static constexpr int THREADS = CTHREADS + 32;          // + producer warp
   static constexpr int OB = 4;
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int MAX_NOB = 4;                      // register blocks of 4 outputs per thread (x RPT rows)
 };
 
-template <class T>
-__global__ void __launch_bounds__(VqCfg<T>::THREADS)
+template <class T, int NOB>
+__global__ void __launch_bounds__(VqCfg<T>::THREADS, 1)
 k_vq(T* V, i64 ld, i64 ntiles, const typename Elem<T>::real_t* __restrict__ Qg, int ldq, int kplusp, int nout,
-     T* resid, int do_resid, int kev, DevCtl* ctl, double2* partial, int decide_kind, int ncv, const DevComm* cm) {
+     T* resid, int do_resid, int kev, DevCtl* ctl, double2* partial, int decide_kind, int ncv, const DevComm* cm,
+     int nstages) {
   typedef typename Elem<T>::real_t TR;
   typedef VqCfg<T> C;
-  constexpr int R = C::R, OG = C::OG, OB = C::OB;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int nout_pad = (nout + OB - 1) / OB * OB;
-  TR* Qs = reinterpret_cast<TR*>(smem);                                   // [kplusp][nout_pad]
-  T* tile = reinterpret_cast<T*>(smem + (size_t)kplusp * nout_pad * sizeof(TR));  // [kplusp][R]
-  __shared__ double2 sw[C::THREADS / 32 * 3];
+  constexpr int R = C::R, OB = C::OB, CT = C::CTHREADS, SEG = C::SEG, NO = OB * NOB, RPT = C::RPT;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int nout_pad = (nout + NO - 1) / NO * NO;                          // whole passes of NO outputs
+  const uint32_t stage_bytes = (uint32_t)kplusp * SEG;
+  unsigned char* p = smem + (size_t)nstages * stage_bytes;
+  TR* Qs = reinterpret_cast<TR*>(p);                                       // [kplusp][nout_pad]
+  p += ((size_t)kplusp * nout_pad * sizeof(TR) + 15) / 16 * 16;
+  uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += C::MAX_STAGES * 8;
+  uint64_t* empty = reinterpret_cast<uint64_t*>(p);
+  __shared__ double2 sw[CT / 32 * 3];
   __shared__ int sh_flag;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CT / 32); }
+    fence_mbar_init();
+  }
   for (int idx = tid; idx < kplusp * nout_pad; idx += C::THREADS) {
     const int c = idx / nout_pad, o = idx % nout_pad;
     Qs[idx] = (o < nout) ? Qg[c + (size_t)o * ldq] : Real<TR>::from(0.0);
   }
-  TR sigma = Real<TR>::from(0.0), beta = Real<TR>::from(0.0);
-  if (do_resid) {
-    sigma = Qg[(kplusp - 1) + (size_t)(kev - 1) * ldq];   // Q[kplusp,kev]   (src/dsapps.jl:850)
-    beta = load_real<TR>(ctl->rnorm1);                    // H[kev+1,1], parked by the launcher
-  }
-  const int row = tid % R, og = tid / R;
+  __syncthreads();
   NormAcc nacc;
   nacc.init();
-  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const i64 row0 = t * R;
-    __syncthreads();
-    for (int idx = tid; idx < kplusp * R; idx += C::THREADS) {
-      const int c = idx / R, rr = idx % R;
-      tile[idx] = V[(size_t)c * ld + row0 + rr];
+  if (warp == CT / 32) {
+    // ---------------- producer warp
+    int s = 0;
+    uint32_t par = 0;
+    for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(&empty[s], par ^ 1u);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], stage_bytes);
+      __syncwarp();
+      unsigned char* st = smem + (size_t)s * stage_bytes;
+      const i64 row0 = t * R;
+      for (int c = lane; c < kplusp; c += 32) bulk_g2s(st + (size_t)c * SEG, V + (size_t)c * ld + row0, SEG, &full[s]);
+      if (++s == nstages) { s = 0; par ^= 1u; }
     }
-    __syncthreads();
-    for (int ob = og * OB; ob < nout_pad; ob += OG * OB) {
-      T y0 = Elem<T>::zero(), y1 = Elem<T>::zero(), y2 = Elem<T>::zero(), y3 = Elem<T>::zero();
-      const TR* q = Qs + ob;
-#pragma unroll 4
-      for (int c = 0; c < kplusp; ++c) {
-        const T x = tile[c * R + row];
-        const TR* qc = q + (size_t)c * nout_pad;
-        Elem<T>::add_mul_real(y0, x, qc[0]);
-        Elem<T>::add_mul_real(y1, x, qc[1]);
-        Elem<T>::add_mul_real(y2, x, qc[2]);
-        Elem<T>::add_mul_real(y3, x, qc[3]);
-      }
-      T yy[4] = {y0, y1, y2, y3};
+  } else {
+    // ---------------- consumers: thread = RPT adjacent rows x NO outputs in registers (RPT * NO independent FMA chains:
+    // the chains are kplusp long, so it is this count, not the warp count, that hides the FP64 latency)
+    TR sigma = Real<TR>::from(0.0), beta = Real<TR>::from(0.0);
+    if (do_resid) {
+      sigma = Qg[(kplusp - 1) + (size_t)(kev - 1) * ldq];   // Q[kplusp,kev]   (src/dsapps.jl:850)
+      beta = load_real<TR>(ctl->rnorm1);                    // H[kev+1,1], parked by the launcher
+    }
+    const int row = tid * RPT;
+    int s = 0;
+    uint32_t par = 0;
+    for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const i64 row0 = t * R;
+      // the residual entries of these rows: issued before the wait so that their latency hides behind it
+      T rres[RPT];
 #pragma unroll
-      for (int u = 0; u < OB; ++u) {
-        const int o = ob + u;
-        if (o < nout) {
-          V[(size_t)o * ld + row0 + row] = yy[u];
-          if (do_resid && o == kev) {  // beta > 0: r <- sigma r + beta v_{kev+1}  (:850-854)
-            T rv = Elem<T>::mul_real(resid[row0 + row], sigma);
-            Elem<T>::add_mul_real(rv, yy[u], beta);
-            resid[row0 + row] = rv;
-            nacc.add(rv);
+      for (int q = 0; q < RPT; ++q) rres[q] = do_resid ? resid[row0 + row + q] : Elem<T>::zero();
+      mbar_wait(&full[s], par);
+      const T* xs = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes) + row;
+      for (int o0 = 0; o0 < nout_pad; o0 += NO) {
+        T y[RPT][NO];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int u = 0; u < NO; ++u) y[q][u] = Elem<T>::zero();
+        const TR* qc = Qs + o0;
+#pragma unroll 4
+        for (int c = 0; c < kplusp; ++c) {
+          T x[RPT];
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) x[q] = xs[(size_t)c * R + q];
+#pragma unroll
+          for (int u = 0; u < NO; ++u) {
+            const TR qv = qc[u];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) Elem<T>::add_mul_real(y[q][u], x[q], qv);
+          }
+          qc += nout_pad;
+        }
+#pragma unroll
+        for (int u = 0; u < NO; ++u) {
+          const int o = o0 + u;
+          if (o < nout) {
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) V[(size_t)o * ld + row0 + row + q] = y[q][u];
+            if (do_resid && o == kev) {  // beta > 0: r <- sigma r + beta v_{kev+1}  (:850-854)
+#pragma unroll
+              for (int q = 0; q < RPT; ++q) {
+                T rv = Elem<T>::mul_real(rres[q], sigma);
+                Elem<T>::add_mul_real(rv, y[q][u], beta);
+                resid[row0 + row + q] = rv;
+                nacc.add(rv);
+              }
+            }
           }
         }
       }
-    }
-    if (do_resid && nout == kev && og == 0) {  // beta == 0: r <- sigma r
-      T rv = Elem<T>::mul_real(resid[row0 + row], sigma);
-      resid[row0 + row] = rv;
-      nacc.add(rv);
+      if (do_resid && nout == kev) {  // beta == 0: r <- sigma r
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          T rv = Elem<T>::mul_real(rres[q], sigma);
+          resid[row0 + row + q] = rv;
+          nacc.add(rv);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == nstages) { s = 0; par ^= 1u; }
     }
   }
   if (!do_resid) return;
-  ddbl m = warp_sum_dd(nacc.med), b = warp_sum_dd(nacc.big), s = warp_sum_dd(nacc.sml);
-  const int warp = tid >> 5, lane = tid & 31;
-  if (lane == 0) {
-    sw[warp * 3 + 0] = make_double2(m.hi, m.lo);
-    sw[warp * 3 + 1] = make_double2(b.hi, b.lo);
-    sw[warp * 3 + 2] = make_double2(s.hi, s.lo);
+  if (warp < CT / 32) {
+    ddbl m = warp_sum_dd(nacc.med), b = warp_sum_dd(nacc.big), s = warp_sum_dd(nacc.sml);
+    if (lane == 0) {
+      sw[warp * 3 + 0] = make_double2(m.hi, m.lo);
+      sw[warp * 3 + 1] = make_double2(b.hi, b.lo);
+      sw[warp * 3 + 2] = make_double2(s.hi, s.lo);
+    }
   }
   __syncthreads();
   if (tid < 3) {
     double2 acc = make_double2(0.0, 0.0);
-    for (int w = 0; w < C::THREADS / 32; ++w) acc = slot_add<false>(acc, sw[w * 3 + tid]);
+    for (int w = 0; w < CT / 32; ++w) acc = slot_add<false>(acc, sw[w * 3 + tid]);
     partial[(size_t)blockIdx.x * kMaxSlots + tid] = acc;
   }
   if (last_block_reduce<false>(ctl, partial, 0, 3, &sh_flag)) {
@@ -109,34 +174,52 @@ k_vq(T* V, i64 ld, i64 ntiles, const typename Elem<T>::real_t* __restrict__ Qg, 
   }
 }
 
-template <class T>
-static int launch_vq_t(ga_ctx* c, int kplusp, int nout, bool do_resid, int kev) {
+template <class T, int NOB>
+static int launch_vq_nob(ga_ctx* c, int kplusp, int nout, bool do_resid, int kev) {
   typedef typename Elem<T>::real_t TR;
   typedef VqCfg<T> C;
+  constexpr int NO = C::OB * NOB;
+  const int nout_pad = (nout + NO - 1) / NO * NO;
+  const size_t fixed = ((size_t)kplusp * nout_pad * sizeof(TR) + 15) / 16 * 16 + 2 * C::MAX_STAGES * 8 + 64;
+  int nst = (int)((kVqSmemBytes - fixed) / ((size_t)kplusp * C::SEG));
+  if (nst > C::MAX_STAGES) nst = C::MAX_STAGES;
+  if (nst < 1) return set_err(c, GA_ERR_ARG, "vq: shared memory budget exceeded");
   const i64 ntiles = c->n_pad / C::R;
-  const int nout_pad = (nout + C::OB - 1) / C::OB * C::OB;
-  const size_t smem = (size_t)kplusp * nout_pad * sizeof(TR) + (size_t)kplusp * C::R * sizeof(T);
+  const size_t smem = fixed + (size_t)nst * kplusp * C::SEG;
   static PerDeviceOnce attr_set;
   if (attr_set.need(c->device)) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_vq<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GA_CUDA(c, cudaFuncSetAttribute(k_vq<T, NOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVqSmemBytes));
     attr_set.done(c->device);
   }
-  if (smem > 200 * 1024) return set_err(c, GA_ERR_ARG, "vq: shared memory budget exceeded");
-  int per_sm = (int)((220 * 1024) / (smem + 2048));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  i64 grid = (i64)c->sm_count * per_sm;
+  i64 grid = (i64)c->sm_count;
   if (grid > ntiles) grid = ntiles;
   if (grid > kMaxCtas) grid = kMaxCtas;
   if (grid < 1) grid = 1;
   const bool single = c->world == 1 || c->devcomm != nullptr;  // decide inside the kernel
-  k_vq<T><<<(int)grid, C::THREADS, smem, c->stream>>>((T*)c->V, c->n_pad, ntiles, (const TR*)c->qdev, c->ncv_pad,
-                                                    kplusp, nout, (T*)c->resid, do_resid ? 1 : 0, kev, c->ctl,
-                                                    c->partial, single ? DK_NORM : DK_NONE, c->ncv, c->world > 1 ? c->devcomm : nullptr);
+  k_vq<T, NOB><<<(int)grid, C::THREADS, smem, c->stream>>>((T*)c->V, c->n_pad, ntiles, (const TR*)c->qdev, c->ncv_pad,
+                                                         kplusp, nout, (T*)c->resid, do_resid ? 1 : 0, kev, c->ctl,
+                                                         c->partial, single ? DK_NORM : DK_NONE, c->ncv,
+                                                         c->world > 1 ? c->devcomm : nullptr, nst);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (do_resid && !single) return launch_decide(c, 0, -1, DK_NORM);
   return 0;
+}
+
+template <class T>
+static int launch_vq_t(ga_ctx* c, int kplusp, int nout, bool do_resid, int kev) {
+  // the smallest register blocking that covers the outputs in the fewest passes
+  constexpr int MAXB = VqCfg<T>::MAX_NOB;
+  const int blocks = (nout + 3) / 4;
+  const int passes = (blocks + MAXB - 1) / MAXB;
+  const int nob = (blocks + passes - 1) / passes;
+  if (nob <= 1) return launch_vq_nob<T, 1>(c, kplusp, nout, do_resid, kev);
+  if (nob == 2 || MAXB == 2) return launch_vq_nob<T, 2>(c, kplusp, nout, do_resid, kev);
+  if constexpr (MAXB >= 4) {
+    if (nob == 3) return launch_vq_nob<T, 3>(c, kplusp, nout, do_resid, kev);
+    return launch_vq_nob<T, 4>(c, kplusp, nout, do_resid, kev);
+  }
+  return launch_vq_nob<T, 2>(c, kplusp, nout, do_resid, kev);
 }
 
 // Q (kplusp x nout, ld = ncv_pad, real type) must already be in c->qdev; for do_resid the

@@ -103,6 +103,33 @@ def test_f32_lanczos_properties(pkg, syn, O, ncv):
     ctx.close()
 
 
+def test_f32_lockstep_against_f32_oracle(pkg, syn, O):
+    """The Float32 device path in lock step with the oracle's own Float32 instantiation (oracle.F32: Float32 vectors,
+    binary32 dlarnv incl. reseed, Float64 factorisation): bit-identical start vector and seed, the same DGKS counters,
+    H to Float32 accuracy over the first steps (the device accumulates the dots in binary64, the reference's sgemv in
+    binary32, so later steps drift at the 1e-7-per-step level), and the same eigenvalues from a whole solve."""
+    m, ncv = 60, 20
+    A = syn.to_scipy(syn.laplacian2d(m)).astype(np.float32)
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), ncv)
+    ora = O.Oracle(A, ncv, dtype=O.F32)
+    assert ctx.getv0()[0] == 0 and ora.dgetv0() == 0
+    assert np.array_equal(np.asarray(ctx.download_resid()), np.asarray(ora.resid))
+    assert tuple(ctx.iseed) == tuple(int(v) for v in ora.iseed)
+    rn = ctx.norm2_resid()
+    assert abs(rn - ora.rnorm) <= 1e-14 * rn
+    H = np.zeros((ncv, 2))
+    info, rn = ctx.lanczos(0, ncv, H, rn)
+    assert info == 0 and ora.dsaitr(0, ncv) == 0
+    Ho = np.asarray(ora.H)
+    assert np.max(np.abs(H[:10] - Ho[:10])) <= 2e-5 * np.max(np.abs(Ho))
+    assert ctx.stats()["nopx"] == ora.stats()["nopx"] == ncv
+    assert abs(ctx.stats()["nrorth"] - ora.stats()["nrorth"]) <= 2
+    ctx.close()
+    res = pkg.eigs(np.float32, np.float64, A, 4, ncv=ncv)
+    o = O.Oracle(A, ncv, dtype=O.F32).symeigs(4, tol=float(np.finfo(np.float32).eps) / 2)
+    assert o["info"] == 0 and np.allclose(res.values, np.asarray(o["values"]), rtol=1e-5)
+
+
 def test_f32_eigs_kats(pkg):
     """test/interface_simple.jl:36-49 (15 x 15 KAT, which = :LA, Float32 and Float32/Float64) and the docstring
     example symeigs(Float32, ArpackSimpleOp(Diagonal(1.0:n)), 5; which=:SA) (src/interface.jl:105-110)."""

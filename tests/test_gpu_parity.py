@@ -266,12 +266,36 @@ def test_lanczos_identity_restart(pkg, O):
     oinfo = ora.dsaitr(0, 2)
     assert info == oinfo == 0
     assert ctx.stats()["nrstrt"] == ora.stats()["nrstrt"] > 0
+    assert ctx.stats()["nitref"] == ora.stats()["nitref"] > 0      # both DGKS refinement rounds are taken (:1424-1446)
     assert np.linalg.norm(ctx.download_resid()) <= n * np.finfo(float).eps
     V = ctx.download_v(0, 2)
     assert np.allclose(V.T @ V, np.eye(2), atol=1e-14)
     assert tuple(ctx.iseed) == tuple(ora.iseed)              # same dlarnv stream consumed
     assert np.allclose(V, ora.Vt[:2].T, atol=1e-14)
     assert H[1, 0] == 0.0                                    # H[j,1] = 0 after a restart (:1259-1263)
+    ctx.close()
+
+
+def test_lanczos_second_refinement_lockstep(pkg, O):
+    """A nearly invariant subspace (diag(1, ..., 1, 1 + 1e-8)): the first DGKS correction does not pass the 0.717 test, so the
+    second refinement round runs (src/dsaitr.jl:1424-1446) -- in the step kernel that is the on-demand sweep that forms
+    the second round's dot products (k_gs_step.cuh phases 3 and 4).  H, V and the counters against the oracle."""
+    n = 50
+    d = np.ones(n)
+    d[-1] = 1 + 1e-8
+    A = sp.diags(d).tocsr()
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), 4)
+    ora = O.Oracle(A, 4)
+    assert ctx.getv0()[0] == 0 and ora.dgetv0() == 0
+    H = np.zeros((4, 2))
+    info, rn = ctx.lanczos(0, 4, H, ctx.norm2_resid())
+    assert info == ora.dsaitr(0, 4) == 0
+    st, so = ctx.stats(), ora.stats()
+    assert st["nitref"] == so["nitref"] > 0 and st["nrorth"] == so["nrorth"] and st["nrstrt"] == so["nrstrt"]
+    assert np.array_equal(H, np.asarray(ora.H))
+    V = np.asarray(ctx.download_v())
+    assert np.array_equal(V, np.swapaxes(np.asarray(ora.Vt), 0, 1))
+    assert rn == ora.rnorm
     ctx.close()
 
 
@@ -504,6 +528,41 @@ def test_plain_dots_option(pkg, syn, O):
     assert np.max(np.abs(res.values - exact) / exact) <= 1e-10
 
 
+def test_normalize_tiny_rnorm_dlascl_branch(pkg, syn, O):
+    """src/dsaitr.jl:1097-1105: v_j = resid / rnorm is a multiplication by 1/rnorm only while rnorm >= floatmin; below
+    that the reference scales like dlascl (_scale_from_to(rnorm, 1, v), src/arpack-blas.jl:25-76) because 1/rnorm would
+    overflow.  A start vector of subnormal entries takes that branch on the device (k_vec.cu) and in the oracle.  The
+    oracle runs with the reference's x86 norm here (80-bit accumulators, src/arpack-blas-nrm2.jl:272-299): its
+    double-double norm (:157-215, the non-x86 path) squares in binary64 and returns 0 for such a vector, so only an
+    x86 run of the reference can reach this branch at all; the device norm (scaled three-range accumulation) agrees
+    with the x87 value."""
+    m, ncv = 16, 8
+    A = syn.to_scipy(syn.laplacian2d(m))
+    n = m * m
+    x = np.asarray(O.dlarnv(n)[0]) * 1e-310                          # subnormal entries
+    ctx = pkg.Context(pkg.ArpackSimpleOp(A), ncv)
+    ctx.upload_resid(x)
+    rn = ctx.norm2_resid()
+    assert 0.0 < rn < np.finfo(float).tiny
+    with O.arith("plain"):
+        ora = O.Oracle(A, ncv)
+        ora.resid[:] = x
+        assert rn == O.norm2(x)
+        ora.rnorm = rn
+        assert ora.dsaitr(0, 1) == 0
+        vo = np.asarray(ora.Vt)[0].copy()
+        Ho = np.asarray(ora.H)[:1].copy()
+        rno = ora.rnorm
+    H = np.zeros((ncv, 2))
+    info, rn1 = ctx.lanczos(0, 1, H, rn)
+    assert info == 0
+    v = np.asarray(ctx.download_v(0, 1))[:, 0]
+    assert np.array_equal(v, vo)                                     # element-wise scaling: the same bits
+    assert abs(np.linalg.norm(v) - 1.0) <= 1e-12                     # relative precision of subnormal inputs ~1e-13
+    assert np.allclose(H[:1], Ho, rtol=1e-13) and abs(rn1 - rno) <= 1e-13 * rno
+    ctx.close()
+
+
 def test_eigs_laplacian_analytic(pkg, syn, O):
     """C2 at reduced size: eigs(A, 10; ncv=40) on the 2-D Laplacian vs the analytic spectrum, the
     oracle, Ritz estimates (bounds <= tol*|lambda|) and true residuals."""
@@ -523,11 +582,30 @@ def test_eigs_laplacian_analytic(pkg, syn, O):
 
 
 def test_eigs_sprand_c1(pkg, syn, O):
-    """C1 (README example shape) at n = 20000: nev = 2, ncv = 12."""
-    A = syn.to_scipy(syn.sprand_sym(20000, 5.0, seed=1234))
+    """C1 at BASELINE size (README example shape): sprand-symmetric n = 100 000, nev = 2, ncv = 12, which = :LM.
+    Oracle parity: eigenvalues to 1e-10, identical restart and operator-application counts."""
+    A = syn.to_scipy(syn.sprand_sym(100000, 5.0, seed=1234))
     res, ora = _check_against_oracle(pkg, O, A, 2, 12)
+    assert int(res.iparam[2]) == ora["niter"] and res.stats["nopx"] == ora["stats"]["nopx"]
     Z = res.vectors
     assert np.max(np.linalg.norm(A @ Z - Z * res.values, axis=0) / np.abs(res.values)) <= 1e-10
+    assert np.allclose(Z.T @ Z, np.eye(2), atol=1e-12)
+
+
+def test_eigs_sprand_c3_double64(pkg, syn, O):
+    """C3 at BASELINE size: the C1 matrix in Double64 (double-double kernels), nev = 2, ncv = 12: eigenvalues to 1e-26
+    of the oracle's Double64 path, restart counts within +-1, Ritz residuals at the Double64 level."""
+    csr = syn.sprand_sym(100000, 5.0, seed=1234)
+    A = syn.to_scipy(csr)
+    res, ora = _check_against_oracle(pkg, O, A, 2, 12, dtype="dd")
+    assert abs(res.stats["nopx"] - ora["stats"]["nopx"]) <= 12
+    lam = np.asarray(res.values)
+    Z = np.asarray(res.vectors)                                    # (n, 2, (hi, lo))
+    for i in range(2):
+        z = Z[:, i, 0] + Z[:, i, 1]
+        r = A @ Z[:, i, 0] - lam[i, 0] * Z[:, i, 0]                # binary64 evaluation of the residual: bounded by eps64 |lambda|
+        assert np.linalg.norm(r) <= 64 * np.finfo(float).eps * abs(lam[i, 0])
+        assert abs(np.dot(z, z) - 1.0) <= 1e-14
 
 
 def test_eigs_complex_hermitian(pkg, syn, O):
@@ -624,6 +702,30 @@ def test_svds_golden_values(pkg):
     _check_svd(Ac, U, s, V, tol=60)
     U, s, V = pkg.svds(A, 2, which="SA", ritzvec=False)
     assert U.shape[1] == 0 and V.shape[1] == 0 and len(s) == 2
+
+
+def test_svds_singular_case(pkg):
+    """test/interface_simple.jl:83-98 on the device: a rank-deficient tall matrix, smallest singular values.
+    svds(A, 1; which=:SA, ncv=2) must raise (nev < ncv leaves no room: the reference's ArpackException), the ncv = 20
+    solve either meets sigma ~ 0 while forming U (ArpackException, src/idonow_ops.jl:300-303) or returns residuals within
+    n sqrt(eps), and svds(A, 2; which=:SA, ritzvec=false) returns [0, 0] with empty U, V."""
+    import scipy.sparse as sp
+
+    n = 80
+    A = sp.vstack([sp.diags(np.arange(1.0, n + 1)), sp.csr_matrix((20, n))]).tolil()
+    A[n - 5:n, n - 5:n] = 0
+    A = A.tocsr()
+    with pytest.raises((pkg.ArpackException, ValueError)):
+        pkg.svds(A, 1, which="SA", ncv=2)
+    try:
+        U, s, V = pkg.svds(A, 1, which="SA", ncv=20)
+    except pkg.ArpackException as e:
+        assert "sigma" in str(e)
+    else:
+        assert np.max(pkg.svd_residuals(A, U, s, V)) <= n * np.sqrt(np.finfo(float).eps)
+    U, s, V = pkg.svds(A, 2, which="SA", ritzvec=False)
+    assert np.allclose(s, [0.0, 0.0], atol=2 * n * np.sqrt(np.finfo(float).eps))
+    assert U.shape[1] == 0 and V.shape[1] == 0
 
 
 def test_svds_arpack_example(pkg):

@@ -25,6 +25,9 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static void clear_operator(ga_ctx* c) {   // before a new operator is installed
+  for (auto& w : c->Wblk) w.free_all();
+  c->Wblk.clear();
+  c->wblk_cols = 0;
   c->op_kind = 0;
   c->op_cb = c->av_cb = c->atv_cb = nullptr;
   c->op_user = nullptr;
@@ -101,6 +104,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
   if (const char* e = getenv("GA_SPMV_V1")) c->use_spmv_stream = !(e[0] == '1');
   if (const char* e = getenv("GA_GS_XPREFETCH")) c->gs_xprefetch = !(e[0] == '0');
+  if (const char* e = getenv("GA_NORMAL_COLBLOCK")) c->normal_colblock = atoll(e) > 0 ? atoll(e) : 0;
   if (const char* e = getenv("GA_GS_SEG1024_FROM")) c->gs_seg1024_from = atoi(e) > 0 ? atoi(e) : c->gs_seg1024_from;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
@@ -131,6 +135,7 @@ void ga_destroy(ga_ctx* c) {
   comm_destroy(c);
   c->A.free_all();
   c->At.free_all();
+  for (auto& w : c->Wblk) w.free_all();
   general_free(c);
   cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev); cudaFree(c->wbuf);
@@ -228,6 +233,27 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
   return spmv_autotune(c, c->A, c->V, c->resid);
 }
 
+// Host transpose (conjugate transpose for ComplexF64) of rows [r0, r1) of a CSR matrix with `ncols` columns: the result
+// has `ncols` rows and r1 - r0 columns (local indices).  Counting sort, entries of a row in ascending column order.
+static void csr_slab_adjoint(const ga_ctx* c, int64_t r0, int64_t r1, int64_t ncols, const int64_t* rowptr, const int32_t* col,
+                             const void* val, std::vector<int64_t>& tp, std::vector<int32_t>& tc, std::vector<char>& tv) {
+  const size_t es = c->esize;
+  const int64_t k0 = rowptr[r0], nnz = rowptr[r1] - k0;
+  tp.assign((size_t)ncols + 1, 0);
+  for (int64_t k = 0; k < nnz; ++k) tp[(size_t)col[k0 + k] + 1]++;
+  for (int64_t j = 0; j < ncols; ++j) tp[(size_t)j + 1] += tp[(size_t)j];
+  tc.resize((size_t)std::max<int64_t>(nnz, 1));
+  tv.resize((size_t)std::max<int64_t>(nnz, 1) * es);
+  std::vector<int64_t> pos(tp.begin(), tp.end() - 1);
+  for (int64_t i = r0; i < r1; ++i)
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int64_t d = pos[(size_t)col[k]]++;
+      tc[(size_t)d] = (int32_t)(i - r0);
+      memcpy(&tv[(size_t)d * es], (const char*)val + (size_t)k * es, es);
+      if (c->dtype == GA_C64) ((double*)&tv[(size_t)d * es])[1] *= -1.0;
+    }
+}
+
 int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col, const void* val) {
   if (!c || !rowptr || !col || !val || m <= 0 || n <= 0) return GA_ERR_ARG;
   if (c->world != 1) return set_err(c, GA_ERR_ARG, "multi-GPU contexts take ga_set_normal_csr_dist (this rank's rows of the tall orientation + halo plan)");
@@ -235,29 +261,56 @@ int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, co
   if (c->n != (left ? n : m)) return set_err(c, GA_ERR_ARG, "normal operator: context size must be min(m, n) side");
   GA_CUDA(c, cudaSetDevice(c->device));
   clear_operator(c);
-  int rc = csr_upload(c, c->A, m, n, rowptr, col, val, 0);
-  if (rc) return rc;
-  // explicit adjoint (conjugate transpose) CSR, built on the host once
-  const i64 nnz = rowptr[m];
-  std::vector<int64_t> tp((size_t)n + 1, 0);
-  for (i64 k = 0; k < nnz; ++k) tp[(size_t)col[k] + 1]++;
-  for (i64 j = 0; j < n; ++j) tp[(size_t)j + 1] += tp[(size_t)j];
-  std::vector<int32_t> tc((size_t)nnz);
-  std::vector<char> tv((size_t)nnz * c->esize);
-  std::vector<int64_t> pos(tp.begin(), tp.end() - 1);
-  for (i64 i = 0; i < m; ++i)
-    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-      const i64 d = pos[(size_t)col[k]]++;
-      tc[(size_t)d] = (int32_t)i;
-      memcpy(&tv[(size_t)d * c->esize], (const char*)val + (size_t)k * c->esize, c->esize);
-      if (c->dtype == GA_C64) {
-        double* z = (double*)&tv[(size_t)d * c->esize];
-        z[1] = -z[1];
+  // The long vector of the normal operator (max(m, n) entries) is the x of the second product.  Beyond ~64 MiB its
+  // random gathers miss L2: the wide matrix is then kept in column blocks of 32 MiB of that vector (k_spmv.cu:normal_wide)
+  const i64 longside = left ? m : n;
+  i64 blockw = c->normal_colblock > 0 ? c->normal_colblock : ((i64)longside * (i64)c->esize > (64LL << 20) ? (32LL << 20) / (i64)c->esize : 0);
+  if (blockw > 0) blockw = (blockw + row_pad(c) - 1) / row_pad(c) * row_pad(c);
+  const bool blocked = blockw > 0 && blockw < longside;
+  // A and A^H.  Blocked: only the TALL one of the two is uploaded whole (it is the first product, and the half
+  // ga_svd_vectors applies); the wide one exists as column blocks = adjoints of row slabs of the tall one.
+  int rc = 0;
+  std::vector<int64_t> tp;
+  std::vector<int32_t> tc;
+  std::vector<char> tv;
+  if (!blocked || left) {
+    if ((rc = csr_upload(c, c->A, m, n, rowptr, col, val, 0))) return rc;
+  } else {
+    c->A.free_all();
+  }
+  if (!blocked || !left) {
+    csr_slab_adjoint(c, 0, m, n, rowptr, col, val, tp, tc, tv);            // A^H: n x m
+    if ((rc = csr_upload(c, c->At, n, m, tp.data(), tc.data(), tv.data(), 0))) return rc;
+  } else {
+    c->At.free_all();
+  }
+  if (blocked) {
+    const i64 nb = (longside + blockw - 1) / blockw;
+    c->Wblk.resize((size_t)nb);
+    c->wblk_cols = blockw;
+    if (left) {
+      // wide = A^H (n x m): column block b = adjoint of rows [b w, (b+1) w) of A
+      std::vector<int64_t> bp;
+      std::vector<int32_t> bc;
+      std::vector<char> bv;
+      for (i64 b = 0; b < nb; ++b) {
+        const i64 r0 = b * blockw, r1 = std::min<i64>(m, r0 + blockw);
+        csr_slab_adjoint(c, r0, r1, n, rowptr, col, val, bp, bc, bv);
+        if ((rc = csr_upload(c, c->Wblk[(size_t)b], n, r1 - r0, bp.data(), bc.data(), bv.data(), 0))) return rc;
+      }
+    } else {
+      // wide = A (m x n): column block b = adjoint of rows [b w, (b+1) w) of A^H (held in tp / tc / tv)
+      std::vector<int64_t> bp;
+      std::vector<int32_t> bc;
+      std::vector<char> bv;
+      for (i64 b = 0; b < nb; ++b) {
+        const i64 r0 = b * blockw, r1 = std::min<i64>(n, r0 + blockw);
+        csr_slab_adjoint(c, r0, r1, m, tp.data(), tc.data(), tv.data(), bp, bc, bv);
+        if ((rc = csr_upload(c, c->Wblk[(size_t)b], m, r1 - r0, bp.data(), bc.data(), bv.data(), 0))) return rc;
       }
     }
-  rc = csr_upload(c, c->At, n, m, tp.data(), tc.data(), tv.data(), 0);
-  if (rc) return rc;
-  c->normal_m = m; c->normal_n = n; c->normal_left = left;
+  }
+  c->normal_m = m; c->normal_n = n; c->normal_left = left; c->normal_dist = false;
   const i64 extra = left ? m : n;
   const i64 extra_pad = (extra + row_pad(c) - 1) / row_pad(c) * row_pad(c);
   cudaFree(c->xfull);
@@ -266,10 +319,17 @@ int ga_set_normal_csr(ga_ctx* c, int64_t m, int64_t n, const int64_t* rowptr, co
   GA_CUDA(c, cudaMemset(c->xfull, 0, (size_t)extra_pad * c->esize));
   c->xfull_len = extra_pad;
   c->op_kind = 2;
-  // A: m x n (x has n entries, y has m); At: n x m.  V's first column / resid / xfull serve as operands.
-  const bool a_first = left;   // left: x (problem size n) -> A -> xfull (m) -> At -> resid
-  if ((rc = spmv_autotune(c, c->A, a_first ? c->V : c->xfull, a_first ? c->xfull : c->resid))) return rc;
-  return spmv_autotune(c, c->At, a_first ? c->xfull : c->V, a_first ? c->resid : c->xfull);
+  // autotune the streamed SpMV per matrix.  V's first column / resid / xfull serve as operands.
+  // left: x (n) -> A -> xfull (m) -> A^H -> resid;  right: x (m) -> A^H -> xfull (n) -> A -> resid
+  CsrDev& tall = left ? c->A : c->At;
+  if ((rc = spmv_autotune(c, tall, c->V, c->xfull))) return rc;
+  if (!blocked) return spmv_autotune(c, left ? c->At : c->A, c->xfull, c->resid);
+  if ((rc = spmv_autotune(c, c->Wblk[0], c->xfull, c->resid))) return rc;
+  for (size_t b = 1; b < c->Wblk.size(); ++b) {
+    c->Wblk[b].tune_groups = c->Wblk[0].tune_groups;
+    c->Wblk[b].tune_stages = c->Wblk[0].tune_stages;
+  }
+  return 0;
 }
 
 // Row-sharded normal operator (see the header): T_loc and its adjoint in the [own | halo] column space.

@@ -153,6 +153,9 @@ struct ga_ctx {
   ga_op_fn op_cb = nullptr, av_cb = nullptr, atv_cb = nullptr; void* op_user = nullptr;
   const void* gs_dotvec = nullptr;     // when set, the MODE 0 sweep forms V' * (this vector) instead of V' * resid
   ga::i64 normal_m = 0, normal_n = 0; bool normal_left = true;
+  std::vector<ga::CsrDev> Wblk;      // normal operator, single GPU: the wide matrix of the second product in column blocks (k_spmv.cu:normal_wide)
+  ga::i64 wblk_cols = 0;             // columns per block
+  ga::i64 normal_colblock = 0;       // forced block width (GA_NORMAL_COLBLOCK at ga_create; 0 = automatic: 32 MiB of the long vector)
 
   // collectives (NCCL, loaded at run time)
   void* nccl_comm = nullptr;

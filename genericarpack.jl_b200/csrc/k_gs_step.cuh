@@ -70,6 +70,20 @@ __device__ __forceinline__ void grid_barrier(DevCtl* ctl) {
 template <class T, bool PLAIN> struct StepAcc { typedef typename Elem<T>::acc_t type; };
 template <> struct StepAcc<double, true> { typedef double type; };
 
+// one round of the in-warp butterfly on a reduced slot; the first argument only selects the arithmetic (the accumulator type)
+__device__ __forceinline__ double2 slot_from_acc(double v) { return make_double2(v, 0.0); }
+__device__ __forceinline__ double2 slot_from_acc(dot2 v) { double h, l; two_sum(v.hi, v.lo, h, l); return make_double2(h, l); }
+__device__ __forceinline__ double2 slot_from_acc(cdbl v) { return make_double2(v.re, v.im); }
+__device__ __forceinline__ double2 slot_from_acc(ddbl v) { return make_double2(v.hi, v.lo); }
+__device__ __forceinline__ double2 slot_butterfly(double, double2 s, int m) { s.x += shfl_xor_d(s.x, m); return s; }   // plain tree (warp_sum_slot_fast(double))
+__device__ __forceinline__ double2 slot_butterfly(cdbl, double2 s, int m) { s.x += shfl_xor_d(s.x, m); s.y += shfl_xor_d(s.y, m); return s; }
+__device__ __forceinline__ double2 slot_butterfly_dd(double2 s, int m) {
+  const ddbl r = dd_add(ddbl(s.x, s.y), ddbl(shfl_xor_d(s.x, m), shfl_xor_d(s.y, m)));
+  return make_double2(r.hi, r.lo);
+}
+__device__ __forceinline__ double2 slot_butterfly(dot2, double2 s, int m) { return slot_butterfly_dd(s, m); }
+__device__ __forceinline__ double2 slot_butterfly(ddbl, double2 s, int m) { return slot_butterfly_dd(s, m); }
+
 // NCT = register accumulators per consumer thread = ceil(j / TG): the thread's columns are g, g + TG, ...
 template <class T, int SEG, int NCT, bool PLAIN>
 __global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
@@ -248,21 +262,34 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
         ++kk;
       }
       GA_TRACE(2 + 8 * ph, blockIdx.x == 0 && tid == 0)
+      // Warp-level sums of all accumulators at once: the butterfly rounds are the OUTER loop, so the NCT (and the three
+      // norm) dependent chains of double-double additions interleave instead of running one after the other (this sits
+      // on the critical path between two sweeps).  Same operations per value as warp_sum_slot_fast / warp_sum_dd.
       if (mode != 2) {
+        double2 sl[NCT];
 #pragma unroll
-        for (int i = 0; i < NCT; ++i) {
-          if (g + TG * i < j) {
-            double2 sl = warp_sum_slot_fast(acc[i]);
-            if (lane == 0) redw[warp * (NC + 3) + i] = sl;
-          }
+        for (int i = 0; i < NCT; ++i) sl[i] = slot_from_acc(acc[i]);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+#pragma unroll
+          for (int i = 0; i < NCT; ++i) sl[i] = slot_butterfly(acc[i], sl[i], m);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < NCT; ++i)
+            if (g + TG * i < j) redw[warp * (NC + 3) + i] = sl[i];
         }
       }
       if (g == 0) {
-        ddbl m = warp_sum_dd(nacc.med), b = warp_sum_dd(nacc.big), sm = warp_sum_dd(nacc.sml);
+        ddbl nn[3] = {nacc.med, nacc.big, nacc.sml};
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) nn[k] = dd_add(nn[k], ddbl(shfl_xor_d(nn[k].hi, m), shfl_xor_d(nn[k].lo, m)));
+        }
         if (lane == 0) {
-          redw[warp * (NC + 3) + NC + 0] = make_double2(m.hi, m.lo);
-          redw[warp * (NC + 3) + NC + 1] = make_double2(b.hi, b.lo);
-          redw[warp * (NC + 3) + NC + 2] = make_double2(sm.hi, sm.lo);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) redw[warp * (NC + 3) + NC + k] = make_double2(nn[k].hi, nn[k].lo);
         }
       }
       // r was written with generic-proxy stores; the next phase reads it with TMA (async proxy)

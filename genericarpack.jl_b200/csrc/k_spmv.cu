@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
                                                               const T* __restrict__ val, const T* __restrict__ x,
                                                               const T* xh, int nsplit,
                                                               T* __restrict__ y, DevCtl* ctl, int gated,
-                                                              const DevComm* cm) {
+                                                              const DevComm* cm, int accumulate) {
   typedef SpmvCfg<T> C;
   if (gated && ctl->status != ST_OK) return;
   if (cm) {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
     __syncthreads();
     for (int r = r0 + tid; r < r1; r += C::THREADS) {
       const int a = rowptr[r] - k0, b = rowptr[r + 1] - k0;
-      T s = Elem<T>::zero();
+      T s = accumulate ? y[r] : Elem<T>::zero();      // column-blocked operators: continue the row's running sum
       for (int q = a; q < b; ++q) Elem<T>::add(s, prod[q]);
       y[r] = s;
     }
@@ -87,7 +87,11 @@ __global__ void __launch_bounds__(SpmvCfg<T>::THREADS) k_spmv(const int* __restr
       if (tid < off) { T a = prod[tid]; Elem<T>::add(a, prod[tid + off]); prod[tid] = a; }
       __syncthreads();
     }
-    if (tid == 0) y[r0] = prod[0];
+    if (tid == 0) {
+      T a = prod[0];
+      if (accumulate) { T b = y[r0]; Elem<T>::add(b, a); a = b; }
+      y[r0] = a;
+    }
   }
 }
 
@@ -139,7 +143,7 @@ template <class T, int NG>
 __global__ void __launch_bounds__(SpmvStreamCfg<T, NG>::THREADS, 1)
 k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ rowptr, const int* __restrict__ col,
               const T* __restrict__ val, const T* __restrict__ x, const T* xh, int nsplit,
-              T* __restrict__ y, DevCtl* ctl, int gated, const DevComm* cm, int NST, unsigned int* chk) {
+              T* __restrict__ y, DevCtl* ctl, int gated, const DevComm* cm, int NST, unsigned int* chk, int accumulate) {
   typedef SpmvStreamCfg<T, NG> C;
   constexpr int GT = C::GT, GROUPS = C::GROUPS;
   if (gated && ctl->status != ST_OK) return;
@@ -239,7 +243,7 @@ k_spmv_stream(const int4* __restrict__ desc, int ndesc, const int* __restrict__ 
     const int nr = d.y - d.x;
     for (int r = gt; r < nr; r += GT) {
       const int a = rp[r] - k0, e = rp[r + 1] - k0;
-      T sum = Elem<T>::zero();
+      T sum = accumulate ? y[d.x + r] : Elem<T>::zero();   // column-blocked operators: continue the row's running sum
       for (int q = a; q < e; ++q) Elem<T>::add(sum, vs[q]);
       y[d.x + r] = sum;
     }
@@ -256,7 +260,8 @@ template <class T>
 __global__ void __launch_bounds__(256) k_spmv_long(const int* __restrict__ longrow, const int* __restrict__ rowptr,
                                                    const int* __restrict__ col, const T* __restrict__ val,
                                                    const T* __restrict__ x, const T* xh, int nsplit,
-                                                   T* __restrict__ y, DevCtl* ctl, int gated, const DevComm* cm) {
+                                                   T* __restrict__ y, DevCtl* ctl, int gated, const DevComm* cm,
+                                                   int accumulate) {
   if (gated && ctl->status != ST_OK) return;
   if (cm) {
     if (threadIdx.x < (unsigned)cm->world && cm->recv_counts[threadIdx.x] > 0)
@@ -274,7 +279,11 @@ __global__ void __launch_bounds__(256) k_spmv_long(const int* __restrict__ longr
     if (tid < off) { T a = red[tid]; Elem<T>::add(a, red[tid + off]); red[tid] = a; }
     __syncthreads();
   }
-  if (tid == 0) y[r] = red[0];
+  if (tid == 0) {
+    T a = red[0];
+    if (accumulate) { T b = y[r]; Elem<T>::add(b, a); a = b; }
+    y[r] = a;
+  }
 }
 
 // tuning overrides (GA_SPMV_STAGES, GA_SPMV_GROUPS); 0 = use the per-matrix autotuned values
@@ -288,7 +297,7 @@ static void spmv_read_env() {
 
 template <class T, int NG>
 static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, int nsplit,
-                                const DevComm* cm, int nst) {
+                                const DevComm* cm, int nst, bool accumulate) {
   typedef SpmvStreamCfg<T, NG> C;
   static PerDeviceOnce attr_set;
   if (attr_set.need(c->device)) {
@@ -301,14 +310,14 @@ static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void*
   k_spmv_stream<T, NG><<<grid, C::THREADS, C::smem_bytes(nst), c->stream>>>(M.desc, M.ndesc, M.rowptr, M.col,
                                                                            (const T*)M.val, (const T*)x,
                                                                            (const T*)c->halo, nsplit, (T*)y, c->ctl,
-                                                                           gated ? 1 : 0, cm, nst, c->spmv_chk);
+                                                                           gated ? 1 : 0, cm, nst, c->spmv_chk, accumulate ? 1 : 0);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   return 0;
 }
 
 template <class T>
-static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
+static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo, bool accumulate) {
   typedef SpmvStreamCfg<T> C;
   const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
   const int nsplit = split ? (int)c->n_pad : 2147483647;
@@ -319,13 +328,13 @@ static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void*
   if (g_spmv_force_groups > 0) ngroups = g_spmv_force_groups;
   if (nst > C::MAX_STAGES) nst = C::MAX_STAGES;
   if (M.ndesc > 0) {
-    int rc = ngroups == 6 ? spmv_stream_launch_g<T, 6>(c, M, x, y, gated, nsplit, cm, nst)
-                          : spmv_stream_launch_g<T, 4>(c, M, x, y, gated, nsplit, cm, nst);
+    int rc = ngroups == 6 ? spmv_stream_launch_g<T, 6>(c, M, x, y, gated, nsplit, cm, nst, accumulate)
+                          : spmv_stream_launch_g<T, 4>(c, M, x, y, gated, nsplit, cm, nst, accumulate);
     if (rc) return rc;
   }
   if (M.nlong > 0) {
     k_spmv_long<T><<<M.nlong, 256, 0, c->stream>>>(M.longrow, M.rowptr, M.col, (const T*)M.val, (const T*)x,
-                                                  (const T*)c->halo, nsplit, (T*)y, c->ctl, gated ? 1 : 0, cm);
+                                                  (const T*)c->halo, nsplit, (T*)y, c->ctl, gated ? 1 : 0, cm, accumulate ? 1 : 0);
     GA_CUDA(c, cudaGetLastError());
     c->launches += 1;
   }
@@ -333,28 +342,28 @@ static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void*
 }
 
 template <class T>
-static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) {
+static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo, bool accumulate) {
   if (M.nblk <= 0) return;
   const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
   k_spmv<T><<<M.nblk, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
                                                           (const T*)c->halo, split ? (int)c->n_pad : 2147483647,
                                                           (T*)y, c->ctl, gated ? 1 : 0,
-                                                          (split && wait_halo) ? c->devcomm : nullptr);
+                                                          (split && wait_halo) ? c->devcomm : nullptr, accumulate ? 1 : 0);
 }
-static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo = false) {
+static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo = false, bool accumulate = false) {
   if (c->use_spmv_stream) {
     switch (c->dtype) {
-      case GA_F64: return spmv_stream_launch_t<double>(c, M, x, y, gated, wait_halo);
-      case GA_C64: return spmv_stream_launch_t<cdbl>(c, M, x, y, gated, wait_halo);
-      case GA_F32: return spmv_stream_launch_t<float>(c, M, x, y, gated, wait_halo);
-      default: return spmv_stream_launch_t<ddbl>(c, M, x, y, gated, wait_halo);
+      case GA_F64: return spmv_stream_launch_t<double>(c, M, x, y, gated, wait_halo, accumulate);
+      case GA_C64: return spmv_stream_launch_t<cdbl>(c, M, x, y, gated, wait_halo, accumulate);
+      case GA_F32: return spmv_stream_launch_t<float>(c, M, x, y, gated, wait_halo, accumulate);
+      default: return spmv_stream_launch_t<ddbl>(c, M, x, y, gated, wait_halo, accumulate);
     }
   }
   switch (c->dtype) {
-    case GA_F64: spmv_launch_t<double>(c, M, x, y, gated, wait_halo); break;
-    case GA_C64: spmv_launch_t<cdbl>(c, M, x, y, gated, wait_halo); break;
-    case GA_F32: spmv_launch_t<float>(c, M, x, y, gated, wait_halo); break;
-    default: spmv_launch_t<ddbl>(c, M, x, y, gated, wait_halo); break;
+    case GA_F64: spmv_launch_t<double>(c, M, x, y, gated, wait_halo, accumulate); break;
+    case GA_C64: spmv_launch_t<cdbl>(c, M, x, y, gated, wait_halo, accumulate); break;
+    case GA_F32: spmv_launch_t<float>(c, M, x, y, gated, wait_halo, accumulate); break;
+    default: spmv_launch_t<ddbl>(c, M, x, y, gated, wait_halo, accumulate); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
@@ -471,6 +480,20 @@ static int normal_half(ga_ctx* c, bool adjoint, const void* x, void* y, bool gat
   return spmv_launch(c, adjoint ? c->At : c->A, x, y, gated);
 }
 
+// Second product of the normal operator, y = W z with the WIDE matrix W (A^H for a tall A, A for a wide one) and the
+// long intermediate z.  Its x gathers are random over z: at C5's size (z = 50M doubles) almost every gather is its own
+// 32-byte DRAM sector and the product runs at ~0.4 of the HBM peak.  W is therefore stored in COLUMN BLOCKS whose slice
+// of z stays L2-resident (ga_set_normal_csr); the blocks are applied in ascending column order, each continuing the
+// row's running sum, so every y_i sees the same additions in the same order as the unblocked row sum: same bits.
+static int normal_wide(ga_ctx* c, const void* z, void* y, bool gated) {
+  if (c->Wblk.empty()) return spmv_launch(c, c->normal_left ? c->At : c->A, z, y, gated);
+  for (size_t b = 0; b < c->Wblk.size(); ++b) {
+    int rc = spmv_launch(c, c->Wblk[b], (const char*)z + (size_t)b * c->wblk_cols * c->esize, y, gated, false, b > 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // y = OP x for device vectors of the (local) problem size.
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
@@ -490,11 +513,11 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   if (c->normal_left) {
     int rc = normal_half(c, false, xin, c->xfull, gated);
     if (rc) return rc;
-    return normal_half(c, true, c->xfull, y, gated);
+    return c->av_cb ? normal_half(c, true, c->xfull, y, gated) : normal_wide(c, c->xfull, y, gated);
   } else {
     int rc = normal_half(c, true, xin, c->xfull, gated);
     if (rc) return rc;
-    return normal_half(c, false, c->xfull, y, gated);
+    return c->av_cb ? normal_half(c, false, c->xfull, y, gated) : normal_wide(c, c->xfull, y, gated);
   }
 }
 

@@ -190,6 +190,39 @@ def test_normal_opx(pkg, syn, O):
     ctx2.close()
 
 
+@pytest.mark.parametrize("dtype", ["f64", "c64"])
+def test_normal_opx_column_blocked(pkg, syn, O, dtype, monkeypatch):
+    """The second product of the normal operator in column blocks (k_spmv.cu:normal_wide; automatic above 64 MiB of long
+    vector, forced here with GA_NORMAL_COLBLOCK so that a small matrix takes 10 blocks): every block continues the row's
+    running sum, so the result is the same bits as the unblocked product -- for a tall A (blocks of A^H), for a wide A
+    (blocks of A), with rows that are empty inside a block, and through a whole svds."""
+    A = syn.to_scipy(syn.tall_sparse(5000, 300, 6))
+    if dtype == "c64":
+        A = (A + 1j * A.multiply(A > 0.5)).tocsr()
+    x, _ = O.dlarnv(300, dtype=O.C64 if dtype == "c64" else O.F64)
+    x = np.asarray(x)
+    ref = A.conj().T @ (A @ x)
+    res = {}
+    for blocked in (False, True):
+        if blocked:
+            monkeypatch.setenv("GA_NORMAL_COLBLOCK", "512")
+        else:
+            monkeypatch.delenv("GA_NORMAL_COLBLOCK", raising=False)
+        for name, M in (("tall", A), ("wide", A.conj().T.tocsr())):
+            ctx = pkg.Context(pkg.ArpackNormalOp(M, dtype=dtype), 4)
+            res[(name, blocked)] = np.asarray(ctx.opx(x)).copy()
+            ctx.close()
+    for name in ("tall", "wide"):
+        assert np.allclose(res[(name, False)], ref, rtol=1e-12)
+        assert np.array_equal(res[(name, True)], res[(name, False)])
+    if dtype == "f64":
+        monkeypatch.setenv("GA_NORMAL_COLBLOCK", "512")
+        U, S, V = pkg.svds(A, 3, ncv=12)
+        monkeypatch.delenv("GA_NORMAL_COLBLOCK", raising=False)
+        U0, S0, V0 = pkg.svds(A, 3, ncv=12)
+        assert np.array_equal(S, S0) and np.array_equal(V, V0) and np.array_equal(U, U0)
+
+
 # ---------------------------------------------------------------- dsaitr
 def _run_both(pkg, O, A, ncv, dtype, k_np_list):
     op = pkg.ArpackSimpleOp(A, dtype=dtype)

@@ -83,6 +83,15 @@ __device__ __forceinline__ double2 slot_butterfly_dd(double2 s, int m) {
 }
 __device__ __forceinline__ double2 slot_butterfly(dot2, double2 s, int m) { return slot_butterfly_dd(s, m); }
 __device__ __forceinline__ double2 slot_butterfly(ddbl, double2 s, int m) { return slot_butterfly_dd(s, m); }
+// a + b for two reduced slots, in the arithmetic of the accumulator kind (first argument: tag only)
+__device__ __forceinline__ double2 slot_add_recv(double, double2 a, double2 b) { return make_double2(a.x + b.x, 0.0); }
+__device__ __forceinline__ double2 slot_add_recv(cdbl, double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 slot_add_recv_dd(double2 a, double2 b) {
+  const ddbl r = dd_add(ddbl(a.x, a.y), ddbl(b.x, b.y));
+  return make_double2(r.hi, r.lo);
+}
+__device__ __forceinline__ double2 slot_add_recv(dot2, double2 a, double2 b) { return slot_add_recv_dd(a, b); }
+__device__ __forceinline__ double2 slot_add_recv(ddbl, double2 a, double2 b) { return slot_add_recv_dd(a, b); }
 
 // NCT = register accumulators per consumer thread = ceil(j / TG): the thread's columns are g, g + TG, ...
 template <class T, int SEG, int NCT, bool PLAIN>
@@ -262,23 +271,33 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
         ++kk;
       }
       GA_TRACE(2 + 8 * ph, blockIdx.x == 0 && tid == 0)
-      // Warp-level sums of all accumulators at once: the butterfly rounds are the OUTER loop, so the NCT (and the three
-      // norm) dependent chains of double-double additions interleave instead of running one after the other (this sits
-      // on the critical path between two sweeps).  Same operations per value as warp_sum_slot_fast / warp_sum_dd.
+      // Warp-level sums of all NCT accumulators.  A butterfly per value costs 5 double-double additions per lane and value
+      // (with error-free dots that was 3 us of FP64 work per phase for the 16 warps of a CTA, on the critical path between
+      // two sweeps); here the values are reduced TRANSPOSED: in the round with lane mask m a lane keeps one half of its
+      // values and hands the other half to its partner, so after log2(NP) rounds every lane owns one value (index
+      // lane / (32 / NP)) summed over a subset of lanes, and ordinary butterfly rounds finish it: NP - 1 + 5 - log2(NP)
+      // additions per lane instead of 5 * NCT.
       if (mode != 2) {
-        double2 sl[NCT];
+        constexpr int NP = NCT <= 1 ? 1 : NCT <= 2 ? 2 : NCT <= 4 ? 4 : NCT <= 8 ? 8 : 16;
+        double2 sl[NP];
 #pragma unroll
-        for (int i = 0; i < NCT; ++i) sl[i] = slot_from_acc(acc[i]);
+        for (int i = 0; i < NP; ++i) sl[i] = i < NCT ? slot_from_acc(acc[i < NCT ? i : 0]) : make_double2(0.0, 0.0);
+        int m = 16;
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
+        for (int h = NP / 2; h >= 1; h >>= 1, m >>= 1) {
+          const bool up = (lane & m) != 0;
 #pragma unroll
-          for (int i = 0; i < NCT; ++i) sl[i] = slot_butterfly(acc[i], sl[i], m);
+          for (int i = 0; i < h; ++i) {
+            const double2 send = up ? sl[i] : sl[i + h];
+            const double2 keep = up ? sl[i + h] : sl[i];
+            sl[i] = slot_add_recv(acc[0], keep, make_double2(shfl_xor_d(send.x, m), shfl_xor_d(send.y, m)));
+          }
         }
-        if (lane == 0) {
 #pragma unroll
-          for (int i = 0; i < NCT; ++i)
-            if (g + TG * i < j) redw[warp * (NC + 3) + i] = sl[i];
-        }
+        for (; m >= 1; m >>= 1) sl[0] = slot_add_recv(acc[0], sl[0], make_double2(shfl_xor_d(sl[0].x, m), shfl_xor_d(sl[0].y, m)));
+        constexpr int LPV = 32 / NP;                   // lanes per value
+        const int idx = lane / LPV;
+        if ((lane % LPV) == 0 && idx < NCT && g + TG * idx < j) redw[warp * (NC + 3) + idx] = sl[0];
       }
       if (g == 0) {
         ddbl nn[3] = {nacc.med, nacc.big, nacc.sml};

@@ -97,7 +97,13 @@ int ga_comm_ipc_import(ga_ctx* ctx, const void* all_handles /* world x 128 bytes
  * ga_set_csr: ArpackSimpleOp(A) (src/idonow_ops.jl:115-123).  Full (both triangles) CSR of the
  * n_local rows owned by this rank, global column indices, 0-based.  val has the ctx dtype.
  * ga_set_normal_csr: ArpackNormalOp(A) for svds (src/idonow_ops.jl:216-277): A is m x n CSR,
- * OP = A^H A (m > n, problem size n) or A A^H (m <= n, problem size m). */
+ * OP = A^H A (m > n, problem size n) or A A^H (m <= n, problem size m).  When the long side exceeds 64 MiB of vector the
+ * wide matrix of the second product is kept in column blocks whose slice of the intermediate stays L2-resident; the
+ * result is bit-identical to the unblocked product.
+ * Limits (all ga_set_*csr* calls; GA_ERR_ARG with a message in ga_last_error): per GPU at most 2^31 - 1 rows and
+ * 2^31 - 1 stored entries (the device copy of rowptr is 32-bit); rowptr must be non-decreasing and every column index
+ * inside [0, ncols) (checked at upload: the kernels gather x[col] unchecked).  The basis is limited to
+ * ncv <= GA_MAX_NCV columns (ga_create; the Gram-Schmidt kernels keep a thread's accumulators in registers). */
 int ga_set_csr(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col, const void* val);
 /* Row-sharded ArpackSimpleOp (world_size > 1).  The caller (who owns rendezvous) remaps the
  * columns of this rank's rows: own column g -> g - row_offset; remote column -> n_pad + its

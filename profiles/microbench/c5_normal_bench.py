@@ -12,7 +12,10 @@ t0 = time.time(); csr = syn.tall_sparse_stream(m, n, 10); tgen = time.time() - t
 nnz = int(csr[0][-1])
 alg_bytes = 2 * (nnz * 12 + (m + 1) * 8) + 8 * (2 * n + 2 * m)          # normal-operator apply
 out = {"m": m, "n": n, "nnz": nnz, "gen_s": round(tgen, 1), "algorithmic_GB_per_apply": round(alg_bytes / 1e9, 3)}
-for label, env in (("unblocked", str(1 << 40)), ("blocked_32MiB", None)):
+sweep = [("unblocked", str(1 << 40)), ("blocked_32MiB", None)]
+if len(sys.argv) > 2 and sys.argv[2] == "sweep":      # block width in elements of the long vector
+    sweep = [("blocked_%dMiB" % (w * 8 >> 20), str(w)) for w in (1 << 20, 1 << 21, 1 << 22, 1 << 23)]
+for label, env in sweep:
     if env is None:
         os.environ.pop("GA_NORMAL_COLBLOCK", None)
     else:

@@ -1,5 +1,6 @@
 // Device-side control block and the per-problem context of the B200 Lanczos library.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
@@ -197,6 +198,9 @@ struct ga_ctx {
   bool coop = false;                    // device supports cooperative launches (persistent step kernel)
   bool use_step_kernel = true;
   bool dot_plain = false;               // GA_OPT_DOT_MODE = GA_DOT_PLAIN: one FMA per product in the Float64 step kernel (default: Dot2)
+  int gs_min_stages_2k = 3;             // step kernel: 2 KiB column segments need this many ring stages, else 1 KiB tiles moved by tensor-map copies (GA_GS_MIN2K: 2 = the round-1 rule)
+  std::vector<CUtensorMap> gs_maps;     // tensor maps of V, box = R rows x j columns, index j (lazily encoded; k_gs_step.cu)
+  std::vector<char> gs_maps_ok;
   int gs_seg1024_from = 1 << 30;        // step kernel: 1 KiB column segments from this many columns on (default: only when 2 KiB stages no longer fit twice)
   bool gs_xprefetch = true;             // cross-phase V prefetch of the step kernel (GA_GS_XPREFETCH=0 at ga_create: debug A/B switch)
   bool use_spmv_stream = true;          // TMA-staged persistent SpMV (GA_SPMV_V1=1 selects the first kernel)
@@ -258,6 +262,7 @@ struct PerDeviceOnce {
   void done(int dev) { mask.fetch_or(1ULL << (dev & 63), std::memory_order_release); }
 };
 
+const CUtensorMap* gs_tensor_map(ga_ctx* c, int j, int rows);   // k_gs_step.cu
 int sync_ctl(ga_ctx* c);  // copy DevCtl to the pinned mirror and synchronise the stream
 int status_error(ga_ctx* c, const char* where);  // after sync_ctl: ST_COMM -> GA_ERR_COMM, ST_NUMERIC -> GA_ERR_NUMERIC
 

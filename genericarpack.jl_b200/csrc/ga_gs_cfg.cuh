@@ -14,8 +14,9 @@ template <class T, int SEG> struct GsCfg {
   // one column segment of the tile; measured on B200 (profiles/microbench/tma_bulk_rate.cu) the
   // per-SM bulk-copy issue rate caps 1 KiB copies at ~4.3 TB/s chip-wide while 2 KiB copies reach
   // ~6.8 TB/s, hence 2 KiB segments: R = 256 rows (F64) / 128 rows (C64, DD).
-  // SEG = 1024 (one row per thread) is the fallback for j > ~47 columns, where 2 KiB segments
-  // would leave fewer than two pipeline stages in shared memory.
+  // SEG = 1024 (tiles of half the rows) serves wide bases, where fewer than three 2 KiB-segment stages would
+  // fit in shared memory; those tiles are moved by one tensor-map copy each (k_gs_step.cuh), which is
+  // not subject to the per-copy issue rate.
   static constexpr int SEG_BYTES = SEG;
   static constexpr int R = SEG_BYTES / (int)sizeof(T);
   // Thread layout (16 consumer warps + 1 producer warp; 17 warps are allocated as 20, which caps

@@ -1,5 +1,6 @@
 // Thin inline-PTX wrappers: mbarrier + 1-D bulk async copy (TMA, UBLKCP in SASS) for sm_100a.
 #pragma once
+#include <cuda.h>          // CUtensorMap (type and enums only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,6 +49,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
           smem_u32(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// global -> shared copy of a 2-D box described by a tensor map (UTMALDG in SASS): one instruction moves
+// box_rows x box_cols elements; (x, y) = coordinates of the box origin in elements of dimension 0 / 1.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

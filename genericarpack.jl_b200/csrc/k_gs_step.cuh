@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "ga_gs_cfg.cuh"
@@ -70,19 +71,11 @@ __device__ __forceinline__ void grid_barrier(DevCtl* ctl) {
 template <class T, bool PLAIN> struct StepAcc { typedef typename Elem<T>::acc_t type; };
 template <> struct StepAcc<double, true> { typedef double type; };
 
-// one round of the in-warp butterfly on a reduced slot; the first argument only selects the arithmetic (the accumulator type)
+// reduced (hi, lo) / (re, im) slot of one register accumulator
 __device__ __forceinline__ double2 slot_from_acc(double v) { return make_double2(v, 0.0); }
 __device__ __forceinline__ double2 slot_from_acc(dot2 v) { double h, l; two_sum(v.hi, v.lo, h, l); return make_double2(h, l); }
 __device__ __forceinline__ double2 slot_from_acc(cdbl v) { return make_double2(v.re, v.im); }
 __device__ __forceinline__ double2 slot_from_acc(ddbl v) { return make_double2(v.hi, v.lo); }
-__device__ __forceinline__ double2 slot_butterfly(double, double2 s, int m) { s.x += shfl_xor_d(s.x, m); return s; }   // plain tree (warp_sum_slot_fast(double))
-__device__ __forceinline__ double2 slot_butterfly(cdbl, double2 s, int m) { s.x += shfl_xor_d(s.x, m); s.y += shfl_xor_d(s.y, m); return s; }
-__device__ __forceinline__ double2 slot_butterfly_dd(double2 s, int m) {
-  const ddbl r = dd_add(ddbl(s.x, s.y), ddbl(shfl_xor_d(s.x, m), shfl_xor_d(s.y, m)));
-  return make_double2(r.hi, r.lo);
-}
-__device__ __forceinline__ double2 slot_butterfly(dot2, double2 s, int m) { return slot_butterfly_dd(s, m); }
-__device__ __forceinline__ double2 slot_butterfly(ddbl, double2 s, int m) { return slot_butterfly_dd(s, m); }
 // a + b for two reduced slots, in the arithmetic of the accumulator kind (first argument: tag only)
 __device__ __forceinline__ double2 slot_add_recv(double, double2 a, double2 b) { return make_double2(a.x + b.x, 0.0); }
 __device__ __forceinline__ double2 slot_add_recv(cdbl, double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -97,8 +90,13 @@ __device__ __forceinline__ double2 slot_add_recv(ddbl, double2 a, double2 b) { r
 template <class T, int SEG, int NCT, bool PLAIN>
 __global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
 k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ctl, double2* partial, int nstages,
-          int ncv, const DevComm* cm, unsigned long long* trace, int xprefetch) {
+          int ncv, const DevComm* cm, unsigned long long* trace, int xprefetch, const __grid_constant__ CUtensorMap vmap) {
   typedef GsCfg<T, SEG> C;
+  // 1 KiB column segments (tiles of half the rows: used when fewer than three 2 KiB stages fit) are moved by ONE tensor-map
+  // copy per tile (box = R rows x j columns): 1 KiB 1-D bulk copies are capped by the TMA issue rate (4.3 TB/s chip-wide,
+  // profiles/microbench/tma_bulk_rate.cu), a box copy is one instruction whatever its row length
+  constexpr bool TMAP = (SEG == 1024);
+  constexpr int XS = (int)(sizeof(T) / (sizeof(T) == 4 ? 4 : 8));   // map elements per row (Float32 maps count floats, the others doubles)
   typedef typename StepAcc<T, PLAIN>::type acc_t;
 #define GA_TRACE(slot, cond)                                                        \
   if (trace != nullptr && (cond)) {                                                 \
@@ -186,9 +184,16 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
           mbar_wait(&empty[s], par ^ 1u);
           if (lane == 0) mbar_arrive_expect_tx(&full[s], stage_bytes);
           __syncwarp();
-          for (int c = lane; c <= j; c += 32) {
-            const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (wr + row0);
-            bulk_g2s(st + (size_t)c * SEGB, src, SEGB, &full[s]);
+          if (TMAP) {
+            if (lane == 0) {
+              tma_load_2d(st, &vmap, (int)(row0 * XS), 0, &full[s]);
+              bulk_g2s(st + (size_t)j * SEGB, wr + row0, SEGB, &full[s]);
+            }
+          } else {
+            for (int c = lane; c <= j; c += 32) {
+              const T* src = (c < j) ? (V + (size_t)c * ldv + row0) : (wr + row0);
+              bulk_g2s(st + (size_t)c * SEGB, src, SEGB, &full[s]);
+            }
           }
         }
         if (++s == nstages) { s = 0; par ^= 1u; }
@@ -202,7 +207,11 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
           __syncwarp();
           unsigned char* st = smem + (size_t)s * stage_bytes;
           const i64 row0 = t * R;
-          for (int c = lane; c < j; c += 32) bulk_g2s(st + (size_t)c * SEGB, V + (size_t)c * ldv + row0, SEGB, &full[s]);
+          if (TMAP) {
+            if (lane == 0) tma_load_2d(st, &vmap, (int)(row0 * XS), 0, &full[s]);
+          } else {
+            for (int c = lane; c < j; c += 32) bulk_g2s(st + (size_t)c * SEGB, V + (size_t)c * ldv + row0, SEGB, &full[s]);
+          }
           if (++s == nstages) { s = 0; par ^= 1u; }
         }
       }
@@ -425,8 +434,15 @@ static int launch_step_nct(ga_ctx* c, int j, int nstages) {
     c->prof_used += 2;
     GA_CUDA(c, cudaEventRecord(e0, c->stream));
   }
+  alignas(64) CUtensorMap vmap;
+  memset(&vmap, 0, sizeof(vmap));
+  if (SEG == 1024) {
+    const CUtensorMap* m = gs_tensor_map(c, j, C::R);
+    if (!m) return GA_ERR_CUDA;
+    vmap = *m;
+  }
   void* args[] = {(void*)&V, (void*)&ldv, (void*)&j, (void*)&wr, (void*)&ntiles, (void*)&ctl, (void*)&partial,
-                  (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace, (void*)&xprefetch};
+                  (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace, (void*)&xprefetch, (void*)&vmap};
   GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG, NCT, PLAIN>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
@@ -454,7 +470,7 @@ static int launch_step_tp(ga_ctx* c, int j) {
   // 2 KiB segments need two stages: (j + 1) * 4 KiB <= budget, i.e. j <= 51 -> NCT <= NC2MAX
   constexpr int J2MAX = (int)((kGsSmemBytes - C2::FIXED_SMEM) / 4096) - 1;
   constexpr int NC2MAX = (J2MAX + C2::TG - 1) / C2::TG < C2::NC ? (J2MAX + C2::TG - 1) / C2::TG : C2::NC;
-  if (nst >= 2 && j < c->gs_seg1024_from) {
+  if (nst >= c->gs_min_stages_2k && j < c->gs_seg1024_from) {
     if (nst > C2::MAX_STAGES) nst = C2::MAX_STAGES;
     return launch_step_pick<T, 2048, PLAIN, 1, NC2MAX>(c, j, nst, nct);
   }
@@ -462,11 +478,9 @@ static int launch_step_tp(ga_ctx* c, int j) {
   nst = (int)(budget1 / ((size_t)(j + 1) * 1024));
   if (nst > C1::MAX_STAGES) nst = C1::MAX_STAGES;
   if (nst < 2) return set_err(c, GA_ERR_ARG, "gs: too many columns for the shared-memory pipeline");
-#ifdef GA_NC1MIN   /* development: 1 KiB-segment instantiations from fewer columns on (A/B of the stage depth for j > 32) */
-  constexpr int NC1MIN = GA_NC1MIN;
-#else
-  constexpr int NC1MIN = (J2MAX + 1 + C1::TG - 1) / C1::TG;   // first j served by 1 KiB segments is J2MAX + 1
-#endif
+  // 1 KiB segments serve every j for which fewer than three 2 KiB stages fit: (j + 1) * 6 KiB > budget
+  constexpr int J3MAX = (int)((kGsSmemBytes - C2::FIXED_SMEM) / (3 * 2048)) - 1;
+  constexpr int NC1MIN = (J3MAX + 1 + C1::TG - 1) / C1::TG;
   return launch_step_pick<T, 1024, PLAIN, NC1MIN, C1::NC>(c, j, nst, nct);
 }
 

@@ -567,23 +567,54 @@ int launch_normal_half(ga_ctx* c, const void* x, void* y) {
 }
 
 // Upload a host CSR (int64 rowptr, int32 col, T val) and build the row blocks.
+// like GA_CUDA, but drains the stream first: asynchronous copies out of the CALLER's arrays may be in flight
+#define GA_CUDA_DRAIN(ctx, call)                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      cudaStreamSynchronize((ctx)->stream);                                                          \
+      return ga::set_err((ctx), GA_ERR_CUDA, std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " + #call + ": " + cudaGetErrorString(e_)); \
+    }                                                                                                \
+  } while (0)
+
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift) {
   M.free_all();
   const i64 nnz = rowptr[nrows] - rowptr[0];
   if (nnz >= (i64)2147483647LL || nrows >= (i64)2147483647LL)
     return set_err(c, GA_ERR_ARG, "csr: more than 2^31-1 non-zeros or rows per rank is not supported");
+  if (nnz < 0) return set_err(c, GA_ERR_ARG, "csr: rowptr is not non-decreasing");
   const int cap = c->esize == 8 ? SpmvCfg<double>::CAP : SpmvCfg<cdbl>::CAP;
   const int maxrows = SpmvCfg<double>::MAXROWS;
-  std::vector<int> rp((size_t)nrows + 1);
   const int64_t base = rowptr[0];
-  // the kernels gather x[col] unchecked: a bad index must be an argument error here, not a device fault there
-  for (i64 i = 0; i < nrows; ++i)
-    if (rowptr[i + 1] < rowptr[i]) return set_err(c, GA_ERR_ARG, "csr: rowptr is not non-decreasing");
-  for (i64 k = 0; k < nnz; ++k) {
-    const i64 cc = (i64)col[base + k] - col_shift;
-    if (cc < 0 || cc >= ncols) return set_err(c, GA_ERR_ARG, "csr: column index outside [0, ncols)");
+  M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
+  // The two big arrays go first: their copies (from pinned host memory: true DMA) run while the host validates the
+  // indices and builds the row blocks below.  +8 elements: the streamed kernel copies 16-byte aligned supersets of each segment.
+  GA_CUDA(c, cudaMalloc(&M.col, sizeof(int) * (size_t)(std::max<i64>(nnz, 1) + 8)));
+  GA_CUDA(c, cudaMalloc(&M.val, c->esize * (size_t)(std::max<i64>(nnz, 1) + 8)));
+  GA_CUDA(c, cudaMemsetAsync((char*)M.col + sizeof(int) * (size_t)std::max<i64>(nnz, 1), 0, sizeof(int) * 8, c->stream));
+  GA_CUDA(c, cudaMemsetAsync((char*)M.val + c->esize * (size_t)std::max<i64>(nnz, 1), 0, c->esize * 8, c->stream));
+  if (nnz > 0) {
+    GA_CUDA(c, cudaMemcpyAsync(M.val, (const char*)val + (size_t)base * c->esize, c->esize * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    if (col_shift == 0) GA_CUDA(c, cudaMemcpyAsync(M.col, col + base, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
   }
+  auto fail = [&](const char* msg) {   // nothing may still be reading the caller's arrays when we return
+    cudaStreamSynchronize(c->stream);
+    M.free_all();
+    return set_err(c, GA_ERR_ARG, msg);
+  };
+  // the kernels gather x[col] unchecked: a bad index must be an argument error here, not a device fault there
+  // (min / max scans: the compiler vectorises them, ~10 ms per 10^8 entries)
+  {
+    int64_t dmin = 0;
+    for (i64 i = 0; i < nrows; ++i) dmin = std::min<int64_t>(dmin, rowptr[i + 1] - rowptr[i]);
+    if (dmin < 0) return fail("csr: rowptr is not non-decreasing");
+    int32_t cmin = 2147483647, cmax = -2147483647 - 1;
+    const int32_t* cb = col + base;
+    for (i64 k = 0; k < nnz; ++k) { cmin = std::min(cmin, cb[k]); cmax = std::max(cmax, cb[k]); }
+    if (nnz > 0 && ((i64)cmin - col_shift < 0 || (i64)cmax - col_shift >= ncols)) return fail("csr: column index outside [0, ncols)");
+  }
+  std::vector<int> rp((size_t)nrows + 1);
   for (i64 i = 0; i <= nrows; ++i) rp[(size_t)i] = (int)(rowptr[i] - base);
   std::vector<int> blk;
   blk.reserve((size_t)(nnz / (cap / 2) + nrows / maxrows + 16));
@@ -595,7 +626,7 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
     r = e;
   }
   blk.push_back((int)nrows);
-  M.nrows = nrows; M.ncols = ncols; M.nnz = nnz; M.nblk = (int)blk.size() - 1;
+  M.nblk = (int)blk.size() - 1;
   // row blocks of the streamed kernel: <= CAP non-zeros and <= MAXROWS rows; longer rows go to a list
   std::vector<int4> desc;
   std::vector<int> longrow;
@@ -613,33 +644,24 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
     }
   }
   M.ndesc = (int)desc.size(); M.nlong = (int)longrow.size();
-  // +8 elements: the streamed kernel copies 16-byte aligned supersets of each segment
-  GA_CUDA(c, cudaMalloc(&M.rowptr, sizeof(int) * ((size_t)nrows + 1 + 8)));
-  GA_CUDA(c, cudaMalloc(&M.col, sizeof(int) * (size_t)(std::max<i64>(nnz, 1) + 8)));
-  GA_CUDA(c, cudaMalloc(&M.val, c->esize * (size_t)(std::max<i64>(nnz, 1) + 8)));
-  GA_CUDA(c, cudaMemsetAsync((char*)M.rowptr + sizeof(int) * ((size_t)nrows + 1), 0, sizeof(int) * 8, c->stream));
-  GA_CUDA(c, cudaMemsetAsync((char*)M.col + sizeof(int) * (size_t)std::max<i64>(nnz, 1), 0, sizeof(int) * 8, c->stream));
-  GA_CUDA(c, cudaMemsetAsync((char*)M.val + c->esize * (size_t)std::max<i64>(nnz, 1), 0, c->esize * 8, c->stream));
-  GA_CUDA(c, cudaMalloc(&M.rowblk, sizeof(int) * blk.size()));
-  GA_CUDA(c, cudaMalloc(&M.desc, sizeof(int4) * std::max<size_t>(desc.size(), 1)));
-  GA_CUDA(c, cudaMalloc(&M.longrow, sizeof(int) * std::max<size_t>(longrow.size(), 1)));
+  GA_CUDA_DRAIN(c, cudaMalloc(&M.rowptr, sizeof(int) * ((size_t)nrows + 1 + 8)));
+  GA_CUDA_DRAIN(c, cudaMemsetAsync((char*)M.rowptr + sizeof(int) * ((size_t)nrows + 1), 0, sizeof(int) * 8, c->stream));
+  GA_CUDA_DRAIN(c, cudaMalloc(&M.rowblk, sizeof(int) * blk.size()));
+  GA_CUDA_DRAIN(c, cudaMalloc(&M.desc, sizeof(int4) * std::max<size_t>(desc.size(), 1)));
+  GA_CUDA_DRAIN(c, cudaMalloc(&M.longrow, sizeof(int) * std::max<size_t>(longrow.size(), 1)));
   if (!desc.empty())
-    GA_CUDA(c, cudaMemcpyAsync(M.desc, desc.data(), sizeof(int4) * desc.size(), cudaMemcpyHostToDevice, c->stream));
+    GA_CUDA_DRAIN(c, cudaMemcpyAsync(M.desc, desc.data(), sizeof(int4) * desc.size(), cudaMemcpyHostToDevice, c->stream));
   if (!longrow.empty())
-    GA_CUDA(c, cudaMemcpyAsync(M.longrow, longrow.data(), sizeof(int) * longrow.size(), cudaMemcpyHostToDevice, c->stream));
-  GA_CUDA(c, cudaMemcpyAsync(M.rowptr, rp.data(), sizeof(int) * rp.size(), cudaMemcpyHostToDevice, c->stream));
-  GA_CUDA(c, cudaMemcpyAsync(M.rowblk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
-  if (col_shift == 0) {
-    GA_CUDA(c, cudaMemcpyAsync(M.col, col + base, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
-  } else {
+    GA_CUDA_DRAIN(c, cudaMemcpyAsync(M.longrow, longrow.data(), sizeof(int) * longrow.size(), cudaMemcpyHostToDevice, c->stream));
+  GA_CUDA_DRAIN(c, cudaMemcpyAsync(M.rowptr, rp.data(), sizeof(int) * rp.size(), cudaMemcpyHostToDevice, c->stream));
+  GA_CUDA_DRAIN(c, cudaMemcpyAsync(M.rowblk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
+  if (col_shift != 0 && nnz > 0) {
     std::vector<int> cc((size_t)nnz);
     for (i64 k = 0; k < nnz; ++k) cc[(size_t)k] = (int)(col[base + k] - col_shift);
-    GA_CUDA(c, cudaMemcpyAsync(M.col, cc.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
-    GA_CUDA(c, cudaStreamSynchronize(c->stream));
+    GA_CUDA_DRAIN(c, cudaMemcpyAsync(M.col, cc.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    GA_CUDA_DRAIN(c, cudaStreamSynchronize(c->stream));
   }
-  GA_CUDA(c, cudaMemcpyAsync(M.val, (const char*)val + (size_t)base * c->esize, c->esize * (size_t)nnz,
-                             cudaMemcpyHostToDevice, c->stream));
-  GA_CUDA(c, cudaStreamSynchronize(c->stream));
+  GA_CUDA_DRAIN(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 

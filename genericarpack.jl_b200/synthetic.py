@@ -104,18 +104,20 @@ def tall_sparse(m, n, nnz_per_row=10, seed=7):
     return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.copy(), A.shape
 
 
-def tall_sparse_stream(m, n, nnz_per_row=10, seed=7, chunk_rows=1 << 22):
+def tall_sparse_stream(m, n, nnz_per_row=10, seed=7, chunk_rows=1 << 22, row_range=None):
     """C5 at full size (50M x 2M, nnz = 5e8) without the COO detour of tall_sparse: rows are generated chunk by chunk
     straight into CSR (same SplitMix64 streams, so entry k of row i is the same (column, value) pair as tall_sparse's),
     columns sorted within each row, duplicate columns of a row kept as separate entries (a valid CSR operator; tall_sparse
     sums them, which changes values in ~2e-5 of the rows only).  Peak host memory ~ nnz * 12 bytes + one chunk."""
-    nnz = m * nnz_per_row
+    ra, rb = (0, m) if row_range is None else row_range        # row_range: only these rows of the same matrix (sharded runs)
+    nnz = (rb - ra) * nnz_per_row
+    base = ra * nnz_per_row
     rowptr = np.arange(0, nnz + 1, nnz_per_row, dtype=np.int64)
     col = np.empty(nnz, dtype=np.int32)
     val = np.empty(nnz, dtype=np.float64)
     with np.errstate(over="ignore"):
-        for r0 in range(0, m, chunk_rows):
-            r1 = min(m, r0 + chunk_rows)
+        for r0 in range(ra, rb, chunk_rows):
+            r1 = min(rb, r0 + chunk_rows)
             k0, k1 = r0 * nnz_per_row, r1 * nnz_per_row
             idx = np.arange(k0 + 1, k1 + 1, dtype=np.uint64)
 
@@ -128,9 +130,9 @@ def tall_sparse_stream(m, n, nnz_per_row=10, seed=7, chunk_rows=1 << 22):
             c = (mix(seed) % np.uint64(n)).astype(np.int32).reshape(r1 - r0, nnz_per_row)
             v = ((mix(seed + 1) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)).reshape(r1 - r0, nnz_per_row)
             order = np.argsort(c, axis=1, kind="stable")
-            col[k0:k1] = np.take_along_axis(c, order, axis=1).ravel()
-            val[k0:k1] = np.take_along_axis(v, order, axis=1).ravel()
-    return rowptr, col, val, (m, n)
+            col[k0 - base:k1 - base] = np.take_along_axis(c, order, axis=1).ravel()
+            val[k0 - base:k1 - base] = np.take_along_axis(v, order, axis=1).ravel()
+    return rowptr, col, val, (rb - ra, n)
 
 
 def to_scipy(csr):

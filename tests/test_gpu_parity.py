@@ -281,6 +281,35 @@ def test_lanczos_parity_small(pkg, syn, O, dtype):
     ctx.close()
 
 
+@pytest.mark.parametrize("dtype,ncv", [("f64", 44), ("c64", 44), ("dd", 44), ("f64", 60), ("c64", 60), ("dd", 60)])
+def test_lanczos_wide_basis_tensor_map_path(pkg, syn, O, dtype, ncv):
+    """Bases wider than 32 columns leave room for fewer than three 2 KiB-segment stages; the step kernel then works on
+    tiles of half the rows, each moved by ONE tensor-map copy (cp.async.bulk.tensor, k_gs_step.cuh).  Same arithmetic:
+    Float64 H / V bitwise equal to the oracle (exact dots), ComplexF64 / Double64 at their lock-step tolerances,
+    V'V = I, and the three-term relation."""
+    A = syn.to_scipy(syn.hermitian_stencil(40) if dtype == "c64" else syn.laplacian2d(48))
+    ctx, ora, H, rn, infos = _run_both(pkg, O, A, ncv, dtype, [(0, 10), (10, ncv - 10)])
+    assert infos == [(0, 0), (0, 0)]
+    V = np.asarray(ctx.download_v())
+    Vo = np.swapaxes(np.asarray(ora.Vt), 0, 1)
+    if dtype == "f64":
+        assert np.array_equal(H, np.asarray(ora.H)) and np.array_equal(V, Vo)
+        Vf, Hf, rf = V, H, np.asarray(ctx.download_resid())
+    elif dtype == "dd":
+        Vf, Hf, rf = _dd_float(V), _dd_float(H), _dd_float(np.asarray(ctx.download_resid()))
+        assert np.max(np.abs((H[..., 0] - ora.H[..., 0]) + (H[..., 1] - ora.H[..., 1]))) <= 1e-22 * np.max(np.abs(Hf))
+    else:
+        Vf, Hf, rf = V, H, np.asarray(ctx.download_resid())
+        k = 24                                                  # plain complex accumulators: rounding differences grow with j
+        assert np.allclose(Hf[:k], np.asarray(ora.H)[:k], rtol=1e-8, atol=1e-8 * np.max(np.abs(Hf)))
+    assert np.allclose(Vf.conj().T @ Vf, np.eye(ncv), atol=1e-12)
+    T = np.diag(Hf[:, 1]) + np.diag(Hf[1:, 0], 1) + np.diag(Hf[1:, 0], -1)
+    R = A @ Vf - Vf @ T
+    assert np.allclose(R[:, :-1], 0, atol=1e-11) and np.allclose(R[:, -1], rf, atol=1e-11)
+    assert ctx.stats()["nopx"] == ora.stats()["nopx"] == ncv
+    ctx.close()
+
+
 def test_lanczos_identity_restart(pkg, O):
     """test/dsaitr_simple.jl:140-178: identity operator -> invariant subspace after one step ->
     dgetv0 restart inside the call; resid stays ~0; counters agree with the oracle.  The start

@@ -8,7 +8,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 timeout 200 $TR tests/dist_gpu_check.py 300 > $OUT/dist_check_n$N.json 2> $OUT/dist_check_n$N.err; echo "dist check rc=$?"
 tail -1 $OUT/dist_check_n$N.json
 ( time timeout 400 $TR bench.py --gpus $N --no-cpu --trace > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err ) 2>&1 | tail -3; echo "bench rc=$?"
-( time timeout 300 $TR bench.py --gpus $N --no-cpu --no-e2e --no-tts --no-gate --m 8000 --steps 5 > $OUT/bench_64M_n$N.json 2> $OUT/bench_64M_n$N.err ) 2>&1 | tail -3; echo "bench 64M rc=$?"
+( time timeout 300 $TR bench.py --gpus $N --no-cpu --no-e2e --no-tts --no-gate --grid 8000 --steps 5 > $OUT/bench_64M_n$N.json 2> $OUT/bench_64M_n$N.err ) 2>&1 | tail -3; echo "bench 64M rc=$?"
 for f in $OUT/bench_n$N.json $OUT/bench_64M_n$N.json; do python - $f <<'PY'
 import json,sys
 try:

@@ -87,7 +87,12 @@ __device__ __forceinline__ double2 slot_add_recv(dot2, double2 a, double2 b) { r
 __device__ __forceinline__ double2 slot_add_recv(ddbl, double2 a, double2 b) { return slot_add_recv_dd(a, b); }
 
 // NCT = register accumulators per consumer thread = ceil(j / TG): the thread's columns are g, g + TG, ...
-template <class T, int SEG, int NCT, bool PLAIN>
+// SETS = independent consumer sets.  SETS = 1: all 16 consumer warps work on every tile (2 rows per thread).  SETS = 2 (short
+// bases): the warps form two sets of 8 that take alternate tiles, a thread owning 4 rows of its tile.  A short basis makes a
+// small tile, and what a warp spends per tile is then mostly a latency chain (wait -> LDS -> FP64 chain -> named barrier ->
+// ...) that does not shrink with the tile: twice the rows per thread halve the chains per byte, and the two sets hide
+// each other's waits (profiles/r02/README.md: j = 11 ran at 4.7 TB/s against 6.7 TB/s at j = 28).
+template <class T, int SEG, int NCT, bool PLAIN, int SETS>
 __global__ void __launch_bounds__(GsCfg<T, SEG>::THREADS, 1)
 k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ctl, double2* partial, int nstages,
           int ncv, const DevComm* cm, unsigned long long* trace, int xprefetch, const __grid_constant__ CUtensorMap vmap) {
@@ -105,7 +110,13 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
     trace[slot] = t_;                                                               \
   }
   GA_TRACE(0, blockIdx.x == 0 && threadIdx.x == 0)
-  constexpr int R = C::R, TG = C::TG, NC = C::NC, SLICES = C::SLICES, CWARPS = C::CWARPS, RPT = C::RPT, ROWL = C::ROWL;
+  constexpr int R = C::R, TG = C::TG, NC = C::NC, CWARPS = C::CWARPS;
+  constexpr int ROWL = C::ROWL / SETS;          // row lanes of one consumer set
+  constexpr int RPT = R / ROWL;                  // rows per thread
+  constexpr int SLICES = ROWL / 32;              // warps per column group inside a set
+  constexpr int SWARPS = CWARPS / SETS;          // consumer warps per set
+  static_assert(SETS == 1 || SETS == 2, "consumer sets");
+  static_assert(SLICES >= 1 && RPT * ROWL == R, "thread layout");
   constexpr uint32_t SEGB = C::SEG_BYTES;
   constexpr bool CPLX = Elem<T>::is_complex;
   static_assert(NCT >= 1 && NCT <= NC, "columns per thread");
@@ -116,7 +127,7 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
   const uint32_t stage_bytes = (uint32_t)(j + 1) * SEGB;
   unsigned char* p = smem + (size_t)nstages * stage_bytes;
   T* hs = reinterpret_cast<T*>(p);                  p += kMaxNcv * 16;
-  T* pr = reinterpret_cast<T*>(p);                  p += 2 * TG * SEGB;
+  T* pr = reinterpret_cast<T*>(p);                  p += SETS * 2 * TG * SEGB;
   double2* redw = reinterpret_cast<double2*>(p);    p += CWARPS * (NC + 3) * 16;
   uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += C::MAX_STAGES * 8;
   uint64_t* empty = reinterpret_cast<uint64_t*>(p); p += C::MAX_STAGES * 8;
@@ -124,12 +135,13 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CWARPS); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SWARPS); }
     fence_mbar_init();
   }
   __syncthreads();
 
-  const int slice = warp % SLICES, g = warp / SLICES, rl = slice * 32 + lane;
+  const int set = (warp / SWARPS) % SETS, wset = warp % SWARPS;   // (the producer warp gets set 0; it never uses it)
+  const int slice = wset % SLICES, g = wset / SLICES, rl = slice * 32 + lane;
 #define ROWIDX(q) ((sizeof(T) <= 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
   int it = 0;  // running tile counter of this CTA: the stage ring and its parities continue across phases
   int npre = 0;  // producer warp: tiles of the upcoming phase whose V columns are already in flight
@@ -227,11 +239,14 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       int coff[NCT];
 #pragma unroll
       for (int i = 0; i < NCT; ++i) { const int c = g + TG * i; coff[i] = (c < j ? c : j) * R; }
-      int s = s0;
+      // this set's tiles: the set-th, (set + SETS)-th, ... of the CTA's sequence, i.e. every SETS-th ring stage
+      int s = s0 + set;
       uint32_t par = par0;
+      if (s >= nstages) { s -= nstages; par ^= 1u; }
       bool first = true;
       int kk = 0;   // tiles done in this phase (parity = which half of the partial-sum exchange buffer)
-      for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      T* prs = pr + (size_t)set * 2 * TG * R;
+      for (i64 t = (i64)blockIdx.x + (i64)set * gridDim.x; t < ntiles; t += (i64)SETS * gridDim.x) {
         mbar_wait(&full[s], par);
         GA_TRACE(1 + 8 * ph, blockIdx.x == 0 && tid == 0 && first)
         first = false;
@@ -249,10 +264,10 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
 #pragma unroll
             for (int q = 0; q < RPT; ++q) Elem<T>::sub_mul(p0[q], tile[coff[i] + ROWIDX(q)], hc);
           }
-          T* prb = pr + (size_t)(kk & 1) * TG * R;
+          T* prb = prs + (size_t)(kk & 1) * TG * R;
 #pragma unroll
           for (int q = 0; q < RPT; ++q) prb[g * R + ROWIDX(q)] = p0[q];
-          named_bar_sync(1 + slice, TG * 32);
+          named_bar_sync(1 + set * SLICES + slice, TG * 32);
 #pragma unroll
           for (int g2 = 0; g2 < TG; ++g2) {
 #pragma unroll
@@ -276,7 +291,8 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == nstages) { s = 0; par ^= 1u; }
+        s += SETS;
+        if (s >= nstages) { s -= nstages; par ^= 1u; }
         ++kk;
       }
       GA_TRACE(2 + 8 * ph, blockIdx.x == 0 && tid == 0)
@@ -329,17 +345,20 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
     // CTA partials -> global
     for (int s = tid; s < nslots; s += blockDim.x) {
       double2 a = make_double2(0.0, 0.0);
+      // warps of column group gg: set * SWARPS + gg * SLICES + slice, summed in ascending warp order
       if (s < j) {
         if (mode != 2) {
           const int gg = s % TG, i = s / TG;
-          for (int sl = 0; sl < SLICES; ++sl) {
-            double2 v = redw[(gg * SLICES + sl) * (NC + 3) + i];
-            a = CPLX ? slot_add<true>(a, v) : slot_add<false>(a, v);
-          }
+          for (int st = 0; st < SETS; ++st)
+            for (int sl = 0; sl < SLICES; ++sl) {
+              double2 v = redw[(st * SWARPS + gg * SLICES + sl) * (NC + 3) + i];
+              a = CPLX ? slot_add<true>(a, v) : slot_add<false>(a, v);
+            }
         }
       } else {
         const int k = s - j;
-        for (int sl = 0; sl < SLICES; ++sl) a = slot_add<false>(a, redw[sl * (NC + 3) + NC + k]);
+        for (int st = 0; st < SETS; ++st)
+          for (int sl = 0; sl < SLICES; ++sl) a = slot_add<false>(a, redw[(st * SWARPS + sl) * (NC + 3) + NC + k]);
       }
       partial[(size_t)blockIdx.x * kMaxSlots + s] = a;
     }
@@ -404,15 +423,15 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
 #undef ROWIDX
 }
 
-template <class T, int SEG, int NCT, bool PLAIN>
+template <class T, int SEG, int NCT, bool PLAIN, int SETS>
 static int launch_step_nct(ga_ctx* c, int j, int nstages) {
   typedef GsCfg<T, SEG> C;
   i64 ntiles = c->n_pad / C::R;
   const size_t stage_bytes = (size_t)(j + 1) * C::SEG_BYTES;
-  size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM;
+  size_t smem = (size_t)nstages * stage_bytes + C::FIXED_SMEM + (size_t)(SETS - 1) * 2 * C::TG * C::SEG_BYTES;
   static PerDeviceOnce attr_set;
   if (attr_set.need(c->device)) {
-    GA_CUDA(c, cudaFuncSetAttribute(k_gs_step<T, SEG, NCT, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
+    GA_CUDA(c, cudaFuncSetAttribute(k_gs_step<T, SEG, NCT, PLAIN, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmemBytes));
     attr_set.done(c->device);
   }
   int grid = (int)(ntiles < (i64)c->sm_count ? ntiles : (i64)c->sm_count);
@@ -443,22 +462,25 @@ static int launch_step_nct(ga_ctx* c, int j, int nstages) {
   }
   void* args[] = {(void*)&V, (void*)&ldv, (void*)&j, (void*)&wr, (void*)&ntiles, (void*)&ctl, (void*)&partial,
                   (void*)&nstages, (void*)&ncv, (void*)&cm, (void*)&trace, (void*)&xprefetch, (void*)&vmap};
-  GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG, NCT, PLAIN>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
+  GA_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_gs_step<T, SEG, NCT, PLAIN, SETS>, dim3(grid), dim3(C::THREADS), args, smem, c->stream));
   c->launches += 1;
   if (c->prof) GA_CUDA(c, cudaEventRecord(e1, c->stream));
   return 0;
 }
 
 // NCT = ceil(j / TG), one instantiation each in [LO, HI]
-template <class T, int SEG, bool PLAIN, int LO, int HI>
+template <class T, int SEG, bool PLAIN, int SETS, int LO, int HI>
 static int launch_step_pick(ga_ctx* c, int j, int nstages, int nct) {
   if constexpr (LO > HI) {
     return set_err(c, GA_ERR_ARG, "gs: no step-kernel instantiation for this many columns");
   } else {
-    if (nct <= LO) return launch_step_nct<T, SEG, LO, PLAIN>(c, j, nstages);
-    return launch_step_pick<T, SEG, PLAIN, LO + 1, HI>(c, j, nstages, nct);
+    if (nct <= LO) return launch_step_nct<T, SEG, LO, PLAIN, SETS>(c, j, nstages);
+    return launch_step_pick<T, SEG, PLAIN, SETS, LO + 1, HI>(c, j, nstages, nct);
   }
 }
+
+// two-set instantiations exist for NCT <= this (j <= 24 columns for 8-byte elements)
+template <class T> constexpr int kGsTwoSetMaxNct() { return (sizeof(T) == 16) ? 3 : 6; }
 
 template <class T, bool PLAIN>
 static int launch_step_tp(ga_ctx* c, int j) {
@@ -470,9 +492,18 @@ static int launch_step_tp(ga_ctx* c, int j) {
   // 2 KiB segments need two stages: (j + 1) * 4 KiB <= budget, i.e. j <= 51 -> NCT <= NC2MAX
   constexpr int J2MAX = (int)((kGsSmemBytes - C2::FIXED_SMEM) / 4096) - 1;
   constexpr int NC2MAX = (J2MAX + C2::TG - 1) / C2::TG < C2::NC ? (J2MAX + C2::TG - 1) / C2::TG : C2::NC;
+  // short bases: two consumer sets (they need the larger exchange buffer and at least four stages)
+  constexpr int NCT2SETS = kGsTwoSetMaxNct<T>();
+  if (c->gs_two_sets && nct <= NCT2SETS && j < c->gs_seg1024_from) {
+    int nst2 = (int)((budget2 - 2 * C2::TG * 2048) / ((size_t)(j + 1) * 2048));
+    if (nst2 >= 4) {
+      if (nst2 > C2::MAX_STAGES) nst2 = C2::MAX_STAGES;
+      return launch_step_pick<T, 2048, PLAIN, 2, 1, NCT2SETS>(c, j, nst2, nct);
+    }
+  }
   if (nst >= c->gs_min_stages_2k && j < c->gs_seg1024_from) {
     if (nst > C2::MAX_STAGES) nst = C2::MAX_STAGES;
-    return launch_step_pick<T, 2048, PLAIN, 1, NC2MAX>(c, j, nst, nct);
+    return launch_step_pick<T, 2048, PLAIN, 1, 1, NC2MAX>(c, j, nst, nct);
   }
   const size_t budget1 = kGsSmemBytes - C1::FIXED_SMEM;
   nst = (int)(budget1 / ((size_t)(j + 1) * 1024));
@@ -481,7 +512,7 @@ static int launch_step_tp(ga_ctx* c, int j) {
   // 1 KiB segments serve every j for which fewer than three 2 KiB stages fit: (j + 1) * 6 KiB > budget
   constexpr int J3MAX = (int)((kGsSmemBytes - C2::FIXED_SMEM) / (3 * 2048)) - 1;
   constexpr int NC1MIN = (J3MAX + 1 + C1::TG - 1) / C1::TG;
-  return launch_step_pick<T, 1024, PLAIN, NC1MIN, C1::NC>(c, j, nst, nct);
+  return launch_step_pick<T, 1024, PLAIN, 1, NC1MIN, C1::NC>(c, j, nst, nct);
 }
 
 

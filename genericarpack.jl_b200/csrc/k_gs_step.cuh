@@ -142,7 +142,11 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
 
   const int set = (warp / SWARPS) % SETS, wset = warp % SWARPS;   // (the producer warp gets set 0; it never uses it)
   const int slice = wset % SLICES, g = wset / SLICES, rl = slice * 32 + lane;
-#define ROWIDX(q) ((sizeof(T) <= 8) ? (rl * RPT + (q)) : (rl + (q) * ROWL))
+  // rows of a thread: PAIRS of adjacent rows (one LDS.128 for 8-byte elements; 16-byte lane stride = conflict-free), further
+  // pairs 2 * ROWL rows apart; 16-byte elements: single rows ROWL apart; Float32: quadruples
+  constexpr int RADJ0 = (sizeof(T) == 16) ? 1 : 16 / (int)sizeof(T);        // adjacent rows per 16-byte shared-memory read
+  constexpr int RADJ = RPT < RADJ0 ? RPT : RADJ0;
+#define ROWIDX(q) (((q) / RADJ) * (ROWL * RADJ) + rl * RADJ + ((q) % RADJ))
   int it = 0;  // running tile counter of this CTA: the stage ring and its parities continue across phases
   int npre = 0;  // producer warp: tiles of the upcoming phase whose V columns are already in flight
   const int nslots = j + 3;

@@ -104,6 +104,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
   if (const char* e = getenv("GA_SPMV_V1")) c->use_spmv_stream = !(e[0] == '1');
   if (const char* e = getenv("GA_GS_XPREFETCH")) c->gs_xprefetch = !(e[0] == '0');
+  if (const char* e = getenv("GA_VQ_STREAM")) c->vq_stream = !(e[0] == '0');
   if (const char* e = getenv("GA_GS_TWO_SETS")) c->gs_two_sets = !(e[0] == '0');
   if (const char* e = getenv("GA_GS_MIN2K")) c->gs_min_stages_2k = atoi(e) >= 2 ? atoi(e) : c->gs_min_stages_2k;
   if (const char* e = getenv("GA_NORMAL_COLBLOCK")) c->normal_colblock = atoll(e) > 0 ? atoll(e) : 0;

@@ -201,6 +201,7 @@ struct ga_ctx {
   int gs_min_stages_2k = 3;             // step kernel: 2 KiB column segments need this many ring stages, else 1 KiB tiles moved by tensor-map copies (GA_GS_MIN2K: 2 = the round-1 rule)
   std::vector<CUtensorMap> gs_maps;     // tensor maps of V, box = R rows x j columns, index j (lazily encoded; k_gs_step.cu)
   std::vector<char> gs_maps_ok;
+  bool vq_stream = true;                // V*Q: streaming two-group kernel for up to 16 outputs (GA_VQ_STREAM=0 at ga_create: A/B switch)
   bool gs_two_sets = true;              // step kernel: two consumer sets for short bases (GA_GS_TWO_SETS=0 at ga_create: A/B switch)
   int gs_seg1024_from = 1 << 30;        // step kernel: 1 KiB column segments from this many columns on (default: only when 2 KiB stages no longer fit twice)
   bool gs_xprefetch = true;             // cross-phase V prefetch of the step kernel (GA_GS_XPREFETCH=0 at ga_create: debug A/B switch)

@@ -15,6 +15,8 @@ out = {"m": m, "n": n, "nnz": nnz, "gen_s": round(tgen, 1), "algorithmic_GB_per_
 sweep = [("unblocked", str(1 << 40)), ("blocked_32MiB", None)]
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":      # block width in elements of the long vector
     sweep = [("blocked_%dMiB" % (w * 8 >> 20), str(w)) for w in (1 << 20, 1 << 21, 1 << 22, 1 << 23)]
+if len(sys.argv) > 2 and sys.argv[2] == "blocked":
+    sweep = [("blocked_32MiB", None)]
 for label, env in sweep:
     if env is None:
         os.environ.pop("GA_NORMAL_COLBLOCK", None)

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace ga {
@@ -603,34 +604,59 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
     M.free_all();
     return set_err(c, GA_ERR_ARG, msg);
   };
-  // the kernels gather x[col] unchecked: a bad index must be an argument error here, not a device fault there
-  // (min / max scans: the compiler vectorises them, ~10 ms per 10^8 entries)
-  {
-    int64_t dmin = 0;
-    for (i64 i = 0; i < nrows; ++i) dmin = std::min<int64_t>(dmin, rowptr[i + 1] - rowptr[i]);
-    if (dmin < 0) return fail("csr: rowptr is not non-decreasing");
-    int32_t cmin = 2147483647, cmax = -2147483647 - 1;
-    const int32_t* cb = col + base;
-    for (i64 k = 0; k < nnz; ++k) { cmin = std::min(cmin, cb[k]); cmax = std::max(cmax, cb[k]); }
-    if (nnz > 0 && ((i64)cmin - col_shift < 0 || (i64)cmax - col_shift >= ncols)) return fail("csr: column index outside [0, ncols)");
-  }
+  // the kernels gather x[col] unchecked: a bad index must be an argument error here, not a device fault there.
+  // Host passes over the index arrays (range check of col, monotonicity + 32-bit copy of rowptr, the two row-block
+  // lists) run on a few host threads: at C2's size (16M rows, 80M entries) they are 125 ms on one thread -- more than
+  // the DMA of the matrix itself, and all of it inside the end-to-end time of a solve.
   std::vector<int> rp((size_t)nrows + 1);
-  for (i64 i = 0; i <= nrows; ++i) rp[(size_t)i] = (int)(rowptr[i] - base);
-  std::vector<int> blk;
-  blk.reserve((size_t)(nnz / (cap / 2) + nrows / maxrows + 16));
-  i64 r = 0;
-  while (r < nrows) {
-    blk.push_back((int)r);
-    i64 e = r + 1;  // a row always fits "alone" (long-row path if needed)
-    while (e < nrows && (e - r) < maxrows && (rp[(size_t)e + 1] - rp[(size_t)r]) <= cap) ++e;
-    r = e;
+  {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nthr = (nnz + nrows < (1 << 20)) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+    std::vector<int64_t> dmin((size_t)nthr, 0);
+    std::vector<int32_t> cmin((size_t)nthr, 2147483647), cmax((size_t)nthr, -2147483647 - 1);
+    const int32_t* cb = col + base;
+    auto scan = [&](int t) {
+      const i64 r0 = nrows * t / nthr, r1 = nrows * (t + 1) / nthr;
+      int64_t d = 0;
+      for (i64 i = r0; i < r1; ++i) {
+        d = std::min<int64_t>(d, rowptr[i + 1] - rowptr[i]);
+        rp[(size_t)i] = (int)(rowptr[i] - base);
+      }
+      dmin[(size_t)t] = d;
+      const i64 k0 = nnz * t / nthr, k1 = nnz * (t + 1) / nthr;
+      int32_t lo = 2147483647, hi = -2147483647 - 1;
+      for (i64 k = k0; k < k1; ++k) { lo = std::min(lo, cb[k]); hi = std::max(hi, cb[k]); }
+      cmin[(size_t)t] = lo; cmax[(size_t)t] = hi;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthr; ++t) th.emplace_back(scan, t);
+    scan(0);
+    for (auto& x : th) x.join();
+    rp[(size_t)nrows] = (int)(rowptr[nrows] - base);
+    for (int t = 0; t < nthr; ++t)
+      if (dmin[(size_t)t] < 0) return fail("csr: rowptr is not non-decreasing");
+    if (nnz > 0) {
+      const int32_t lo = *std::min_element(cmin.begin(), cmin.end()), hi = *std::max_element(cmax.begin(), cmax.end());
+      if ((i64)lo - col_shift < 0 || (i64)hi - col_shift >= ncols) return fail("csr: column index outside [0, ncols)");
+    }
   }
-  blk.push_back((int)nrows);
-  M.nblk = (int)blk.size() - 1;
-  // row blocks of the streamed kernel: <= CAP non-zeros and <= MAXROWS rows; longer rows go to a list
+  // row blocks of the first kernel (<= CAP non-zeros, <= MAXROWS rows) and of the streamed kernel (one pipeline stage each;
+  // longer rows go to a list): two independent sequential scans, one host thread each
+  std::vector<int> blk;
   std::vector<int4> desc;
   std::vector<int> longrow;
-  {
+  auto build_blk = [&]() {
+    blk.reserve((size_t)(nnz / (cap / 2) + nrows / maxrows + 16));
+    i64 r = 0;
+    while (r < nrows) {
+      blk.push_back((int)r);
+      i64 e = r + 1;  // a row always fits "alone" (long-row path if needed)
+      while (e < nrows && (e - r) < maxrows && (rp[(size_t)e + 1] - rp[(size_t)r]) <= cap) ++e;
+      r = e;
+    }
+    blk.push_back((int)nrows);
+  };
+  auto build_desc = [&]() {
     const int scap = c->esize <= 8 ? SpmvStreamCfg<double>::CAP : SpmvStreamCfg<cdbl>::CAP;   // same rule as the kernels' sizeof(T)
     const int smax = SpmvStreamCfg<double>::MAXROWS;
     desc.reserve((size_t)(nnz / (scap / 2) + nrows / smax + 16));
@@ -642,7 +668,16 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
       desc.push_back(make_int4((int)r0, (int)e, rp[(size_t)r0], rp[(size_t)e]));
       r0 = e;
     }
+  };
+  if (nrows > (1 << 18)) {
+    std::thread t1(build_blk);
+    build_desc();
+    t1.join();
+  } else {
+    build_blk();
+    build_desc();
   }
+  M.nblk = (int)blk.size() - 1;
   M.ndesc = (int)desc.size(); M.nlong = (int)longrow.size();
   GA_CUDA_DRAIN(c, cudaMalloc(&M.rowptr, sizeof(int) * ((size_t)nrows + 1 + 8)));
   GA_CUDA_DRAIN(c, cudaMemsetAsync((char*)M.rowptr + sizeof(int) * ((size_t)nrows + 1), 0, sizeof(int) * 8, c->stream));

@@ -56,7 +56,10 @@ def main():
         csr = syn.sprand_sym(100000, 5.0, seed=1234)
         A = syn.to_scipy(csr)
     if "c1" in which:
+        cold, _, _ = solve(pkg, pkg.ArpackSimpleOp(csr), 2, 12)      # first solve of the process: includes the lazy load of every kernel it uses
         out, vals, vecs = solve(pkg, pkg.ArpackSimpleOp(csr), 2, 12)
+        out["cold_first_solve_s"] = cold["solve_s"]
+        out["us_per_lanczos_step"] = round(out["solve_s"] * 1e6 / max(out["lanczos_steps"], 1), 1)
         out["values"] = [float(v) for v in vals]
         out["max_ritz_residual_rel"] = float(np.max(np.linalg.norm(A @ vecs - vecs * vals, axis=0) / np.abs(vals)))
         if O:

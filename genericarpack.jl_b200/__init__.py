@@ -42,7 +42,7 @@ GA_OPT_DOT_MODE, GA_DOT_EXACT, GA_DOT_PLAIN = 1, 0, 1   # include/garpack_b200.h
 
 # every symbol include/garpack_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
-    "ga_create", "ga_destroy", "ga_set_option", "ga_get_option", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
+    "ga_create", "ga_destroy", "ga_trim_cache", "ga_set_option", "ga_get_option", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid", "ga_bnorm_resid",
     "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_host_tridiag_eig", "ga_host_ritz_and_bounds", "ga_host_sort_pair", "ga_host_select_shifts", "ga_host_count_converged", "ga_host_chase_shifts", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
@@ -654,6 +654,13 @@ class Context:
         nconv = int(iparam[4])
         vecs = np.swapaxes(Zt[:nconv], 0, 1) if ritzvec else None
         return rc, values[:nconv], bounds[:nconv], vecs, iparam
+
+
+def trim_cache():
+    """ga_trim_cache: give the device blocks the library keeps for the next context back to the driver."""
+    L = lib()
+    L.ga_trim_cache.restype = None
+    L.ga_trim_cache()
 
 
 def comm_unique_id(buf=None):

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "ga_ctx.cuh"
@@ -16,6 +17,83 @@ int comm_ipc_export(ga_ctx* c, void* out128);
 int comm_ipc_import(ga_ctx* c, const void* all_handles);
 void comm_destroy(ga_ctx* c);
 void solve_free(ga_ctx* c);  // ga_host.cu
+
+// ---- cache of large device blocks (see ga_ctx.cuh)
+namespace {
+struct DevBlock { void* p; size_t bytes; int dev; };
+std::mutex g_cache_mu;
+std::vector<DevBlock> g_cache_free;                  // parked blocks
+std::vector<DevBlock> g_cache_live;                  // big blocks handed out (so that dev_free knows their size)
+size_t g_cache_bytes = 0;
+constexpr size_t kCacheMinBlock = 32u << 20;
+size_t cache_cap() {
+  static size_t cap = [] { const char* e = getenv("GA_CACHE_BYTES"); return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)24 << 30); }();
+  return cap;
+}
+}  // namespace
+cudaError_t dev_alloc(void** p, size_t bytes) {
+  *p = nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes >= kCacheMinBlock) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache_free.size(); ++i)
+      if (g_cache_free[i].bytes == bytes && g_cache_free[i].dev == dev) {
+        *p = g_cache_free[i].p;
+        g_cache_bytes -= bytes;
+        g_cache_live.push_back(g_cache_free[i]);
+        g_cache_free.erase(g_cache_free.begin() + (long)i);
+        return cudaSuccess;
+      }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess && bytes >= kCacheMinBlock) {   // out of memory with blocks parked: give them back and retry once
+    cudaGetLastError();
+    dev_cache_trim();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess && bytes >= kCacheMinBlock) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_live.push_back(DevBlock{*p, bytes, dev});
+  }
+  return e;
+}
+void dev_free(void* p) {
+  if (!p) return;
+  bool big = false;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (const DevBlock& b : g_cache_live) big = big || b.p == p;
+  }
+  if (big) cudaDeviceSynchronize();   // cudaFree would have waited for work still using the block; a parked block must be idle too
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache_live.size(); ++i)
+      if (g_cache_live[i].p == p) {
+        const DevBlock b = g_cache_live[i];
+        g_cache_live.erase(g_cache_live.begin() + (long)i);
+        if (g_cache_bytes + b.bytes <= cache_cap()) {
+          g_cache_free.push_back(b);
+          g_cache_bytes += b.bytes;
+          return;
+        }
+        break;
+      }
+  }
+  cudaFree(p);
+}
+void dev_cache_trim() {
+  std::vector<DevBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    blocks.swap(g_cache_free);
+    g_cache_bytes = 0;
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const DevBlock& b : blocks) { cudaSetDevice(b.dev); cudaFree(b.p); }
+  cudaSetDevice(cur);
+}
 
 int set_err(ga_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
@@ -71,6 +149,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   if (dtype < 0 || dtype > 3 || (dtype == GA_F32 && world_size != 1) || n_global <= 0 || n_local <= 0 || ncv <= 0 || ncv > kMaxNcv || world_size < 1 ||
       rank < 0 || rank >= world_size || row_offset < 0 || row_offset + n_local > n_global)
     return GA_ERR_ARG;
+  const double t_create0 = now_s();
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GA_ERR_CUDA;  // no silent CPU fallback
   ga_ctx* c = new ga_ctx();
@@ -104,6 +183,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
   if (const char* e = getenv("GA_SPMV_V1")) c->use_spmv_stream = !(e[0] == '1');
   if (const char* e = getenv("GA_GS_XPREFETCH")) c->gs_xprefetch = !(e[0] == '0');
+  if (const char* e = getenv("GA_UPLOAD_THREADS")) c->upload_threads = atoi(e) >= 1 ? atoi(e) : c->upload_threads;
   if (const char* e = getenv("GA_VQ_STREAM")) c->vq_stream = !(e[0] == '0');
   if (const char* e = getenv("GA_GS_TWO_SETS")) c->gs_two_sets = !(e[0] == '0');
   if (const char* e = getenv("GA_GS_MIN2K")) c->gs_min_stages_2k = atoi(e) >= 2 ? atoi(e) : c->gs_min_stages_2k;
@@ -112,8 +192,8 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
-  CK(cudaMalloc(&c->V, (size_t)c->n_pad * ncv * c->esize));
-  CK(cudaMalloc(&c->resid, (size_t)c->n_pad * c->esize));
+  CK(dev_alloc(&c->V, (size_t)c->n_pad * ncv * c->esize));
+  CK(dev_alloc(&c->resid, (size_t)c->n_pad * c->esize));
   CK(cudaMemsetAsync(c->V, 0, (size_t)c->n_pad * ncv * c->esize, c->stream));
   CK(cudaMemsetAsync(c->resid, 0, (size_t)c->n_pad * c->esize, c->stream));
   c->vs.V = c->V; c->vs.w = c->resid; c->vs.ld = c->n_pad; c->vs.rows = c->n;
@@ -126,6 +206,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   CK(cudaMalloc(&c->qdev, (size_t)kMaxNcv * kMaxNcv * 16));
   CK(cudaStreamSynchronize(c->stream));
 #undef CK
+  if (getenv("GA_TIMING")) fprintf(stderr, "ga_create: %.1f ms\n", (now_s() - t_create0) * 1e3);
   *out = c;
   return 0;
 }
@@ -140,7 +221,7 @@ void ga_destroy(ga_ctx* c) {
   c->At.free_all();
   for (auto& w : c->Wblk) w.free_all();
   general_free(c);
-  cudaFree(c->V); cudaFree(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
+  dev_free(c->V); dev_free(c->resid); cudaFree(c->xfull); cudaFree(c->ctl); cudaFree(c->partial);
   cudaFree(c->gather); cudaFree(c->qdev); cudaFree(c->zdev); cudaFree(c->wbuf);
   cudaFree(c->send_idx); cudaFree(c->send_buf); cudaFree(c->halo); cudaFree(c->trace); cudaFree(c->spmv_chk); cudaFree(c->zinv); cudaFree(c->zrecv);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
@@ -152,6 +233,8 @@ void ga_destroy(ga_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
+
+void ga_trim_cache(void) { dev_cache_trim(); }
 
 int ga_set_option(ga_ctx* c, int key, int64_t value) {
   if (!c) return GA_ERR_ARG;
@@ -186,10 +269,14 @@ int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void*
   GA_CUDA(c, cudaSetDevice(c->device));
   clear_operator(c);
   if (c->world != 1) return set_err(c, GA_ERR_ARG, "multi-GPU contexts take ga_set_csr_dist (local columns + halo plan)");
+  const double t0 = now_s();
   int rc = csr_upload(c, c->A, c->n, c->n_global, rowptr, col, val, 0);
   if (rc) return rc;
   c->op_kind = 1;
-  return spmv_autotune(c, c->A, c->V, c->resid);
+  const double t1 = now_s();
+  rc = spmv_autotune(c, c->A, c->V, c->resid);
+  if (getenv("GA_TIMING")) fprintf(stderr, "ga_set_csr: upload %.1f ms, autotune %.1f ms\n", (t1 - t0) * 1e3, (now_s() - t1) * 1e3);
+  return rc;
 }
 
 // Row-sharded operator: this rank's rows with columns already remapped by the caller:

@@ -87,6 +87,15 @@ struct DevComm {
   long long zp_halo_elem;                   // = n_pad: partial results are laid out [own rows | halo columns]
 };
 
+// Process-wide cache of large device blocks (>= 32 MiB, exact-size reuse, bounded): a solve creates a context (basis, CSR
+// arrays: gigabytes) and destroys it; cudaMalloc / cudaFree of such blocks cost 15-250 ms on B200 (mapping + scrubbing) and sit
+// inside the end-to-end time of every solve.  dev_free parks big blocks, dev_alloc hands them back to the next context
+// of the same shape.  Blocks handed to other processes (cudaIpc: halo, mailboxes) never come from here.  ga_trim_cache()
+// returns everything to the driver; GA_CACHE_BYTES (default 24 GiB) bounds what is kept.
+cudaError_t dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+void dev_cache_trim();
+
 struct CsrDev {
   i64 nrows = 0, ncols = 0, nnz = 0;
   int* rowptr = nullptr;    // nrows+1 (32-bit: nnz < 2^31 per rank)
@@ -102,7 +111,7 @@ struct CsrDev {
   int nlong = 0;
   int tune_groups = 4, tune_stages = 6;  // consumer groups / pipeline stages picked by the upload-time autotune
   void free_all() {
-    cudaFree(rowptr); cudaFree(col); cudaFree(val); cudaFree(rowblk); cudaFree(desc); cudaFree(longrow);
+    dev_free(rowptr); dev_free(col); dev_free(val); cudaFree(rowblk); cudaFree(desc); cudaFree(longrow);
     rowptr = col = rowblk = longrow = nullptr; val = nullptr; desc = nullptr; nblk = 0; nnz = 0; ndesc = 0; nlong = 0;
   }
 };
@@ -201,6 +210,7 @@ struct ga_ctx {
   int gs_min_stages_2k = 3;             // step kernel: 2 KiB column segments need this many ring stages, else 1 KiB tiles moved by tensor-map copies (GA_GS_MIN2K: 2 = the round-1 rule)
   std::vector<CUtensorMap> gs_maps;     // tensor maps of V, box = R rows x j columns, index j (lazily encoded; k_gs_step.cu)
   std::vector<char> gs_maps_ok;
+  int upload_threads = 8;               // host threads of csr_upload's index passes (GA_UPLOAD_THREADS at ga_create)
   bool vq_stream = true;                // V*Q: streaming two-group kernel for up to 16 outputs (GA_VQ_STREAM=0 at ga_create: A/B switch)
   bool gs_two_sets = true;              // step kernel: two consumer sets for short bases (GA_GS_TWO_SETS=0 at ga_create: A/B switch)
   int gs_seg1024_from = 1 << 30;        // step kernel: 1 KiB column segments from this many columns on (default: only when 2 KiB stages no longer fit twice)

@@ -21,6 +21,8 @@
 #include "ga_tma.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <thread>
@@ -581,6 +583,9 @@ int launch_normal_half(ga_ctx* c, const void* x, void* y) {
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift) {
   M.free_all();
+  const bool timing = getenv("GA_TIMING") != nullptr;   // debug: stderr breakdown of the upload
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tt0 = now();
   const i64 nnz = rowptr[nrows] - rowptr[0];
   if (nnz >= (i64)2147483647LL || nrows >= (i64)2147483647LL)
     return set_err(c, GA_ERR_ARG, "csr: more than 2^31-1 non-zeros or rows per rank is not supported");
@@ -591,14 +596,15 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
   M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
   // The two big arrays go first: their copies (from pinned host memory: true DMA) run while the host validates the
   // indices and builds the row blocks below.  +8 elements: the streamed kernel copies 16-byte aligned supersets of each segment.
-  GA_CUDA(c, cudaMalloc(&M.col, sizeof(int) * (size_t)(std::max<i64>(nnz, 1) + 8)));
-  GA_CUDA(c, cudaMalloc(&M.val, c->esize * (size_t)(std::max<i64>(nnz, 1) + 8)));
+  GA_CUDA(c, dev_alloc((void**)&M.col, sizeof(int) * (size_t)(std::max<i64>(nnz, 1) + 8)));
+  GA_CUDA(c, dev_alloc(&M.val, c->esize * (size_t)(std::max<i64>(nnz, 1) + 8)));
   GA_CUDA(c, cudaMemsetAsync((char*)M.col + sizeof(int) * (size_t)std::max<i64>(nnz, 1), 0, sizeof(int) * 8, c->stream));
   GA_CUDA(c, cudaMemsetAsync((char*)M.val + c->esize * (size_t)std::max<i64>(nnz, 1), 0, c->esize * 8, c->stream));
   if (nnz > 0) {
     GA_CUDA(c, cudaMemcpyAsync(M.val, (const char*)val + (size_t)base * c->esize, c->esize * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
     if (col_shift == 0) GA_CUDA(c, cudaMemcpyAsync(M.col, col + base, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
   }
+  const double tt1 = now();
   auto fail = [&](const char* msg) {   // nothing may still be reading the caller's arrays when we return
     cudaStreamSynchronize(c->stream);
     M.free_all();
@@ -611,7 +617,7 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
   std::vector<int> rp((size_t)nrows + 1);
   {
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nthr = (nnz + nrows < (1 << 20)) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+    const int nthr = (nnz + nrows < (1 << 20)) ? 1 : (int)std::max(1u, std::min((unsigned)c->upload_threads, hw ? hw : 1u));
     std::vector<int64_t> dmin((size_t)nthr, 0);
     std::vector<int32_t> cmin((size_t)nthr, 2147483647), cmax((size_t)nthr, -2147483647 - 1);
     const int32_t* cb = col + base;
@@ -640,6 +646,7 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
       if ((i64)lo - col_shift < 0 || (i64)hi - col_shift >= ncols) return fail("csr: column index outside [0, ncols)");
     }
   }
+  const double tt2 = now();
   // row blocks of the first kernel (<= CAP non-zeros, <= MAXROWS rows) and of the streamed kernel (one pipeline stage each;
   // longer rows go to a list): two independent sequential scans, one host thread each
   std::vector<int> blk;
@@ -669,7 +676,7 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
       r0 = e;
     }
   };
-  if (nrows > (1 << 18)) {
+  if (nrows > (1 << 18) && c->upload_threads > 1) {
     std::thread t1(build_blk);
     build_desc();
     t1.join();
@@ -678,8 +685,9 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
     build_desc();
   }
   M.nblk = (int)blk.size() - 1;
+  const double tt3 = now();
   M.ndesc = (int)desc.size(); M.nlong = (int)longrow.size();
-  GA_CUDA_DRAIN(c, cudaMalloc(&M.rowptr, sizeof(int) * ((size_t)nrows + 1 + 8)));
+  GA_CUDA_DRAIN(c, dev_alloc((void**)&M.rowptr, sizeof(int) * ((size_t)nrows + 1 + 8)));
   GA_CUDA_DRAIN(c, cudaMemsetAsync((char*)M.rowptr + sizeof(int) * ((size_t)nrows + 1), 0, sizeof(int) * 8, c->stream));
   GA_CUDA_DRAIN(c, cudaMalloc(&M.rowblk, sizeof(int) * blk.size()));
   GA_CUDA_DRAIN(c, cudaMalloc(&M.desc, sizeof(int4) * std::max<size_t>(desc.size(), 1)));
@@ -696,7 +704,11 @@ int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr
     GA_CUDA_DRAIN(c, cudaMemcpyAsync(M.col, cc.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
     GA_CUDA_DRAIN(c, cudaStreamSynchronize(c->stream));
   }
+  const double tt4 = now();
   GA_CUDA_DRAIN(c, cudaStreamSynchronize(c->stream));
+  if (timing)
+    fprintf(stderr, "csr_upload nnz=%lld: alloc+enqueue %.1f ms, index scans %.1f ms, row blocks %.1f ms, small uploads %.1f ms, drain %.1f ms\n",
+            (long long)nnz, (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3, (tt3 - tt2) * 1e3, (tt4 - tt3) * 1e3, (now() - tt4) * 1e3);
   return 0;
 }
 

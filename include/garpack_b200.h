@@ -76,6 +76,10 @@ int ga_device_sm_count(const ga_ctx* ctx);
  *                               bits of h depend on the partition.  Other element types are not affected. */
 enum { GA_OPT_DOT_MODE = 1 };
 enum { GA_DOT_EXACT = 0, GA_DOT_PLAIN = 1 };
+/* The library keeps large device blocks (basis, CSR arrays; >= 32 MiB) of destroyed contexts for the next context of the same
+ * shape (cudaMalloc / cudaFree of gigabytes cost 15-250 ms per solve otherwise); at most GA_CACHE_BYTES (environment,
+ * default 24 GiB) are kept.  ga_trim_cache returns all of them to the driver. */
+void ga_trim_cache(void);
 int ga_set_option(ga_ctx* ctx, int key, int64_t value);
 int ga_get_option(const ga_ctx* ctx, int key, int64_t* value);
 

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out/r02
 OUT=gpurun_out/r02
-timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 > $OUT/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -12 $OUT/pytest_gpu_final.log
+GA_TEST_SKIP_C5_FULL=1 timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 > $OUT/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -12 $OUT/pytest_gpu_final.log
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_final.log
 ( time timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_final_n1.json 2> $OUT/bench_final_n1.err ) 2>&1 | tail -3; echo "bench rc=$?"
 ( time timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_final_ref.json 2> $OUT/bench_final_ref.err ) 2>&1 | tail -3; echo "ref rc=$?"
@@ -18,7 +18,9 @@ r=json.loads(open("gpurun_out/r02/bench_final_ref.json").read().strip().splitlin
 PY
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-tts --no-gate"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 305 -c 200 --csv --log-file $OUT/launches_final.csv $CMD > $OUT/ncu_list_final.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gs_step -s 110 -c 22 -o $OUT/prof_final_gs $CMD > $OUT/ncu_final_gs.log 2>&1; echo "ncu gs rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:k_gs_step -s 120 -c 3 -o $OUT/prof_final_gs $CMD > $OUT/ncu_final_gs.log 2>&1; echo "ncu gs rc=$?"
+ncu -i $OUT/prof_final_gs.ncu-rep --page raw --csv > $OUT/prof_final_gs_raw.csv 2>/dev/null; rm -f $OUT/prof_final_gs.ncu-rep
+python profiles/microbench/upload_bench.py > $OUT/upload_bench.json 2>&1; tail -1 $OUT/upload_bench.json
 timeout 600 python profiles/run_configs.py c1 c3 c4 > $OUT/configs_final.log 2>&1; echo "configs rc=$?"; cp gpurun_out/configs.json $OUT/configs_final.json
 python - <<'PY'
 import json

@@ -244,6 +244,7 @@ int launch_zero_resid(ga_ctx* c);
 // k_spmv.cu
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated);  // y = OP x (device vectors)
 int spmv_autotune(ga_ctx* c, CsrDev& M, const void* x, void* y);  // time the streamed SpMV's configurations once
+int launch_push_halo(ga_ctx* c, const void* x);                   // fused multi-GPU path: x's halo entries -> the peers (k_vec.cu)
 int launch_normal_half(ga_ctx* c, const void* x, void* y);       // y = A x or A^H x (svds post-processing)
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift);

@@ -562,8 +562,13 @@ int spmv_autotune(ga_ctx* c, CsrDev& M, const void* x, void* y) {
 // (src/idonow_ops.jl:311,322).
 int launch_normal_half(ga_ctx* c, const void* x, void* y) {
   if (c->op_kind != 2) return set_err(c, GA_ERR_NOOP, "not a normal-operator context (ga_set_normal_csr)");
-  if (c->normal_dist) {  // y_loc = T_loc [x_own | halo]: the halo of x travels first (grouped ncclSend/ncclRecv)
-    int rc = comm_halo_exchange(c, x);
+  if (c->normal_dist) {  // y_loc = T_loc [x_own | halo]: the halo of x travels first
+    if (c->devcomm) {    // fused path: push into the peers' halo buffers, the product waits on their flags
+      int rc = launch_push_halo(c, x);
+      if (rc) return rc;
+      return spmv_launch(c, c->A, x, y, false, true);
+    }
+    int rc = comm_halo_exchange(c, x);   // grouped ncclSend/ncclRecv
     if (rc) return rc;
   }
   return normal_half(c, !c->normal_left, x, y, false);

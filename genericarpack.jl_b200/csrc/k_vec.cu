@@ -94,6 +94,55 @@ __global__ void __launch_bounds__(256) k_normalize(T* vj, const T* resid, i64 n,
   if (threadIdx.x == 0) { ctl->hseq = hseq; ctl->ticket = 0u; }
 }
 
+// The halo push of k_normalize on its own (fused multi-GPU path): the entries of x that the peers' rows reference go
+// straight into the peers' halo buffers, the last CTA raises the sequence flags.  Used where a product is applied to a
+// vector that is not being normalised (svds post-processing), so that no NCCL communicator is ever needed on that path
+// (creating one costs seconds on 8 GPUs -- more than the whole C5 solve).
+template <class T>
+__global__ void __launch_bounds__(256) k_push_halo(const T* __restrict__ x, DevCtl* ctl, const DevComm* cm,
+                                                   const int* __restrict__ send_idx) {
+  const unsigned int hseq = ctl->hseq + 1u;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const int nsend = cm->send_off[cm->world];
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nsend; i += stride) {
+    int q = 0;
+    while (i >= cm->send_off[q + 1]) ++q;
+    T* dst = reinterpret_cast<T*>(cm->peer_halo[q]) + cm->dest_off[q] + (i - cm->send_off[q]);
+    *dst = x[send_idx[i]];
+  }
+  __shared__ int sh_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(&ctl->ticket, 1u);
+    sh_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < cm->world && cm->send_off[threadIdx.x + 1] > cm->send_off[threadIdx.x])
+    st_sys_u32(&cm->peer[threadIdx.x]->hflags[cm->rank], hseq);
+  if (threadIdx.x == 0) { ctl->hseq = hseq; ctl->ticket = 0u; }
+}
+
+int launch_push_halo(ga_ctx* c, const void* x) {
+  if (c->world <= 1 || !c->devcomm) return set_err(c, GA_ERR_ARG, "halo push needs the fused multi-GPU path");
+  const int threads = 256;
+  i64 blocks = ((i64)c->nsend + threads - 1) / threads;
+  const i64 maxb = (i64)c->sm_count * 4;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  switch (c->dtype) {
+    case GA_F64: k_push_halo<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)x, c->ctl, c->devcomm, c->send_idx); break;
+    case GA_C64: k_push_halo<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)x, c->ctl, c->devcomm, c->send_idx); break;
+    case GA_F32: k_push_halo<float><<<(int)blocks, threads, 0, c->stream>>>((const float*)x, c->ctl, c->devcomm, c->send_idx); break;
+    default: k_push_halo<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)x, c->ctl, c->devcomm, c->send_idx); break;
+  }
+  GA_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
 int launch_normalize(ga_ctx* c, int jcol, bool push_halo) {
   const int threads = 256;
   const i64 n = c->vs.rows, ld = c->vs.ld;

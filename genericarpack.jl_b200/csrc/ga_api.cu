@@ -183,6 +183,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
   if (const char* e = getenv("GA_NO_STEP_KERNEL")) c->use_step_kernel = !(e[0] == '1');
   if (const char* e = getenv("GA_SPMV_V1")) c->use_spmv_stream = !(e[0] == '1');
   if (const char* e = getenv("GA_GS_XPREFETCH")) c->gs_xprefetch = !(e[0] == '0');
+  if (const char* e = getenv("GA_CG_GRAPH")) c->cg_use_graph = !(e[0] == '0');
   if (const char* e = getenv("GA_UPLOAD_THREADS")) c->upload_threads = atoi(e) >= 1 ? atoi(e) : c->upload_threads;
   if (const char* e = getenv("GA_VQ_STREAM")) c->vq_stream = !(e[0] == '0');
   if (const char* e = getenv("GA_GS_TWO_SETS")) c->gs_two_sets = !(e[0] == '0');

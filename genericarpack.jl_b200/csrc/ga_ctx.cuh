@@ -153,7 +153,10 @@ struct ga_ctx {
   // of the B-inner products, and the work vectors + Jacobi preconditioner of the CG solve with B
   ga::CsrDev Bm;
   void* gz = nullptr;                  // n_pad: A v_j (mode 2: WORKD(IVJ)) or B r (WORKD(IPJ))
-  void* cg_r = nullptr; void* cg_p = nullptr; void* cg_q = nullptr;   // n_pad each
+  void* cg_r = nullptr; void* cg_p = nullptr; void* cg_q = nullptr; void* cg_x = nullptr;   // n_pad each
+  void* cg_graph = nullptr;            // cudaGraphExec_t: 8 CG iterations captured once (k_general.cu)
+  bool cg_graph_tried = false, cg_use_graph = true;   // GA_CG_GRAPH=0 at ga_create: plain launches (A/B switch)
+  size_t cg_graph_launches = 0;
   void* b_dinv = nullptr;              // n_pad reals: 1 / diag(B)
   double cg_tol[2] = {0.0, 0.0};       // relative residual target of the solve (<= 0: 8 eps)
   int cg_maxit = 0;                    // 0: 1000

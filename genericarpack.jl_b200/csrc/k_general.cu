@@ -236,30 +236,76 @@ static int bnorm(ga_ctx* c, const void* x, const void* y, HReal* out) {
   return 0;
 }
 
+// One CG iteration = the B product (streamed SpMV) + three fused vector kernels; every launch early-exits once the
+// convergence flag is set on the device.  At the sizes where this solver matters (n ~ 1e5) an iteration is four launches
+// of a few microseconds each and the HOST is the bottleneck (round 1: 0.78 ms per Lanczos step at n = 90 000), so a batch
+// of 8 iterations is captured once per context into a CUDA graph and replayed: one launch call per 32 kernels.  The graph
+// always solves into the context's own vector (cg_x) so that its kernel arguments never change.
+template <class T, class TR>
+static int cg_enqueue_iterations(ga_ctx* c, int count) {
+  const int grid = vec_grid(c);
+  const i64 n = c->n;
+  T* r = (T*)c->cg_r; T* p = (T*)c->cg_p; T* q = (T*)c->cg_q; T* x = (T*)c->cg_x;
+  const TR* dinv = (const TR*)c->b_dinv;
+  for (int k = 0; k < count; ++k) {
+    int rc;
+    if ((rc = launch_spmv_mat(c, c->Bm, p, q, true))) return rc;
+    k_cg_pq<T><<<grid, 256, 0, c->stream>>>(p, q, n, c->ctl, c->partial);
+    k_cg_update<T, TR><<<grid, 256, 0, c->stream>>>(x, r, p, q, dinv, n, c->ctl, c->partial);
+    k_cg_p<T, TR><<<grid, 256, 0, c->stream>>>(r, p, dinv, n, c->ctl);
+    GA_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+  }
+  return 0;
+}
+
+constexpr int kCgGraphIters = 8;
+
+template <class T, class TR>
+static void cg_build_graph(ga_ctx* c) {
+  c->cg_graph_tried = true;
+  if (!c->cg_use_graph) return;
+  const size_t launches0 = c->launches;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return; }
+  const int rc = cg_enqueue_iterations<T, TR>(c, kCgGraphIters);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+  c->cg_graph_launches = c->launches - launches0;
+  c->launches = launches0;
+  if (rc != 0 || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return; }
+  cudaGraphExec_t ex = nullptr;
+  if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) c->cg_graph = ex;
+  else cudaGetLastError();
+  cudaGraphDestroy(g);
+}
+
 template <class T, class TR>
 static int cg_solve_t(ga_ctx* c, const void* b, void* x) {
   const int grid = vec_grid(c);
   const i64 n = c->n;
-  T* r = (T*)c->cg_r; T* p = (T*)c->cg_p; T* q = (T*)c->cg_q;
+  T* r = (T*)c->cg_r; T* p = (T*)c->cg_p;
   const TR* dinv = (const TR*)c->b_dinv;
   double tol = c->cg_tol[0] > 0.0 ? c->cg_tol[0] : (c->dtype == GA_DD ? 8.0 * 4.930380657631324e-32 : 8.0 * 2.220446049250313e-16);
   const double tol2[2] = {tol * tol, 0.0};
   GA_CUDA(c, cudaMemcpyAsync(c->ctl->cg_tol2, tol2, sizeof(tol2), cudaMemcpyHostToDevice, c->stream));
-  k_cg_init<T, TR><<<grid, 256, 0, c->stream>>>((const T*)b, (T*)x, r, p, dinv, n, c->ctl, c->partial);
+  k_cg_init<T, TR><<<grid, 256, 0, c->stream>>>((const T*)b, (T*)c->cg_x, r, p, dinv, n, c->ctl, c->partial);
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
+  if (!c->cg_graph_tried) cg_build_graph<T, TR>(c);
   const int maxit = c->cg_maxit > 0 ? c->cg_maxit : 1000;
   int it = 0, rc;
   bool done = false;
   int batch = 8;
   while (!done) {
-    for (int k = 0; k < batch && it < maxit; ++k, ++it) {
-      if ((rc = launch_spmv_mat(c, c->Bm, p, q, true))) return rc;
-      k_cg_pq<T><<<grid, 256, 0, c->stream>>>(p, q, n, c->ctl, c->partial);
-      k_cg_update<T, TR><<<grid, 256, 0, c->stream>>>((T*)x, r, p, q, dinv, n, c->ctl, c->partial);
-      k_cg_p<T, TR><<<grid, 256, 0, c->stream>>>(r, p, dinv, n, c->ctl);
-      GA_CUDA(c, cudaGetLastError());
-      c->launches += 3;
+    if (c->cg_graph) {                                   // whole graphs of kCgGraphIters iterations (extra ones are no-ops once converged)
+      for (int k = 0; k < batch && it < maxit; k += kCgGraphIters, it += kCgGraphIters) {
+        GA_CUDA(c, cudaGraphLaunch((cudaGraphExec_t)c->cg_graph, c->stream));
+        c->launches += c->cg_graph_launches;
+      }
+    } else {
+      const int cnt = std::min(batch, maxit - it);
+      if ((rc = cg_enqueue_iterations<T, TR>(c, cnt))) return rc;
+      it += cnt;
     }
     if ((rc = sync_ctl(c))) return rc;
     const DevCtl* hc = c->ctl_host;
@@ -279,6 +325,7 @@ static int cg_solve_t(ga_ctx* c, const void* b, void* x) {
     const double rel = std::sqrt(hc->cg_rr[0] / hc->cg_bb[0]);
     if (rel > c->solve_max_relres) c->solve_max_relres = rel;
   }
+  GA_CUDA(c, cudaMemcpyAsync(x, c->cg_x, (size_t)c->n * c->esize, cudaMemcpyDeviceToDevice, c->stream));
   return set_status_ok(c);
 }
 
@@ -299,8 +346,10 @@ static int general_solve(ga_ctx* c, const void* b, void* x) {
 
 void general_free(ga_ctx* c) {
   c->Bm.free_all();
-  cudaFree(c->gz); cudaFree(c->cg_r); cudaFree(c->cg_p); cudaFree(c->cg_q); cudaFree(c->b_dinv);
-  c->gz = c->cg_r = c->cg_p = c->cg_q = c->b_dinv = nullptr;
+  if (c->cg_graph) { cudaGraphExecDestroy((cudaGraphExec_t)c->cg_graph); c->cg_graph = nullptr; }
+  c->cg_graph_tried = false;
+  cudaFree(c->gz); cudaFree(c->cg_r); cudaFree(c->cg_p); cudaFree(c->cg_q); cudaFree(c->cg_x); cudaFree(c->b_dinv);
+  c->gz = c->cg_r = c->cg_p = c->cg_q = c->cg_x = c->b_dinv = nullptr;
 }
 
 int general_upload(ga_ctx* c, const int64_t* arp, const int32_t* acol, const void* aval, const int64_t* brp,
@@ -336,6 +385,8 @@ int general_upload(ga_ctx* c, const int64_t* arp, const int32_t* acol, const voi
   GA_CUDA(c, cudaMalloc(&c->cg_r, vbytes));
   GA_CUDA(c, cudaMalloc(&c->cg_p, vbytes));
   GA_CUDA(c, cudaMalloc(&c->cg_q, vbytes));
+  GA_CUDA(c, cudaMalloc(&c->cg_x, vbytes));
+  GA_CUDA(c, cudaMemsetAsync(c->cg_x, 0, vbytes, c->stream));
   GA_CUDA(c, cudaMalloc(&c->b_dinv, (size_t)c->n_pad * rs));
   GA_CUDA(c, cudaMemsetAsync(c->gz, 0, vbytes, c->stream));
   GA_CUDA(c, cudaMemsetAsync(c->cg_r, 0, vbytes, c->stream));

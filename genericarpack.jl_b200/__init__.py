@@ -366,6 +366,13 @@ class Context:
         else:
             self.n = int(len(op.rowptr) - 1)
         self.n_global = int(n_global) if n_global is not None else self.n
+        if world_size > 1 and plan is not None:
+            from . import dist as _dist
+            want = _dist.padded_block(self.n_global, world_size, self.dtype)
+            if int(plan["n_pad"]) != want:
+                raise ValueError("the halo plan was built for a local block padded to %d rows, this context pads to %d: "
+                                 "pass dtype= to dist.halo_plan / dist.shard_normal (Float32 blocks are padded to 512 rows)"
+                                 % (int(plan["n_pad"]), want))
         h = ctypes.c_void_p()
         rc = L.ga_create(ctypes.byref(h), self.dtype, self.n_global, self.n, int(row_offset), self.ncv, device, rank,
                          world_size)

@@ -146,7 +146,7 @@ int ga_create(ga_ctx** out, int dtype, int64_t n_global, int64_t n_local, int64_
               int rank, int world_size) {
   if (!out) return GA_ERR_ARG;
   *out = nullptr;
-  if (dtype < 0 || dtype > 3 || (dtype == GA_F32 && world_size != 1) || n_global <= 0 || n_local <= 0 || ncv <= 0 || ncv > kMaxNcv || world_size < 1 ||
+  if (dtype < 0 || dtype > 3 || n_global <= 0 || n_local <= 0 || ncv <= 0 || ncv > kMaxNcv || world_size < 1 ||
       rank < 0 || rank >= world_size || row_offset < 0 || row_offset + n_local > n_global)
     return GA_ERR_ARG;
   const double t_create0 = now_s();

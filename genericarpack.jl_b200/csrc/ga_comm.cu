@@ -184,20 +184,22 @@ int comm_halo_exchange(ga_ctx* c, const void* x_local) {
   NcclApi& a = nccl();
   if (c->nsend > 0) {
     const int threads = 256, blocks = (c->nsend + threads - 1) / threads;
-    if (c->esize == 8) k_pack<double><<<blocks, threads, 0, c->stream>>>((const double*)x_local, c->send_idx, (double*)c->send_buf, c->nsend);
+    if (c->esize == 4) k_pack<float><<<blocks, threads, 0, c->stream>>>((const float*)x_local, c->send_idx, (float*)c->send_buf, c->nsend);
+    else if (c->esize == 8) k_pack<double><<<blocks, threads, 0, c->stream>>>((const double*)x_local, c->send_idx, (double*)c->send_buf, c->nsend);
     else k_pack<double2><<<blocks, threads, 0, c->stream>>>((const double2*)x_local, c->send_idx, (double2*)c->send_buf, c->nsend);
     GA_CUDA(c, cudaGetLastError());
     c->launches += 1;
   }
-  const size_t per = c->esize / 8;
+  const size_t per = c->esize == 4 ? 1 : c->esize / 8;                           // wire words per element
+  const ncclDataType_t wire = c->esize == 4 ? ncclFloat32 : ncclFloat64;
   GA_NCCL(c, a.GroupStart());
   size_t soff = 0, roff = 0;
   for (int q = 0; q < c->world; ++q) {
     if (c->send_counts[q] > 0)
-      GA_NCCL(c, a.Send((const char*)c->send_buf + soff * c->esize, (size_t)c->send_counts[q] * per, ncclFloat64, q,
+      GA_NCCL(c, a.Send((const char*)c->send_buf + soff * c->esize, (size_t)c->send_counts[q] * per, wire, q,
                         (ncclComm_t)c->nccl_comm, c->stream));
     if (c->recv_counts[q] > 0)
-      GA_NCCL(c, a.Recv((char*)c->halo + roff * c->esize, (size_t)c->recv_counts[q] * per, ncclFloat64, q,
+      GA_NCCL(c, a.Recv((char*)c->halo + roff * c->esize, (size_t)c->recv_counts[q] * per, wire, q,
                         (ncclComm_t)c->nccl_comm, c->stream));
     soff += (size_t)c->send_counts[q];
     roff += (size_t)c->recv_counts[q];
@@ -213,15 +215,16 @@ int comm_zp_exchange(ga_ctx* c, const void* zp) {
   if (c->world <= 1) return 0;
   if (int rc = comm_ensure(c)) return rc;
   NcclApi& a = nccl();
-  const size_t per = c->esize / 8;
+  const size_t per = c->esize == 4 ? 1 : c->esize / 8;                           // wire words per element
+  const ncclDataType_t wire = c->esize == 4 ? ncclFloat32 : ncclFloat64;
   GA_NCCL(c, a.GroupStart());
   size_t soff = 0, roff = 0;
   for (int q = 0; q < c->world; ++q) {
     if (c->recv_counts[q] > 0)
-      GA_NCCL(c, a.Send((const char*)zp + ((size_t)c->n_pad + roff) * c->esize, (size_t)c->recv_counts[q] * per, ncclFloat64, q,
+      GA_NCCL(c, a.Send((const char*)zp + ((size_t)c->n_pad + roff) * c->esize, (size_t)c->recv_counts[q] * per, wire, q,
                         (ncclComm_t)c->nccl_comm, c->stream));
     if (c->send_counts[q] > 0)
-      GA_NCCL(c, a.Recv((char*)c->zrecv + soff * c->esize, (size_t)c->send_counts[q] * per, ncclFloat64, q,
+      GA_NCCL(c, a.Recv((char*)c->zrecv + soff * c->esize, (size_t)c->send_counts[q] * per, wire, q,
                         (ncclComm_t)c->nccl_comm, c->stream));
     soff += (size_t)c->send_counts[q];
     roff += (size_t)c->recv_counts[q];

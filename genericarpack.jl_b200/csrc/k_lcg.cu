@@ -93,8 +93,10 @@ __device__ __forceinline__ float lcg_to_unit_f32(unsigned long long x) {
   const float t3 = (float)(unsigned)((x >> 12) & 4095ULL), t4 = (float)(unsigned)(x & 4095ULL);
   return __fmul_rn(R, __fadd_rn(t1, __fmul_rn(R, __fadd_rn(t2, __fmul_rn(R, __fadd_rn(t3, __fmul_rn(R, t4)))))));
 }
-// x[i], i in [i_first, n): value number k0 + (i - i_first) + 1 of the pure stream from `seed`.
-__global__ void __launch_bounds__(256) k_lcg_fill_f32(float* __restrict__ x, i64 n, i64 i_first, i64 k0,
+// Global index i in [i_first, n): value number k0 + (i - i_first) + 1 of the pure stream from `seed`; this rank stores
+// only its rows [row0, row0 + n_local).  Every rank scans the WHOLE index range: where the stream is re-based depends on
+// every earlier draw, and 16M conversions cost less than exchanging the hits would.
+__global__ void __launch_bounds__(256) k_lcg_fill_f32(float* __restrict__ x, i64 n, i64 row0, i64 n_local, i64 i_first, i64 k0,
                                                       unsigned long long seed, const __grid_constant__ LcgPow tab,
                                                       unsigned long long* first_hit) {
   const i64 stride = (i64)gridDim.x * blockDim.x;
@@ -105,14 +107,15 @@ __global__ void __launch_bounds__(256) k_lcg_fill_f32(float* __restrict__ x, i64
   for (i64 i = i0; i < n; i += stride) {
     const float rv = lcg_to_unit_f32(X);
     if (rv == 1.0f) atomicMin(first_hit, (unsigned long long)i);
-    x[i] = __fadd_rn(__fmul_rn(2.0f, rv), -1.0f);                 // :538
+    const i64 il = i - row0;
+    if (il >= 0 && il < n_local) x[il] = __fadd_rn(__fmul_rn(2.0f, rv), -1.0f);   // :538
     X = (X * astride) & kMask48;
   }
 }
 
-// Float32 start vector on one GPU (row0 = 0).  `iseed` is advanced to what the sequential generator leaves behind.
+// Float32 start vector (rows [row0, row0 + n) of the n_global-long vector).  `iseed` is advanced to what the sequential generator leaves behind.
 static int lcg_fill_f32(ga_ctx* c, i64 iseed[4], const LcgPow& tab) {
-  const i64 n = c->n;
+  const i64 n = c->n_global;
   const unsigned long long kTwoC = 2ULL * ((1ULL << 36) | (1ULL << 24) | (1ULL << 12) | 1ULL);   // +2 on every limb
   unsigned long long* hit_dev = reinterpret_cast<unsigned long long*>(c->partial);   // scratch, idle here
   unsigned long long base = seed_to_u64(iseed);   // seed of the 128-value block that holds index i_first
@@ -125,7 +128,7 @@ static int lcg_fill_f32(ga_ctx* c, i64 iseed[4], const LcgPow& tab) {
     const i64 maxb = (i64)c->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    k_lcg_fill_f32<<<(int)blocks, threads, 0, c->stream>>>((float*)c->resid, n, i_first, k0, base, tab, hit_dev);
+    k_lcg_fill_f32<<<(int)blocks, threads, 0, c->stream>>>((float*)c->resid, n, c->row0, c->n, i_first, k0, base, tab, hit_dev);
     GA_CUDA(c, cudaGetLastError());
     c->launches += 1;
     unsigned long long hit = none;

@@ -412,7 +412,11 @@ __global__ void __launch_bounds__(256) k_reduce_scatter(T* __restrict__ out, con
       if (p >= 0) {
         const T* sq = reinterpret_cast<const T*>(src.p[q]);
         T v;
-        if (sizeof(T) == 8) {
+        if (sizeof(T) == 4) {
+          float f;
+          asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(f) : "l"(sq + p));
+          *reinterpret_cast<float*>(&v) = f;
+        } else if (sizeof(T) == 8) {
           double d;
           asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(d) : "l"(sq + p));
           *reinterpret_cast<double*>(&v) = d;
@@ -455,8 +459,8 @@ static int launch_normal_dist(ga_ctx* c, const void* x, void* y, bool gated, boo
   if (blocks > (i64)c->sm_count * 8) blocks = (i64)c->sm_count * 8;
   if (blocks < 1) blocks = 1;
   const DevComm* cm = peer ? c->devcomm : nullptr;
-  if (c->dtype == GA_F32) return set_err(c, GA_ERR_ARG, "Float32 contexts are single-GPU");
   switch (c->dtype) {
+    case GA_F32: k_reduce_scatter<float><<<(int)blocks, threads, 0, c->stream>>>((float*)y, (const float*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
     case GA_F64: k_reduce_scatter<double><<<(int)blocks, threads, 0, c->stream>>>((double*)y, (const double*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
     case GA_C64: k_reduce_scatter<cdbl><<<(int)blocks, threads, 0, c->stream>>>((cdbl*)y, (const cdbl*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;
     default: k_reduce_scatter<ddbl><<<(int)blocks, threads, 0, c->stream>>>((ddbl*)y, (const ddbl*)zp, src, c->zinv, c->n, c->n_pad, c->world, c->rank, c->ctl, gated ? 1 : 0, cm); break;

@@ -11,15 +11,26 @@ import numpy as np
 ROW_PAD = 256  # must match kRowPad in csrc/ga_ctx.cuh
 
 
+def row_pad_for(dtype=None):
+    """Row padding of a context's local block: whole 2 KiB Gram-Schmidt column segments, i.e. 256 rows, 512 for Float32
+    vectors (row_pad in csrc/ga_api.cu).  dtype: a numpy dtype / GA_* code / name as accepted by Context, or None."""
+    if dtype is None:
+        return ROW_PAD
+    if dtype in (3, "f32", "float32") or (not isinstance(dtype, (int, str)) and np.dtype(dtype) == np.float32):
+        return 2 * ROW_PAD
+    return ROW_PAD
+
+
 def block_partition(n, world):
     """Uniform contiguous row blocks: rank r owns [r*blk, min(n, (r+1)*blk))."""
     blk = (n + world - 1) // world
     return blk, [(r * blk, min(n, (r + 1) * blk)) for r in range(world)]
 
 
-def padded_block(n, world):
+def padded_block(n, world, dtype=None):
     blk = (n + world - 1) // world
-    return (blk + ROW_PAD - 1) // ROW_PAD * ROW_PAD
+    pad = row_pad_for(dtype)
+    return (blk + pad - 1) // pad * pad
 
 
 def local_need(col, r0, r1):
@@ -29,15 +40,16 @@ def local_need(col, r0, r1):
     return np.unique(remote)
 
 
-def halo_plan(col, n, rank, world, all_gather_object=None):
-    """Halo plan for this rank's rows (global column indices `col`).
+def halo_plan(col, n, rank, world, all_gather_object=None, dtype=None):
+    """Halo plan for this rank's rows (global column indices `col`).  dtype: the context's element type (only Float32
+    matters: its local blocks are padded to 512 rows, and remote columns are numbered from the padded block size).
 
     all_gather_object(obj) -> list of every rank's obj (default: torch.distributed.all_gather_object).
     Returns dict(col_local int32, nhalo, recv_counts int32[world], send_counts int32[world],
     send_idx int32[sum(send_counts)], need int64[nhalo])."""
     blk, parts = block_partition(n, world)
     r0, r1 = parts[rank]
-    n_pad = padded_block(n, world)
+    n_pad = padded_block(n, world, dtype)
     col = np.asarray(col, dtype=np.int64)
     need = local_need(col, r0, r1)
     owner = need // blk
@@ -72,10 +84,11 @@ def halo_plan(col, n, rank, world, all_gather_object=None):
             "row_range": (r0, r1)}
 
 
-def shard_normal(A, rank, world, all_gather_object=None):
+def shard_normal(A, rank, world, all_gather_object=None, dtype=None):
     """Row sharding of ArpackNormalOp(A) (svds): T = A for m > n (At_side = :left), T = A^H otherwise;
     rank r owns a uniform block of T's rows and the usual block of the length-min(m, n) Lanczos vectors.
-    A: scipy sparse matrix (every rank may pass the full matrix, or just its rows via `rows_of_T`).
+    A: scipy sparse matrix (every rank may pass the full matrix, or just its rows via `rows_of_T`); dtype: the context's
+    element type when it is not A's (Float32 blocks are padded to 512 rows, see halo_plan).
     Returns (csr_rows, plan, n, (t0, t1)): csr_rows = (rowptr int64, col int32 global, val, (mt_local, n))."""
     import scipy.sparse as sp
 
@@ -89,7 +102,7 @@ def shard_normal(A, rank, world, all_gather_object=None):
     Tl = T[t0:t1]
     rowptr = np.ascontiguousarray(Tl.indptr, dtype=np.int64)
     col = np.ascontiguousarray(Tl.indices, dtype=np.int32)
-    plan = halo_plan(col, n, rank, world, all_gather_object)
+    plan = halo_plan(col, n, rank, world, all_gather_object, dtype=A.dtype if dtype is None else dtype)
     return (rowptr, col, Tl.data, (t1 - t0, n)), plan, n, (t0, t1)
 
 

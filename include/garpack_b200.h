@@ -15,7 +15,8 @@
  *   - element types: GA_F64 (double), GA_C64 (re,im pairs), GA_DD (hi,lo pairs = Julia Double64),
  *     GA_F32 (float vectors with a Float64 factorisation: the reference's mixed-precision
  *     symeigs(Float32, Float64, op, nev), src/interface.jl:26-34, README.md:28-35; V, resid, the CSR
- *     values and every host vector/matrix of elements are `float`; single GPU, modes 1 and normal op).
+ *     values and every host vector/matrix of elements are `float`; modes 1 and normal op, one or several GPUs --
+ *     local blocks are padded to 512 rows instead of 256, which the halo plan's column numbering follows).
  *   - "real" scalars (rnorm, H, Q, tol, shifts, Ritz values) are `double` for GA_F64/GA_C64/GA_F32 and
  *     (hi,lo) pairs of double for GA_DD; pointers to them are `void*`/`double*` documented per call.
  *   - host pointers are caller-owned; the library never keeps them after the call returns.
@@ -111,7 +112,7 @@ int ga_comm_ipc_import(ga_ctx* ctx, const void* all_handles /* world x 128 bytes
 int ga_set_csr(ga_ctx* ctx, const int64_t* rowptr, const int32_t* col, const void* val);
 /* Row-sharded ArpackSimpleOp (world_size > 1).  The caller (who owns rendezvous) remaps the
  * columns of this rank's rows: own column g -> g - row_offset; remote column -> n_pad + its
- * position in the halo, n_pad = n_block rounded up to 256 rows, n_block = ceil(n_global/world).
+ * position in the halo, n_pad = n_block rounded up to 256 rows (512 for GA_F32), n_block = ceil(n_global/world).
  * The halo lists the needed remote columns in ascending global order; recv_counts[q] of them are
  * owned by rank q.  send_idx (grouped by destination, send_counts[q] each) are the LOCAL row
  * indices whose x entries rank q needs.  Per OP*x the library packs and exchanges exactly these

@@ -151,3 +151,32 @@ def test_block_partition():
     assert gd.padded_block(16_000_000, 8) == 2_000_128 - 2_000_128 % 256 or gd.padded_block(16_000_000, 8) % 256 == 0
     need = gd.local_need(np.array([0, 5, 9, 4, 7]), 4, 8)
     assert list(need) == [0, 9]
+
+
+def test_float32_blocks_are_padded_to_512_rows():
+    """Float32 contexts pad the local block to whole 2 KiB column segments = 512 rows (row_pad in csrc/ga_api.cu); the
+    halo plan numbers remote columns from that padded size."""
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    import __graft_entry__ as entry
+
+    pkg = entry.load_package()
+    gd = importlib.import_module(entry.PKG_NAME + ".dist")
+    syn = importlib.import_module(entry.PKG_NAME + ".synthetic")
+    assert gd.row_pad_for(None) == gd.row_pad_for(np.float64) == gd.row_pad_for(pkg.GA_C64) == 256
+    assert gd.row_pad_for(np.float32) == gd.row_pad_for("f32") == gd.row_pad_for(pkg.GA_F32) == 512
+    assert gd.padded_block(22500, 2) == 11264 and gd.padded_block(22500, 2, np.float32) == 11264
+    assert gd.padded_block(1300, 2) == 768 and gd.padded_block(1300, 2, np.float32) == 1024
+    # a two-rank plan computed serially (all_gather_object replaced by the precomputed needs)
+    m, world = 36, 2
+    n = m * m
+    blk, parts = gd.block_partition(n, world)
+    cols = [syn.laplacian2d(m, row_range=parts[r])[1] for r in range(world)]
+    needs = [gd.local_need(cols[r], *parts[r]) for r in range(world)]
+    for dt, pad in ((None, 768), (np.float32, 1024)):
+        for r in range(world):
+            plan = gd.halo_plan(cols[r], n, r, world, all_gather_object=lambda obj: needs, dtype=dt)
+            assert plan["n_pad"] == pad and plan["nhalo"] == m
+            remote = (cols[r] < parts[r][0]) | (cols[r] >= parts[r][1])
+            assert np.all(plan["col_local"][remote] >= pad) and np.all(plan["col_local"][~remote] < blk)

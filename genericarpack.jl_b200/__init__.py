@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "ga_create", "ga_destroy", "ga_trim_cache", "ga_set_option", "ga_get_option", "ga_last_error", "ga_device_sm_count", "ga_comm_unique_id", "ga_comm_init", "ga_comm_ipc_export", "ga_comm_ipc_import",
     "ga_set_csr", "ga_set_csr_dist", "ga_set_normal_csr", "ga_set_normal_csr_dist", "ga_opx", "ga_upload_resid", "ga_download_resid", "ga_upload_v",
     "ga_download_v", "ga_getv0", "ga_lanczos", "ga_apply_shifts", "ga_ritz_vectors", "ga_svd_vectors", "ga_norm2_resid", "ga_bnorm_resid",
-    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_host_tridiag_eig", "ga_host_ritz_and_bounds", "ga_host_sort_pair", "ga_host_select_shifts", "ga_host_count_converged", "ga_host_chase_shifts", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
+    "ga_get_stats", "ga_reset_stats", "ga_timer_start", "ga_timer_stop", "ga_profile", "ga_profile_read", "ga_profile_gs_launches", "ga_profile_gs_times", "ga_bench_opx", "ga_debug_trace", "ga_debug_spmv_check", "ga_tune_spmv", "ga_set_op_callback", "ga_set_normal_op_callbacks", "ga_set_generalized_csr", "ga_set_generalized_csr_dist", "ga_set_solve_callback", "ga_bx", "ga_get_solve_stats", "ga_host_tridiag_eig", "ga_host_ritz_and_bounds", "ga_host_sort_pair", "ga_host_select_shifts", "ga_host_count_converged", "ga_host_chase_shifts", "ga_symeigs", "ga_symeigs_begin", "ga_symeigs_iterate", "ga_symeigs_end",
 ]
 
 
@@ -109,6 +109,7 @@ def lib():
         L.ga_set_normal_csr_dist.argtypes = [vp, i64, vp, vp, vp, i32, vp, vp, vp, vp]
         L.ga_opx.argtypes = [vp, vp, vp]
         L.ga_set_generalized_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.ga_set_generalized_csr_dist.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
         L.ga_set_solve_callback.argtypes = [vp, vp, vp]
         L.ga_set_op_callback.argtypes = [vp, vp, vp]
         L.ga_set_normal_op_callbacks.argtypes = [vp, i64, i64, vp, vp, vp]
@@ -330,7 +331,9 @@ class ArpackSymmetricGeneralizedOp(B200ArpackOp):
     arpack_mode = 2
     bmat = "G"
 
-    def __init__(self, A, B, dtype=None, cg_tol=None, cg_maxit=0):
+    def __init__(self, A, B, dtype=None, cg_tol=None, cg_maxit=0, sharded=False):
+        """sharded=True: A and B are this rank's rows (n_local x n, global columns) for a multi-GPU Context, which also
+        needs the common halo plan of dist.shard_generalized."""
         import scipy.sparse as sp
 
         if dtype is None:
@@ -338,7 +341,7 @@ class ArpackSymmetricGeneralizedOp(B200ArpackOp):
             dtype = GA_C64 if cplx else GA_F64
         super().__init__(A, dtype=dtype)
         self.Bop = B200ArpackOp(B, dtype=dtype)
-        if self.Bop.shape != self.shape or self.shape[0] != self.shape[1]:
+        if self.Bop.shape != self.shape or (self.shape[0] != self.shape[1] and not sharded):
             raise ValueError("A and B must be square matrices of the same size")
         self.cg_tol, self.cg_maxit = cg_tol, int(cg_maxit)
 
@@ -389,11 +392,18 @@ class Context:
                 self._ck(L.ga_set_normal_op_callbacks(self.h, m, n, ctypes.cast(op._cb[0], ctypes.c_void_p),
                                                       ctypes.cast(op._cb[1], ctypes.c_void_p), None))
         elif isinstance(op, ArpackSymmetricGeneralizedOp):
-            if world_size != 1:
-                raise ValueError("the generalised problem runs on one GPU")
             tol = None if op.cg_tol is None else np.array([float(op.cg_tol), 0.0])
-            self._ck(L.ga_set_generalized_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val), _p(op.Bop.rowptr),
-                                              _p(op.Bop.col), _p(op.Bop.val), _p(tol), op.cg_maxit))
+            if world_size > 1:   # this rank's rows of A and B, one halo plan for both (dist.shard_generalized)
+                if plan is None or "col_local_b" not in plan:
+                    raise ValueError("a multi-GPU generalised problem needs the common halo plan of A and B (dist.shard_generalized)")
+                self.plan = plan
+                self._ck(L.ga_set_generalized_csr_dist(self.h, _p(op.rowptr), _p(plan["col_local"]), _p(op.val), _p(op.Bop.rowptr),
+                                                       _p(plan["col_local_b"]), _p(op.Bop.val), _p(tol), op.cg_maxit,
+                                                       int(plan["nhalo"]), _p(plan["recv_counts"]), _p(plan["send_counts"]),
+                                                       _p(plan["send_idx"]), _p(plan["send_dest_off"])))
+            else:
+                self._ck(L.ga_set_generalized_csr(self.h, _p(op.rowptr), _p(op.col), _p(op.val), _p(op.Bop.rowptr),
+                                                  _p(op.Bop.col), _p(op.Bop.val), _p(tol), op.cg_maxit))
         elif op.normal and world_size > 1:
             if plan is None:
                 raise ValueError("a multi-GPU context needs the halo plan (dist.halo_plan / dist.shard_normal)")

@@ -106,6 +106,7 @@ static void clear_operator(ga_ctx* c) {   // before a new operator is installed
   for (auto& w : c->Wblk) w.free_all();
   c->Wblk.clear();
   c->wblk_cols = 0;
+  c->general_dist = false;
   c->op_kind = 0;
   c->op_cb = c->av_cb = c->atv_cb = nullptr;
   c->op_user = nullptr;
@@ -286,25 +287,19 @@ int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void*
 // where the halo lists the needed remote columns in ascending global order (= grouped by owner
 // rank), recv_counts[q] of them owned by rank q; send_idx (grouped by destination rank, send_counts[q]
 // each) are the LOCAL row indices whose x entries rank q needs from this rank.
-int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, const void* val, int32_t nhalo,
-                    const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx,
-                    const int32_t* send_dest_off) {
-  if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0) return GA_ERR_ARG;
-  GA_CUDA(c, cudaSetDevice(c->device));
-  if (c->ipc_exported || c->devcomm) return set_err(c, GA_ERR_ARG, "the sharded operator cannot be replaced after ga_comm_ipc_export (peers hold the halo buffer's handle): create a new context");
-  {  // the plan indexes device memory directly: validate it here
-    int ns = 0;
-    for (int q = 0; q < c->world; ++q) {
-      if (send_counts[q] < 0 || recv_counts[q] < 0) return set_err(c, GA_ERR_ARG, "ga_set_csr_dist: negative count in the halo plan");
-      ns += send_counts[q];
-    }
-    for (int k = 0; send_idx && k < ns; ++k)
-      if (send_idx[k] < 0 || send_idx[k] >= c->n) return set_err(c, GA_ERR_ARG, "ga_set_csr_dist: send_idx outside the local rows");
+static int validate_halo_plan(ga_ctx* c, const char* who, const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx) {
+  int ns = 0;   // the plan indexes device memory directly: validate it here
+  for (int q = 0; q < c->world; ++q) {
+    if (send_counts[q] < 0 || recv_counts[q] < 0) return set_err(c, GA_ERR_ARG, std::string(who) + ": negative count in the halo plan");
+    ns += send_counts[q];
   }
-  clear_operator(c);
-  c->normal_dist = false;
-  int rc = csr_upload(c, c->A, c->n, c->n_pad + nhalo, rowptr, col_local, val, 0);
-  if (rc) return rc;
+  for (int k = 0; send_idx && k < ns; ++k)
+    if (send_idx[k] < 0 || send_idx[k] >= c->n) return set_err(c, GA_ERR_ARG, std::string(who) + ": send_idx outside the local rows");
+  return 0;
+}
+// counts, offsets, send list and the halo buffer the peers push into (exported by ga_comm_ipc_export afterwards)
+static int install_halo_plan(ga_ctx* c, int32_t nhalo, const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx,
+                             const int32_t* send_dest_off) {
   c->send_counts.assign(send_counts, send_counts + c->world);
   c->recv_counts.assign(recv_counts, recv_counts + c->world);
   if (send_dest_off) c->dest_off.assign(send_dest_off, send_dest_off + c->world);
@@ -320,6 +315,21 @@ int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, 
   GA_CUDA(c, cudaMalloc(&c->halo, c->esize * (size_t)(nhalo > 0 ? nhalo : 1)));
   if (nsend > 0) GA_CUDA(c, cudaMemcpy(c->send_idx, send_idx, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
   GA_CUDA(c, cudaMemset(c->halo, 0, c->esize * (size_t)(nhalo > 0 ? nhalo : 1)));
+  return 0;
+}
+
+int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, const void* val, int32_t nhalo,
+                    const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx,
+                    const int32_t* send_dest_off) {
+  if (!c || !rowptr || !col_local || !val || !recv_counts || !send_counts || nhalo < 0) return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  if (c->ipc_exported || c->devcomm) return set_err(c, GA_ERR_ARG, "the sharded operator cannot be replaced after ga_comm_ipc_export (peers hold the halo buffer's handle): create a new context");
+  int rc = validate_halo_plan(c, "ga_set_csr_dist", recv_counts, send_counts, send_idx);
+  if (rc) return rc;
+  clear_operator(c);
+  c->normal_dist = false;
+  if ((rc = csr_upload(c, c->A, c->n, c->n_pad + nhalo, rowptr, col_local, val, 0))) return rc;
+  if ((rc = install_halo_plan(c, nhalo, recv_counts, send_counts, send_idx, send_dest_off))) return rc;
   c->op_kind = 1;
   return spmv_autotune(c, c->A, c->V, c->resid);
 }
@@ -518,15 +528,44 @@ int ga_set_generalized_csr(ga_ctx* c, const int64_t* a_rowptr, const int32_t* a_
   if (!c || !a_rowptr || !a_col || !a_val || !b_rowptr || !b_col || !b_val || cg_maxit < 0) return GA_ERR_ARG;
   GA_CUDA(c, cudaSetDevice(c->device));
   clear_operator(c);
-  if (c->world != 1) return set_err(c, GA_ERR_ARG, "generalised problem: single GPU only");
+  if (c->world != 1) return set_err(c, GA_ERR_ARG, "multi-GPU contexts take ga_set_generalized_csr_dist (local columns of A and B + their common halo plan)");
   if (c->dtype == GA_F32) return set_err(c, GA_ERR_ARG, "generalised problem: Float32 vectors are not supported (mode 1 / normal operator only)");
   c->cg_tol[0] = cg_tol ? cg_tol[0] : 0.0;
   c->cg_tol[1] = 0.0;
   c->cg_maxit = cg_maxit;
   c->solve_count = c->solve_iters = 0;
   c->solve_max_relres = 0.0;
-  int rc = general_upload(c, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val);
+  int rc = general_upload(c, c->n, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val);
   if (rc) return rc;
+  c->op_kind = 3;
+  return 0;
+}
+
+// The same problem with rows of A and B block-partitioned over the GPUs (world_size > 1).  A and B share one halo plan:
+// the caller remaps the columns of both matrices against the UNION of their remote columns (ga_set_csr_dist's layout).
+int ga_set_generalized_csr_dist(ga_ctx* c, const int64_t* a_rowptr, const int32_t* a_col_local, const void* a_val,
+                                const int64_t* b_rowptr, const int32_t* b_col_local, const void* b_val, const double* cg_tol,
+                                int cg_maxit, int32_t nhalo, const int32_t* recv_counts, const int32_t* send_counts,
+                                const int32_t* send_idx, const int32_t* send_dest_off) {
+  if (!c || !a_rowptr || !a_col_local || !a_val || !b_rowptr || !b_col_local || !b_val || cg_maxit < 0 || !recv_counts ||
+      !send_counts || nhalo < 0)
+    return GA_ERR_ARG;
+  GA_CUDA(c, cudaSetDevice(c->device));
+  if (c->world < 2) return set_err(c, GA_ERR_ARG, "single-GPU contexts take ga_set_generalized_csr");
+  if (c->dtype == GA_F32) return set_err(c, GA_ERR_ARG, "generalised problem: Float32 vectors are not supported (mode 1 / normal operator only)");
+  if (c->ipc_exported || c->devcomm) return set_err(c, GA_ERR_ARG, "the sharded operator cannot be replaced after ga_comm_ipc_export (peers hold the halo buffer's handle): create a new context");
+  int rc = validate_halo_plan(c, "ga_set_generalized_csr_dist", recv_counts, send_counts, send_idx);
+  if (rc) return rc;
+  clear_operator(c);
+  c->normal_dist = false;
+  c->cg_tol[0] = cg_tol ? cg_tol[0] : 0.0;
+  c->cg_tol[1] = 0.0;
+  c->cg_maxit = cg_maxit;
+  c->solve_count = c->solve_iters = 0;
+  c->solve_max_relres = 0.0;
+  if ((rc = general_upload(c, c->n_pad + nhalo, a_rowptr, a_col_local, a_val, b_rowptr, b_col_local, b_val))) return rc;
+  if ((rc = install_halo_plan(c, nhalo, recv_counts, send_counts, send_idx, send_dest_off))) return rc;
+  c->general_dist = true;
   c->op_kind = 3;
   return 0;
 }
@@ -587,6 +626,8 @@ int ga_bx(ga_ctx* c, const void* x_host, void* y_host) {
   GA_CUDA(c, cudaMemsetAsync(dy, 0, (size_t)c->n_pad * c->esize, c->stream));
   GA_CUDA(c, cudaMemcpyAsync(dx, x_host, (size_t)c->n * c->esize, cudaMemcpyHostToDevice, c->stream));
   int rc = general_bx(c, dx, dy);
+  // several GPUs: a reduction's mailbox exchange keeps the next halo push of any peer behind this product (k_general.cu)
+  if (rc == 0 && c->world > 1) rc = launch_dotc(c, dy, dy);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(y_host, dy, (size_t)c->n * c->esize, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

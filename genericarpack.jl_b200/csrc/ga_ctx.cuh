@@ -184,6 +184,7 @@ struct ga_ctx {
   std::vector<int> dest_off;     // where my entries start in each peer's halo
   // sharded normal operator OP = T^H T (rows of the tall T partitioned, see ga_set_normal_csr_dist)
   bool normal_dist = false;
+  bool general_dist = false;         // row-sharded generalised problem: A and Bm have the [own | halo] column layout
   ga::i64 mt_local = 0, mt_pad = 0;
   void* zp[2] = {nullptr, nullptr};   // partial results T_loc^H (T_loc x), inside the halo allocation (peer-readable)
   int* zinv = nullptr;                // [world][n_pad]: position of own row i in peer q's halo segment, or -1
@@ -247,7 +248,7 @@ int launch_zero_resid(ga_ctx* c);
 // k_spmv.cu
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated);  // y = OP x (device vectors)
 int spmv_autotune(ga_ctx* c, CsrDev& M, const void* x, void* y);  // time the streamed SpMV's configurations once
-int launch_push_halo(ga_ctx* c, const void* x);                   // fused multi-GPU path: x's halo entries -> the peers (k_vec.cu)
+int launch_push_halo(ga_ctx* c, const void* x, bool gated = false);                 // fused multi-GPU path: x's halo entries -> the peers (k_vec.cu)
 int launch_normal_half(ga_ctx* c, const void* x, void* y);       // y = A x or A^H x (svds post-processing)
 int csr_upload(ga_ctx* c, CsrDev& M, i64 nrows, i64 ncols, const int64_t* rowptr, const int32_t* col,
                const void* val, i64 col_shift);
@@ -257,13 +258,14 @@ int launch_decide(ga_ctx* c, int j, int gate_phase, int decide_kind);
 // k_gs_step.cu
 int launch_gs_step(ga_ctx* c, int j);
 // k_spmv.cu: y = M x for any uploaded CSR matrix (device vectors)
-int launch_spmv_mat(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated);
+int launch_spmv_mat(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo = false);
 // k_general.cu: generalised problem A x = lambda B x (mode 2, bmat = :G), host-driven scalar logic
-int general_upload(ga_ctx* c, const int64_t* arp, const int32_t* acol, const void* aval, const int64_t* brp,
+int general_upload(ga_ctx* c, i64 ncols, const int64_t* arp, const int32_t* acol, const void* aval, const int64_t* brp,
                    const int32_t* bcol, const void* bval);
 void general_free(ga_ctx* c);
 int general_opx(ga_ctx* c, const void* x, void* y, void* ax_out);   // y = inv(B) A x; ax_out (may be null) <- A x
 int general_bx(ga_ctx* c, const void* x, void* y);                  // y = B x
+int launch_dotc(ga_ctx* c, const void* a, const void* b);           // ctl->red[0..1] <- sum conj(a_i) b_i (all ranks)
 int general_getv0(ga_ctx* c, int64_t iseed[4], int initv, int j, double* rnorm);
 int general_lanczos(ga_ctx* c, int k, int np, void* H, int ldh, double* rnorm, int64_t iseed[4]);
 int general_resid_bnorm(ga_ctx* c, double* rnorm_out);              // sqrt|resid' B resid| (src/dsaup2.jl:1383-1411)

@@ -19,6 +19,14 @@
 // p = z + beta p.  The scalars stay on the device; the host enqueues batches of iterations and looks at the
 // control block once per batch; when the residual test passes the device parks the rest of the batch
 // (status ST_CG_DONE).  All reductions are fixed-order double-double sums (bit-reproducible).
+//
+// Several GPUs (ga_set_generalized_csr_dist): rows of A, B and of every vector are block-partitioned like the standard
+// problem, A and B share ONE halo plan (the union of their remote columns).  Every product pushes the operand's halo
+// entries into the peers' buffers (k_push_halo) and waits on their flags inside the SpMV; every reduction ends with the
+// mailbox exchange of the Gram-Schmidt sweeps (comm_exchange_slots), so all ranks hold bit-identical scalars, take the
+// same branches and park the same CG iterations.  Two products are always separated by at least one such exchange
+// (CG: (p,q) and (r,z); Lanczos: the B-norms and projections), which is what makes the single halo buffer safe: a
+// peer cannot push the next operand before this rank has finished reading the current one.  Peer-memory path only.
 #include "ga_decide.cuh"
 
 #include <chrono>
@@ -53,7 +61,7 @@ template <> struct DotAcc<ddbl> {
 // CTA-level fixed-order reduction of NS double-double accumulators into partial[cta][0..NS), then the
 // grid-level last-block reduction into ctl->red[0..NS).  Returns true in the last CTA.
 template <int NS>
-__device__ __forceinline__ bool reduce_slots(DevCtl* ctl, double2* partial, ddbl (&v)[NS]) {
+__device__ __forceinline__ bool reduce_slots(DevCtl* ctl, double2* partial, ddbl (&v)[NS], const DevComm* cm) {
   __shared__ double2 sw[8 * NS];
   __shared__ int sh_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,25 +76,27 @@ __device__ __forceinline__ bool reduce_slots(DevCtl* ctl, double2* partial, ddbl
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc = slot_add<false>(acc, sw[w * NS + threadIdx.x]);
     partial[(size_t)blockIdx.x * kMaxSlots + threadIdx.x] = acc;
   }
-  return last_block_reduce<false>(ctl, partial, 0, NS, &sh_flag);
+  const bool last = last_block_reduce<false>(ctl, partial, 0, NS, &sh_flag);
+  if (last && cm) comm_exchange_slots<false>(ctl, cm, 0, NS);   // several GPUs: ctl->red <- the world's sums, rank order
+  return last;
 }
 
 // ---- dot(a, b) = sum conj(a_i) b_i  ->  ctl->red[0] = Re (hi, lo), ctl->red[1] = Im (hi, lo) ------------------
 template <class T>
 __global__ void __launch_bounds__(256) k_dotc(const T* __restrict__ a, const T* __restrict__ b, i64 n, DevCtl* ctl,
-                                              double2* partial) {
+                                              double2* partial, const DevComm* cm) {
   if (ctl->status != ST_OK) return;
   ddbl v[2] = {ddbl(0.0, 0.0), ddbl(0.0, 0.0)};
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) DotAcc<T>::add(v[0], v[1], a[i], b[i]);
-  reduce_slots<2>(ctl, partial, v);
+  reduce_slots<2>(ctl, partial, v, cm);
 }
 
 // ---- conjugate gradients with B ----------------------------------------------------------------------------
 template <class T, class TR>
 __global__ void __launch_bounds__(256) k_cg_init(const T* __restrict__ b, T* __restrict__ x, T* __restrict__ r,
                                                  T* __restrict__ p, const TR* __restrict__ dinv, i64 n, DevCtl* ctl,
-                                                 double2* partial) {
+                                                 double2* partial, const DevComm* cm) {
   if (ctl->status != ST_OK) return;
   ddbl v[2] = {ddbl(0.0, 0.0), ddbl(0.0, 0.0)};   // (r, z), (b, b)
   ddbl unused(0.0, 0.0);
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(256) k_cg_init(const T* __restrict__ b, T* __r
     DotAcc<T>::add(v[0], unused, bi, zi);
     DotAcc<T>::add(v[1], unused, bi, bi);
   }
-  if (reduce_slots<2>(ctl, partial, v) && threadIdx.x == 0) {
+  if (reduce_slots<2>(ctl, partial, v, cm) && threadIdx.x == 0) {
     ctl->cg_rz[0] = ctl->red[0].x; ctl->cg_rz[1] = ctl->red[0].y;
     ctl->cg_bb[0] = ctl->red[1].x; ctl->cg_bb[1] = ctl->red[1].y;
     ctl->cg_rr[0] = ctl->red[1].x; ctl->cg_rr[1] = ctl->red[1].y;
@@ -111,13 +121,13 @@ __global__ void __launch_bounds__(256) k_cg_init(const T* __restrict__ b, T* __r
 
 template <class T>
 __global__ void __launch_bounds__(256) k_cg_pq(const T* __restrict__ p, const T* __restrict__ q, i64 n, DevCtl* ctl,
-                                               double2* partial) {
+                                               double2* partial, const DevComm* cm) {
   if (ctl->status != ST_OK) return;
   ddbl v[1] = {ddbl(0.0, 0.0)};
   ddbl unused(0.0, 0.0);
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) DotAcc<T>::add(v[0], unused, p[i], q[i]);
-  if (reduce_slots<1>(ctl, partial, v) && threadIdx.x == 0) {
+  if (reduce_slots<1>(ctl, partial, v, cm) && threadIdx.x == 0) {
     ctl->cg_pq[0] = ctl->red[0].x; ctl->cg_pq[1] = ctl->red[0].y;
     if (!(ctl->red[0].x > 0.0)) ctl->status = ST_NUMERIC;    // B is not positive definite (or p = 0)
   }
@@ -132,7 +142,7 @@ __device__ __forceinline__ void cg_store(double* p, ddbl v) { p[0] = v.hi; p[1] 
 template <class T, class TR>
 __global__ void __launch_bounds__(256) k_cg_update(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                    const T* __restrict__ q, const TR* __restrict__ dinv, i64 n,
-                                                   DevCtl* ctl, double2* partial) {
+                                                   DevCtl* ctl, double2* partial, const DevComm* cm) {
   if (ctl->status != ST_OK) return;
   const TR rz = cg_real<TR>(ctl->cg_rz), pq = cg_real<TR>(ctl->cg_pq);
   const TR alpha = rz / pq;
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(256) k_cg_update(T* __restrict__ x, T* __restr
     DotAcc<T>::add(v[0], unused, ri, zi);
     DotAcc<T>::add(v[1], unused, ri, ri);
   }
-  if (reduce_slots<2>(ctl, partial, v) && threadIdx.x == 0) {
+  if (reduce_slots<2>(ctl, partial, v, cm) && threadIdx.x == 0) {
     const TR rz_new = cg_real<TR>(reinterpret_cast<const double*>(&ctl->red[0]));
     cg_store(ctl->cg_beta, rz_new / rz);
     ctl->cg_rz[0] = ctl->red[0].x; ctl->cg_rz[1] = ctl->red[0].y;
@@ -185,6 +195,20 @@ static int vec_grid(const ga_ctx* c) {
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
+static const DevComm* gcm(const ga_ctx* c) { return c->world > 1 ? c->devcomm : nullptr; }
+static int need_peer_path(ga_ctx* c) {
+  if (c->world > 1 && !c->devcomm)
+    return set_err(c, GA_ERR_COMM, "generalised problem on several GPUs: the peer-memory path is required (ga_comm_ipc_export / ga_comm_ipc_import)");
+  return 0;
+}
+// y = M x for the (possibly row-sharded) A or B: on several GPUs the operand's halo entries are pushed first
+static int general_spmv(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) {
+  if (c->world <= 1) return launch_spmv_mat(c, M, x, y, gated);
+  int rc = need_peer_path(c);
+  if (rc) return rc;
+  if ((rc = launch_push_halo(c, x, gated))) return rc;
+  return launch_spmv_mat(c, M, x, y, gated, true);
+}
 static int set_status_ok(ga_ctx* c) {
   static const int zeros[4] = {0, 0, 0, 0};  // status, phase, j_break, rstart_j
   GA_CUDA(c, cudaMemcpyAsync(c->ctl, zeros, sizeof(zeros), cudaMemcpyHostToDevice, c->stream));
@@ -216,9 +240,9 @@ static bool h_pos(HReal a) { return a.hi > 0.0 || (a.hi == 0.0 && a.lo > 0.0); }
 int launch_dotc(ga_ctx* c, const void* a, const void* b) {
   const int grid = vec_grid(c);
   switch (c->dtype) {
-    case GA_F64: k_dotc<double><<<grid, 256, 0, c->stream>>>((const double*)a, (const double*)b, c->n, c->ctl, c->partial); break;
-    case GA_C64: k_dotc<cdbl><<<grid, 256, 0, c->stream>>>((const cdbl*)a, (const cdbl*)b, c->n, c->ctl, c->partial); break;
-    default: k_dotc<ddbl><<<grid, 256, 0, c->stream>>>((const ddbl*)a, (const ddbl*)b, c->n, c->ctl, c->partial); break;
+    case GA_F64: k_dotc<double><<<grid, 256, 0, c->stream>>>((const double*)a, (const double*)b, c->n, c->ctl, c->partial, gcm(c)); break;
+    case GA_C64: k_dotc<cdbl><<<grid, 256, 0, c->stream>>>((const cdbl*)a, (const cdbl*)b, c->n, c->ctl, c->partial, gcm(c)); break;
+    default: k_dotc<ddbl><<<grid, 256, 0, c->stream>>>((const ddbl*)a, (const ddbl*)b, c->n, c->ctl, c->partial, gcm(c)); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
@@ -249,9 +273,9 @@ static int cg_enqueue_iterations(ga_ctx* c, int count) {
   const TR* dinv = (const TR*)c->b_dinv;
   for (int k = 0; k < count; ++k) {
     int rc;
-    if ((rc = launch_spmv_mat(c, c->Bm, p, q, true))) return rc;
-    k_cg_pq<T><<<grid, 256, 0, c->stream>>>(p, q, n, c->ctl, c->partial);
-    k_cg_update<T, TR><<<grid, 256, 0, c->stream>>>(x, r, p, q, dinv, n, c->ctl, c->partial);
+    if ((rc = general_spmv(c, c->Bm, p, q, true))) return rc;
+    k_cg_pq<T><<<grid, 256, 0, c->stream>>>(p, q, n, c->ctl, c->partial, gcm(c));
+    k_cg_update<T, TR><<<grid, 256, 0, c->stream>>>(x, r, p, q, dinv, n, c->ctl, c->partial, gcm(c));
     k_cg_p<T, TR><<<grid, 256, 0, c->stream>>>(r, p, dinv, n, c->ctl);
     GA_CUDA(c, cudaGetLastError());
     c->launches += 3;
@@ -288,7 +312,7 @@ static int cg_solve_t(ga_ctx* c, const void* b, void* x) {
   double tol = c->cg_tol[0] > 0.0 ? c->cg_tol[0] : (c->dtype == GA_DD ? 8.0 * 4.930380657631324e-32 : 8.0 * 2.220446049250313e-16);
   const double tol2[2] = {tol * tol, 0.0};
   GA_CUDA(c, cudaMemcpyAsync(c->ctl->cg_tol2, tol2, sizeof(tol2), cudaMemcpyHostToDevice, c->stream));
-  k_cg_init<T, TR><<<grid, 256, 0, c->stream>>>((const T*)b, (T*)c->cg_x, r, p, dinv, n, c->ctl, c->partial);
+  k_cg_init<T, TR><<<grid, 256, 0, c->stream>>>((const T*)b, (T*)c->cg_x, r, p, dinv, n, c->ctl, c->partial, gcm(c));
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (!c->cg_graph_tried) cg_build_graph<T, TR>(c);
@@ -352,13 +376,14 @@ void general_free(ga_ctx* c) {
   c->gz = c->cg_r = c->cg_p = c->cg_q = c->cg_x = c->b_dinv = nullptr;
 }
 
-int general_upload(ga_ctx* c, const int64_t* arp, const int32_t* acol, const void* aval, const int64_t* brp,
+// ncols: n on one GPU; n_pad + nhalo for this rank's rows with the columns remapped to [own | halo] (ga_set_csr_dist)
+int general_upload(ga_ctx* c, i64 ncols, const int64_t* arp, const int32_t* acol, const void* aval, const int64_t* brp,
                    const int32_t* bcol, const void* bval) {
   general_free(c);
   const i64 n = c->n;
-  int rc = csr_upload(c, c->A, n, n, arp, acol, aval, 0);
+  int rc = csr_upload(c, c->A, n, ncols, arp, acol, aval, 0);
   if (rc) return rc;
-  if ((rc = csr_upload(c, c->Bm, n, n, brp, bcol, bval, 0))) return rc;
+  if ((rc = csr_upload(c, c->Bm, n, ncols, brp, bcol, bval, 0))) return rc;
   // Jacobi preconditioner: 1 / real(diag(B)); a non-positive diagonal entry means B is not positive definite
   const size_t rs = c->dtype == GA_DD ? 16 : 8;
   std::vector<double> dinv((size_t)c->n_pad * (rs / 8), 0.0);
@@ -401,7 +426,7 @@ int general_upload(ga_ctx* c, const int64_t* arp, const int32_t* acol, const voi
 // y = inv(B) (A x); ax_out (optional) receives A x, which genopx! leaves in place of x
 int general_opx(ga_ctx* c, const void* x, void* y, void* ax_out) {
   const double t0 = gnow();
-  int rc = launch_spmv_mat(c, c->A, x, c->gz, false);
+  int rc = general_spmv(c, c->A, x, c->gz, false);
   if (rc) return rc;
   if ((rc = general_solve(c, c->gz, y))) return rc;
   if (ax_out && ax_out != c->gz)
@@ -412,7 +437,7 @@ int general_opx(ga_ctx* c, const void* x, void* y, void* ax_out) {
 
 int general_bx(ga_ctx* c, const void* x, void* y) {
   const double t0 = gnow();
-  const int rc = launch_spmv_mat(c, c->Bm, x, y, false);
+  const int rc = general_spmv(c, c->Bm, x, y, false);
   c->stats.nbx += 1;
   c->stats.tmvbx += gnow() - t0;
   return rc;

@@ -298,6 +298,14 @@ static void spmv_read_env() {
   if (const char* e = getenv("GA_SPMV_GROUPS")) { const int v = atoi(e); if (v == 4 || v == 6) g_spmv_force_groups = v; }
 }
 
+// does M's column space have the sharded layout [own rows: n_pad | halo]?  (the sharded simple / normal operator's A, and
+// both matrices of the sharded generalised problem)
+static bool is_split(const ga_ctx* c, const CsrDev& M) {
+  if (c->world <= 1) return false;
+  if (c->general_dist) return &M == &c->A || &M == &c->Bm;
+  return &M == &c->A && (c->op_kind == 1 || c->normal_dist);
+}
+
 template <class T, int NG>
 static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, int nsplit,
                                 const DevComm* cm, int nst, bool accumulate) {
@@ -322,7 +330,7 @@ static int spmv_stream_launch_g(ga_ctx* c, const CsrDev& M, const void* x, void*
 template <class T>
 static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo, bool accumulate) {
   typedef SpmvStreamCfg<T> C;
-  const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
+  const bool split = is_split(c, M);
   const int nsplit = split ? (int)c->n_pad : 2147483647;
   const DevComm* cm = (split && wait_halo) ? c->devcomm : nullptr;
   spmv_read_env();
@@ -347,7 +355,7 @@ static int spmv_stream_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void*
 template <class T>
 static void spmv_launch_t(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo, bool accumulate) {
   if (M.nblk <= 0) return;
-  const bool split = c->world > 1 && &M == &c->A && (c->op_kind == 1 || c->normal_dist);
+  const bool split = is_split(c, M);
   k_spmv<T><<<M.nblk, SpmvCfg<T>::THREADS, 0, c->stream>>>(M.rowblk, M.rowptr, M.col, (const T*)M.val, (const T*)x,
                                                           (const T*)c->halo, split ? (int)c->n_pad : 2147483647,
                                                           (T*)y, c->ctl, gated ? 1 : 0,
@@ -373,7 +381,7 @@ static int spmv_launch(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool 
   return 0;
 }
 
-int launch_spmv_mat(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated) { return spmv_launch(c, M, x, y, gated); }
+int launch_spmv_mat(ga_ctx* c, const CsrDev& M, const void* x, void* y, bool gated, bool wait_halo) { return spmv_launch(c, M, x, y, gated, wait_halo); }
 
 // ---------------------------------------------------------------------------------------------
 // Sharded normal operator OP = T^H T: after z = T_loc^H (T_loc x) every rank owns a full-length
@@ -505,6 +513,7 @@ static int normal_wide(ga_ctx* c, const void* z, void* y, bool gated) {
 int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   if (c->op_kind == 0) return set_err(c, GA_ERR_NOOP, "no operator uploaded (ga_set_csr)");
   const void* xin = x;
+  if (c->op_kind == 3) return general_opx(c, xin, y, nullptr);   // moves its own halos (k_general.cu)
   // Lanczos steps (gated) on the fused path: the normalisation kernel already pushed the halo and
   // the SpMV waits on the peers' flags.  Otherwise the halo travels by NCCL send/recv first.
   const bool fused = gated && c->world > 1 && c->devcomm != nullptr;
@@ -514,7 +523,6 @@ int launch_opx(ga_ctx* c, const void* x, void* y, bool gated) {
   }
   if (c->op_kind == 1 && c->op_cb) return call_op_fn(c, c->op_cb, xin, y, c->n, c->n);
   if (c->op_kind == 1) return spmv_launch(c, c->A, xin, y, gated, fused);
-  if (c->op_kind == 3) return general_opx(c, xin, y, nullptr);
   if (c->normal_dist) return launch_normal_dist(c, xin, y, gated, fused);
   // normal operator (single GPU): left: y = A^H (A x); right: y = A (A^H x)
   if (c->normal_left) {

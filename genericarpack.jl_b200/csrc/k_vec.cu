@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) k_normalize(T* vj, const T* resid, i64 n,
 // (creating one costs seconds on 8 GPUs -- more than the whole C5 solve).
 template <class T>
 __global__ void __launch_bounds__(256) k_push_halo(const T* __restrict__ x, DevCtl* ctl, const DevComm* cm,
-                                                   const int* __restrict__ send_idx) {
+                                                   const int* __restrict__ send_idx, int gated) {
+  if (gated && ctl->status != ST_OK) return;   // parked (every rank sees the same status: the product that would wait is parked too)
   const unsigned int hseq = ctl->hseq + 1u;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   const int nsend = cm->send_off[cm->world];
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) k_push_halo(const T* __restrict__ x, DevC
   if (threadIdx.x == 0) { ctl->hseq = hseq; ctl->ticket = 0u; }
 }
 
-int launch_push_halo(ga_ctx* c, const void* x) {
+int launch_push_halo(ga_ctx* c, const void* x, bool gated) {
   if (c->world <= 1 || !c->devcomm) return set_err(c, GA_ERR_ARG, "halo push needs the fused multi-GPU path");
   const int threads = 256;
   i64 blocks = ((i64)c->nsend + threads - 1) / threads;
@@ -133,10 +134,10 @@ int launch_push_halo(ga_ctx* c, const void* x) {
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
   switch (c->dtype) {
-    case GA_F64: k_push_halo<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)x, c->ctl, c->devcomm, c->send_idx); break;
-    case GA_C64: k_push_halo<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)x, c->ctl, c->devcomm, c->send_idx); break;
-    case GA_F32: k_push_halo<float><<<(int)blocks, threads, 0, c->stream>>>((const float*)x, c->ctl, c->devcomm, c->send_idx); break;
-    default: k_push_halo<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)x, c->ctl, c->devcomm, c->send_idx); break;
+    case GA_F64: k_push_halo<double><<<(int)blocks, threads, 0, c->stream>>>((const double*)x, c->ctl, c->devcomm, c->send_idx, gated ? 1 : 0); break;
+    case GA_C64: k_push_halo<cdbl><<<(int)blocks, threads, 0, c->stream>>>((const cdbl*)x, c->ctl, c->devcomm, c->send_idx, gated ? 1 : 0); break;
+    case GA_F32: k_push_halo<float><<<(int)blocks, threads, 0, c->stream>>>((const float*)x, c->ctl, c->devcomm, c->send_idx, gated ? 1 : 0); break;
+    default: k_push_halo<ddbl><<<(int)blocks, threads, 0, c->stream>>>((const ddbl*)x, c->ctl, c->devcomm, c->send_idx, gated ? 1 : 0); break;
   }
   GA_CUDA(c, cudaGetLastError());
   c->launches += 1;

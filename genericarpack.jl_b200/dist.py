@@ -106,6 +106,33 @@ def shard_normal(A, rank, world, all_gather_object=None, dtype=None):
     return (rowptr, col, Tl.data, (t1 - t0, n)), plan, n, (t0, t1)
 
 
+def shard_generalized(A, B, rank, world, all_gather_object=None):
+    """Row sharding of the generalised problem A x = lambda B x (ArpackSymmetricGeneralizedOp): rank r owns a uniform
+    block of the rows of A and of B; both matrices share ONE halo plan, built from the union of their remote columns.
+    A, B: scipy sparse matrices (n x n).  Returns (rows_a, rows_b, plan, (r0, r1)) with rows_* = (rowptr int64,
+    col int32 global, val, (n_local, n)) and plan = halo_plan(...) whose "col_local" belongs to A's entries and
+    "col_local_b" to B's."""
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix(A); B = sp.csr_matrix(B)
+    n = A.shape[0]
+    if A.shape != (n, n) or B.shape != (n, n):
+        raise ValueError("A and B must be square matrices of the same size")
+    blk, parts = block_partition(n, world)
+    r0, r1 = parts[rank]
+    Al, Bl = A[r0:r1], B[r0:r1]
+    Al.sort_indices(); Bl.sort_indices()
+    ca = np.ascontiguousarray(Al.indices, dtype=np.int32)
+    cb = np.ascontiguousarray(Bl.indices, dtype=np.int32)
+    plan = halo_plan(np.concatenate([ca, cb]), n, rank, world, all_gather_object)
+    both = plan["col_local"]
+    plan["col_local"] = np.ascontiguousarray(both[: len(ca)])
+    plan["col_local_b"] = np.ascontiguousarray(both[len(ca):])
+    rows_a = (np.ascontiguousarray(Al.indptr, dtype=np.int64), ca, Al.data, (r1 - r0, n))
+    rows_b = (np.ascontiguousarray(Bl.indptr, dtype=np.int64), cb, Bl.data, (r1 - r0, n))
+    return rows_a, rows_b, plan, (r0, r1)
+
+
 def setup_comm(ctx, comm_unique_id, rank, world, fused=True):
     """Rendezvous for one context (torch.distributed must be initialised): broadcast the NCCL unique
     id, then (fused=True) all-gather the cudaIpc handles so that the per-step collectives run inside

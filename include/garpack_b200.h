@@ -156,11 +156,21 @@ int ga_set_normal_op_callbacks(ga_ctx* ctx, int64_t m, int64_t n, ga_op_fn av, g
  * src/dgetv0.jl:625-627,696-698, src/dsaup2.jl:1383-1411).  The reference's S is any factorisation object the
  * caller brings; here the solve with B is a Jacobi-preconditioned conjugate-gradient iteration on the device
  * (relative residual cg_tol, NULL -> 8 eps of the real type; at most cg_maxit iterations, 0 -> 1000), or the
- * caller's own solver on device pointers via ga_set_solve_callback.  Single GPU.  After this call
+ * caller's own solver on device pointers via ga_set_solve_callback.  One GPU (several: the _dist variant).  After this call
  * ga_getv0 / ga_lanczos / ga_apply_shifts / ga_symeigs* run mode 2; ga_opx applies inv(B) A. */
 int ga_set_generalized_csr(ga_ctx* ctx, const int64_t* a_rowptr, const int32_t* a_col, const void* a_val,
                            const int64_t* b_rowptr, const int32_t* b_col, const void* b_val,
                            const double* cg_tol, int cg_maxit);
+/* The same problem row-sharded over the GPUs of a multi-GPU context (world_size > 1): this rank's rows of A and of B
+ * with columns remapped as for ga_set_csr_dist against ONE halo plan shared by both matrices (the union of the remote
+ * columns A's and B's rows reference), then ga_comm_init / ga_comm_ipc_export / ga_comm_ipc_import as usual (this path
+ * needs the peer-memory mailboxes; there is no NCCL-only variant).  Every product pushes its operand's halo to the
+ * peers, every B-inner product and CG scalar is reduced over all GPUs inside the kernel that computes it, so all ranks
+ * take the same branches (two-GPU check: same restart count and counters as one GPU, tests/dist_gpu_check_general.py). */
+int ga_set_generalized_csr_dist(ga_ctx* ctx, const int64_t* a_rowptr, const int32_t* a_col_local, const void* a_val,
+                                const int64_t* b_rowptr, const int32_t* b_col_local, const void* b_val,
+                                const double* cg_tol, int cg_maxit, int32_t nhalo, const int32_t* recv_counts,
+                                const int32_t* send_counts, const int32_t* send_idx, const int32_t* send_dest_off);
 /* The S of ArpackSymmetricGeneralizedOp(A, S, B) as a callback: x_dev <- inv(B) rhs_dev, both device vectors of
  * n elements, work enqueued on `cuda_stream` (a cudaStream_t); return 0 on success.  NULL restores the built-in CG. */
 typedef int (*ga_solve_fn)(void* user, const void* rhs_dev, void* x_dev, int64_t n, void* cuda_stream);

@@ -180,3 +180,53 @@ def test_float32_blocks_are_padded_to_512_rows():
             assert plan["n_pad"] == pad and plan["nhalo"] == m
             remote = (cols[r] < parts[r][0]) | (cols[r] >= parts[r][1])
             assert np.all(plan["col_local"][remote] >= pad) and np.all(plan["col_local"][~remote] < blk)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_generalized_common_halo_plan(world):
+    """dist.shard_generalized: A and B share one halo plan (the union of their remote columns).  Emulate the exchange
+    serially: every rank's halo = the entries the owners' send lists deliver, and the [own | halo] products of both
+    matrices must reproduce A x and B x."""
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    import scipy.sparse as sp
+
+    import __graft_entry__ as entry
+
+    entry.load_package()
+    gd = importlib.import_module(entry.PKG_NAME + ".dist")
+    syn = importlib.import_module(entry.PKG_NAME + ".synthetic")
+    m = 23
+    A = syn.to_scipy(syn.laplacian2d(m))
+    n = m * m
+    rng = np.random.default_rng(5)
+    E = sp.random(n, n, density=3.0 / n, random_state=7, format="csr")
+    B = (sp.identity(n) * 4.0 + 0.1 * (E + E.T)).tocsr()          # a different pattern than A's: the union matters
+    blk, parts = gd.block_partition(n, world)
+    needs = []
+    for r in range(world):
+        r0, r1 = parts[r]
+        cols = np.concatenate([A[r0:r1].indices, B[r0:r1].indices])
+        needs.append(gd.local_need(cols, r0, r1))
+    out = [gd.shard_generalized(A, B, r, world, all_gather_object=lambda obj: needs) for r in range(world)]
+    x = rng.standard_normal(n)
+    for r in range(world):
+        ra, rb, plan, (r0, r1) = out[r]
+        assert (r0, r1) == parts[r] and ra[3] == rb[3] == (r1 - r0, n)
+        assert len(plan["col_local"]) == len(ra[1]) and len(plan["col_local_b"]) == len(rb[1])
+        # what the peers deliver, owner by owner, in the order of their send lists for this rank
+        halo = []
+        for q in range(world):
+            pq = out[q][2]
+            off = int(np.sum(pq["send_counts"][:r]))
+            idx = pq["send_idx"][off: off + int(pq["send_counts"][r])]
+            assert int(pq["send_dest_off"][r]) == sum(len(h) for h in halo)
+            halo.append(x[parts[q][0] + idx])
+        halo = np.concatenate(halo)
+        assert len(halo) == plan["nhalo"] and np.array_equal(halo, x[plan["need"]])
+        xext = np.concatenate([x[r0:r1], np.zeros(plan["n_pad"] - (r1 - r0)), halo])
+        for (rowptr, col, val, _), cl, M in ((ra, plan["col_local"], A), (rb, plan["col_local_b"], B)):
+            y = np.zeros(r1 - r0)
+            np.add.at(y, np.repeat(np.arange(r1 - r0), np.diff(rowptr)), val * xext[cl])
+            assert np.allclose(y, (M @ x)[r0:r1], rtol=1e-14, atol=1e-14)

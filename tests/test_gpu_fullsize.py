@@ -41,7 +41,7 @@ def test_c5_svds_full_size_one_gpu(pkg, syn):
           % (t_gen, t_svds, S[0], S[-1]))
 
 
-@pytest.mark.parametrize("script,args", [("dist_gpu_check.py", ["300"]), ("dist_gpu_check_normal.py", []), ("dist_gpu_check_f32.py", [])])
+@pytest.mark.parametrize("script,args", [("dist_gpu_check.py", ["300"]), ("dist_gpu_check_normal.py", []), ("dist_gpu_check_f32.py", []), ("dist_gpu_check_general.py", [])])
 def test_two_gpu_parity_under_torchrun(script, args):
     """The row-sharded path (halo exchange + fused peer-memory slot reduction) against the single-GPU path and the oracle:
     tests/dist_gpu_check*.py under torchrun with two ranks.  Needs two visible GPUs (skipped on a one-GPU box; bench.py's

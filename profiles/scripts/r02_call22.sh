@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, call 22: two consumer sets for the 1 KiB-segment step kernel (wide bases, j >= 33): A/B per j, then tests + bench with it on.
+# Round 2, call 22 (experiment, reverted: see profiles/r02/README.md section 17 and experiments/two_sets_1k_segments.diff; the GA_GS_TWO_SETS_1K switch exists only with that diff applied): two consumer sets for the 1 KiB-segment step kernel (wide bases, j >= 33): A/B per j, then tests + bench with it on.
 set -u
 mkdir -p gpurun_out/r02
 OUT=gpurun_out/r02

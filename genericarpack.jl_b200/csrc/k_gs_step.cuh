@@ -375,7 +375,11 @@ k_gs_step(const T* __restrict__ V, i64 ldv, int j, T* wr, i64 ntiles, DevCtl* ct
       // partial sums in order.  redw (the CTA's own scratch) is free at this point.
       constexpr int SUB = 12;
       const unsigned int G = gridDim.x;
-      double2* scratch = reinterpret_cast<double2*>(pr);   // >= 1024 slots, idle between the phases
+      // (j + 3) * SUB slots of 16 bytes = at most 12.6 KiB.  pr is idle between the phases; with 1 KiB segments of 8-byte
+      // elements it is only 8 KiB and the tail runs on into redw, which lies directly behind it and is idle as well (its
+      // values went into `partial` before the barrier above): pr + redw >= 12.75 KiB for every element type.
+      double2* scratch = reinterpret_cast<double2*>(pr);
+      static_assert((size_t)2 * TG * SEGB + (size_t)CWARPS * (NC + 3) * 16 >= (size_t)(kMaxNcv + 3) * SUB * 16, "scratch of the CTA-0 reduction");
       for (int idx = tid; idx < nslots * SUB; idx += blockDim.x) {
         const int s = idx / SUB, u = idx % SUB;
         const bool cplx = CPLX && s < j;

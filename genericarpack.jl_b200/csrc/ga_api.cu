@@ -281,14 +281,9 @@ int ga_set_csr(ga_ctx* c, const int64_t* rowptr, const int32_t* col, const void*
   return rc;
 }
 
-// Row-sharded operator: this rank's rows with columns already remapped by the caller:
-//   own column g (row0 <= g < row0 + n_local)  ->  g - row0
-//   remote column                               ->  n_pad + position in the halo
-// where the halo lists the needed remote columns in ascending global order (= grouped by owner
-// rank), recv_counts[q] of them owned by rank q; send_idx (grouped by destination rank, send_counts[q]
-// each) are the LOCAL row indices whose x entries rank q needs from this rank.
+// The halo plan of a row-sharded operator (ga_set_csr_dist, ga_set_generalized_csr_dist) indexes device memory directly.
 static int validate_halo_plan(ga_ctx* c, const char* who, const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx) {
-  int ns = 0;   // the plan indexes device memory directly: validate it here
+  int ns = 0;
   for (int q = 0; q < c->world; ++q) {
     if (send_counts[q] < 0 || recv_counts[q] < 0) return set_err(c, GA_ERR_ARG, std::string(who) + ": negative count in the halo plan");
     ns += send_counts[q];
@@ -318,6 +313,12 @@ static int install_halo_plan(ga_ctx* c, int32_t nhalo, const int32_t* recv_count
   return 0;
 }
 
+// Row-sharded operator: this rank's rows with columns already remapped by the caller:
+//   own column g (row0 <= g < row0 + n_local)  ->  g - row0
+//   remote column                               ->  n_pad + position in the halo
+// where the halo lists the needed remote columns in ascending global order (= grouped by owner
+// rank), recv_counts[q] of them owned by rank q; send_idx (grouped by destination rank, send_counts[q]
+// each) are the LOCAL row indices whose x entries rank q needs from this rank.
 int ga_set_csr_dist(ga_ctx* c, const int64_t* rowptr, const int32_t* col_local, const void* val, int32_t nhalo,
                     const int32_t* recv_counts, const int32_t* send_counts, const int32_t* send_idx,
                     const int32_t* send_dest_off) {

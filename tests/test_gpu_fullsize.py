@@ -55,6 +55,6 @@ def test_two_gpu_parity_under_torchrun(script, args):
         pytest.skip("needs two GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(here, script)] + args
+           "--master-port", str(29533 + sum(map(ord, script)) % 40), os.path.join(here, script)] + args   # one port per script
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-2000:])
